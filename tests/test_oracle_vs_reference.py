@@ -1,0 +1,107 @@
+"""Pins oracle/generator_oracle.py against the unmodified reference imported from
+/root/reference (build container only; skipped on the GPU box, where the committed
+tests/golden fixtures made by oracle/make_golden.py take over)."""
+import os
+import sys
+
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..'))
+from oracle import ref_shim, generator_oracle as GO          # noqa: E402
+from vid2vid_b200.utils import make_opt, det_fill_, synth_label_sequence   # noqa: E402
+
+pytestmark = pytest.mark.skipif(not ref_shim.available(), reason='reference tree not mounted')
+
+
+def _close(a, b, tol=2e-5):
+    assert a.shape == b.shape
+    assert (a - b).abs().max().item() <= tol, (a - b).abs().max().item()
+
+
+def _inputs(nc, h, w, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    lab = synth_label_sequence(3, h, w, label_nc=nc - 1, block=4, seed=seed)
+    real_A = GO.encode_input(lab, lab, nc - 1, True)
+    inp = real_A.view(1, -1, h, w)
+    img_prev = torch.rand(1, 6, h, w, generator=g) * 2 - 1
+    mask = (lab[:, -1] == 2).float()
+    return inp, img_prev, mask
+
+
+@pytest.mark.parametrize('fg,no_flow,nd', [(True, False, 3), (False, False, 2), (True, True, 3)])
+def test_composite_generator(fg, no_flow, nd):
+    N = ref_shim.networks()
+    opt = make_opt(ngf=8, n_blocks=3, fg=fg, no_flow=no_flow, n_downsample_G=nd, gpu_ids=[])
+    net = det_fill_(N.define_G(18, 3, 6, 8, 'composite', nd, 'batch', 0, [], opt), seed=1)
+    inp, img_prev, mask = _inputs(6, 16, 32)
+    with torch.no_grad():
+        ref = net(inp, img_prev, mask, None, None, None, False)
+        out = GO.composite_generator(net.state_dict(), inp, img_prev, mask, False, n_downsampling=nd,
+                                     n_blocks=3, use_fg_model=fg, no_flow=no_flow)
+    for r, o in zip(ref, out):
+        if r is None:
+            assert o is None
+        else:
+            _close(r, o)
+
+
+def test_composite_local_generator():
+    N = ref_shim.networks()
+    opt = make_opt(ngf=8, n_blocks_local=2, fg=True, gpu_ids=[])
+    net = det_fill_(N.define_G(18, 3, 6, 4, 'compositeLocal', 3, 'batch', 1, [], opt), seed=2)
+    inp, img_prev, mask = _inputs(6, 16, 32)
+    g = torch.Generator().manual_seed(5)
+    c1, c2, c3 = (torch.randn(1, c, 8, 16, generator=g) for c in (8, 8, 4))
+    with torch.no_grad():
+        ref = net(inp, img_prev, mask, c1, c2, c3, False)
+        out = GO.composite_local_generator(net.state_dict(), inp, img_prev, mask, c1, c2, c3, False,
+                                           n_blocks_local=2, scale=1)
+    for r, o in zip(ref, out):
+        _close(r, o)
+
+
+def test_single_image_generators():
+    N = ref_shim.networks()
+    opt = make_opt(n_blocks=2, n_blocks_local=2, gpu_ids=[])
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(1, 5, 32, 64, generator=g)
+    netg = det_fill_(N.define_G(5, 3, 0, 8, 'global', 2, 'instance', 0, [], opt), seed=3)
+    netl = det_fill_(N.define_G(5, 3, 0, 4, 'local', 2, 'instance', 0, [], opt), seed=4)
+    with torch.no_grad():
+        _close(netg(x), GO.global_generator(netg.state_dict(), x, n_downsampling=2, n_blocks=2))
+        _close(netl(x), GO.local_enhancer(netl.state_dict(), x, n_downsample_global=2, n_blocks_global=2,
+                                          n_blocks_local=2))
+
+
+def test_discriminator():
+    N = ref_shim.networks()
+    net = det_fill_(N.define_D(9, 8, 3, 'batch', 2, True, []), seed=5)
+    g = torch.Generator().manual_seed(6)
+    x = torch.randn(2, 9, 32, 48, generator=g)
+    with torch.no_grad():
+        ref = net(x)
+        out = GO.multiscale_discriminator(net.state_dict(), x, num_D=2, n_layers=3)
+    for rt, ot in zip(ref, out):
+        for r, o in zip(rt, ot):
+            _close(r, o)
+
+
+def test_model_G_inference_multiscale():
+    N = ref_shim.networks()
+    opt = make_opt(label_nc=5, use_instance=True, fg=True, fg_labels=[2], n_scales_spatial=2, ngf=8,
+                   n_blocks=2, n_blocks_local=1, use_single_G=True, n_downsample_G=2, gpu_ids=[],
+                   dataroot='City')
+    single = det_fill_(N.define_G(5, 3, 0, 8, 'global', 2, 'instance', 0, [], opt), seed=9)
+    m = ref_shim.make_model_G(opt, single)
+    det_fill_(m.netG0, seed=10)
+    det_fill_(m.netG1, seed=11)
+    orc = GO.ModelGOracle(opt, [m.netG0.state_dict(), m.netG1.state_dict()], single.state_dict(),
+                          'global', 2)
+    seq = synth_label_sequence(5, 32, 64, label_nc=5, block=4, seed=3)
+    for t in range(3):
+        A = seq[:, t:t + 3]
+        ref_B, ref_A = m.inference(A, None, A)
+        o_B, o_A = orc.inference(A, A)
+        _close(ref_B, o_B)
+        _close(ref_A, o_A)
