@@ -1,0 +1,173 @@
+/* vid2vid-b200 -- C ABI of the sm_100a frame-synthesis engine (libv2v_b200.so).
+ *
+ * Plain pointers and sizes only: no torch / ATen types cross this boundary.  Every function returns
+ * 0 on success and a non-zero code on failure (cudaError_t value, or V2V_ERR_* below);
+ * v2v_last_error() returns a human-readable message for the calling thread.  Nothing here allocates
+ * caller-visible memory: callers own all input / output tensors (the reference's Python Functions
+ * allocate outputs the same way: resample2d.py:17, channelnorm.py:11, correlation.py:22-24).  All work
+ * is enqueued on the cudaStream_t the caller passes (the reference enqueues on
+ * at::cuda::getCurrentCUDAStream(), correlation_cuda.cc:76) and is re-entrant across plans.
+ *
+ * Two groups of entry points:
+ *  (1) stand-alone operators -- one per native op of the reference's pybind11 extensions (b1 in
+ *      SURVEY.md 8b) and per HBM-bound helper of the model layer;
+ *  (2) the plan runtime -- the nn.Module surface (b2): Python describes a generator / discriminator
+ *      once as a graph of logical values and convolution units; the runtime lowers it to halo-padded
+ *      NHWC bf16 buffers, TMA tensor maps, packed weights and a kernel sequence captured in a CUDA
+ *      graph, and runs it per frame against caller-owned fp32 NCHW tensors.
+ */
+#ifndef V2V_B200_H
+#define V2V_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* v2v_stream_t; /* == cudaStream_t */
+typedef struct v2v_plan v2v_plan;
+
+#define V2V_ERR_INVALID 10001
+#define V2V_ERR_STATE 10002
+#define V2V_ERR_UNSUPPORTED 10003
+
+enum { V2V_PAD_NONE = 0, V2V_PAD_ZERO = 1, V2V_PAD_REFLECT = 2 };
+enum { V2V_ACT_NONE = 0, V2V_ACT_RELU = 1, V2V_ACT_LRELU = 2, V2V_ACT_TANH = 3, V2V_ACT_SIGMOID = 4 };
+enum { V2V_NORM_NONE = 0, V2V_NORM_BATCH = 1, V2V_NORM_INSTANCE = 2 };
+enum { V2V_IMPL_UMMA = 0, V2V_IMPL_SIMT = 1 };
+
+int v2v_version(void);
+const char* v2v_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * (1) Stand-alone operators.  All tensors fp32, contiguous NCHW, on the current device.
+ * ---------------------------------------------------------------------------------------------- */
+
+/* correlation_cuda.forward (correlation_cuda.cc:10-87; kernel correlation_cuda_kernel.cu:73-147).
+ * in1,in2 (N,C,H,W) -> out (N, D*D, outH, outW), D = 2*(max_disp/stride2)+1; shapes via
+ * v2v_correlation_out_shape.  kernel_size must be 1 (the only value FlowNetC uses, FlowNetC.py:31).
+ * The reference's rbot1/rbot2 scratch tensors are not needed. */
+int v2v_correlation_out_shape(int H, int W, int pad_size, int kernel_size, int max_displacement, int stride1,
+                              int stride2, int* outC, int* outH, int* outW);
+int v2v_correlation_forward(const float* in1, const float* in2, float* out, int N, int C, int H, int W, int pad_size,
+                            int kernel_size, int max_displacement, int stride1, int stride2, int corr_type_multiply,
+                            v2v_stream_t stream);
+
+/* resample2d_cuda.forward (resample2d_cuda.cc:6-13; kernel resample2d_kernel.cu:15-64).
+ * in1 (N,C,inH,inW), flow (N,2,H,W) -> out (N,C,H,W); kernel_size must be 1. */
+int v2v_resample2d_forward(const float* in1, const float* flow, float* out, int N, int C, int H, int W, int inH,
+                           int inW, int kernel_size, v2v_stream_t stream);
+
+/* channelnorm_cuda.forward (channelnorm_cuda.cc:6-13; kernel channelnorm_kernel.cu:18-60).
+ * in (N,C,H,W) -> out (N,1,H,W) = sqrt(sum_c in^2); norm_deg must be 2. */
+int v2v_channelnorm_forward(const float* in, float* out, int N, int C, int H, int W, int norm_deg,
+                            v2v_stream_t stream);
+
+/* BaseNetwork.resample / BaseModel.resample (models/networks.py:102-115, models/base_model.py:183-196):
+ * grid_sample(image, linspace grid + flow/((dim-1)/2), bilinear, border).  image (N,C,H,W),
+ * flow (N,2,H,W) in pixels.  align_corners: 0 = installed-PyTorch default, 1 = PyTorch-0.4 semantics. */
+int v2v_resample_forward(const float* image, const float* flow, float* out, int N, int C, int H, int W,
+                         int align_corners, v2v_stream_t stream);
+
+/* Vid2VidModelG.encode_input + BaseModel.get_edges (models/vid2vid_model_G.py:86-112,
+ * models/base_model.py:146-152).  labels, inst: (F,H,W) float ids (F = batch*frames; inst may be NULL
+ * when use_instance == 0) -> out (F, label_nc + use_instance, H, W). */
+int v2v_onehot_edges(const float* labels, const float* inst, float* out, int F, int label_nc, int use_instance, int H,
+                     int W, v2v_stream_t stream);
+
+/* AvgPool2d(3, stride=2, padding=1, count_include_pad=False) on P planes (BaseModel.build_pyr,
+ * models/base_model.py:122-134): in (P,H,W) -> out (P,(H-1)/2+1,(W-1)/2+1). */
+int v2v_avgpool3s2(const float* in, float* out, int P, int H, int W, v2v_stream_t stream);
+
+/* Vid2VidModelG.compute_mask (models/vid2vid_model_G.py:322-330): real_A (B,T,C,H,W), frame t ->
+ * mask (B,1,H,W) = clamp(sum over fg_labels of real_A[:, t, label], 0, 1).  n_labels <= 16. */
+int v2v_fg_mask(const float* real_A, float* mask, int B, int T, int C, int H, int W, int t, const int* fg_labels,
+                int n_labels, v2v_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * (2) Plan runtime.
+ *
+ * A plan is built once per (module, input shape): create -> describe (g_* calls, in execution order)
+ * -> finalize -> run per frame.  "values" are logical NHWC activations identified by small ints;
+ * "raws" are un-normalised convolution outputs.  Caller tensors are addressed by IO slot: the
+ * pointers are supplied at run time (v2v_plan_run), so PyTorch may hand over new tensors each call.
+ * Parameter pointers (weights, biases, norm affine / running stats) are device pointers to the
+ * caller's fp32 tensors in PyTorch layout; they are read when weights are (re)packed
+ * (finalize / v2v_plan_repack) and, for norm parameters, at run time.
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct v2v_conv_desc {
+  int Cin, Cout, kh, kw;
+  int stride;          /* 1 or 2 */
+  int pad;             /* padding of the convolution (the ReflectionPad2d amount when pad_mode is reflect) */
+  int pad_mode;        /* V2V_PAD_ZERO / V2V_PAD_REFLECT */
+  int transposed;      /* 1: nn.ConvTranspose2d(stride 2) with `pad` and `output_padding` */
+  int output_padding;
+  const float* weight; /* conv: [Cout][Cin][kh][kw]; transposed: [Cin][Cout][kh][kw] */
+  const float* bias;   /* [Cout] or NULL */
+} v2v_conv_desc;
+
+typedef struct v2v_norm_desc {
+  int kind;                      /* V2V_NORM_* ; statistics are always those of the current tensor (train mode) */
+  const float* gamma;            /* [C] or NULL */
+  const float* beta;             /* [C] or NULL */
+  float* running_mean;           /* [C] or NULL: updated as nn.BatchNorm2d does in train mode */
+  float* running_var;
+  int64_t* num_batches_tracked;  /* or NULL */
+  float momentum, eps;
+} v2v_norm_desc;
+
+typedef struct v2v_head_channel {
+  int slot;        /* IO slot of the destination fp32 NCHW tensor */
+  int channel;     /* destination channel index */
+  int dst_C;       /* channel count of the destination tensor */
+  int act;         /* V2V_ACT_* applied after bias */
+  float scale;     /* multiplied after the activation (flow head: 20 * 2^scale) */
+} v2v_head_channel;
+
+int v2v_plan_create(int device, int conv_impl /* V2V_IMPL_* */, v2v_plan** out);
+int v2v_plan_destroy(v2v_plan* plan);
+
+/* Channels [c_off, c_off + C) of the fp32 NCHW tensor (N, C_src, H, W) bound to IO slot `slot`. */
+int v2v_g_input(v2v_plan* plan, int slot, int N, int C_src, int c_off, int C, int H, int W, int* value_out);
+/* Convolution of a value; result is a raw (pre-norm) tensor. */
+int v2v_g_conv(v2v_plan* plan, int value_in, const v2v_conv_desc* conv, int* raw_out);
+/* value = act(norm(raw)) + add0 + add1   (add ids may be -1).  Conv bias is folded into running_mean only. */
+int v2v_g_norm_act(v2v_plan* plan, int raw_in, const v2v_norm_desc* norm, int act, float slope, int add0, int add1,
+                   int* value_out);
+/* value = act(conv(value_in) + bias)   (layers without normalisation) */
+int v2v_g_conv_act(v2v_plan* plan, int value_in, const v2v_conv_desc* conv, int act, float slope, int* value_out);
+/* Small-Cout head (Cout <= 16): per channel bias + activation + scale -> fp32 NCHW planes of caller tensors. */
+int v2v_g_head(v2v_plan* plan, int value_in, const v2v_conv_desc* conv, const v2v_head_channel* channels);
+/* Export a value as fp32 NCHW into the caller tensor bound to `slot`. */
+int v2v_g_export(v2v_plan* plan, int value, int slot);
+/* Fused warp / blend / fg composite on caller tensors (slots; -1 = absent).  s_raw is read (head output)
+ * and, with a fg model, overwritten with the composited raw image; s_final is written. */
+int v2v_g_composite(v2v_plan* plan, int s_raw, int s_flow, int s_weight, int s_prev, int prev_C, int s_fg, int s_mask,
+                    int s_final, int N, int H, int W, int use_warp, int align_corners);
+
+int v2v_plan_finalize(v2v_plan* plan, v2v_stream_t stream);
+/* Re-read all weight pointers and repack (after an optimiser step / load_state_dict). */
+int v2v_plan_repack(v2v_plan* plan, v2v_stream_t stream);
+/* Run once.  io_ptrs[slot] = device pointer of the caller tensor bound to that slot. */
+int v2v_plan_run(v2v_plan* plan, void* const* io_ptrs, int n_io, int use_graph, v2v_stream_t stream);
+
+/* Introspection (host logic tests, bench accounting). */
+int v2v_plan_num_kernels(const v2v_plan* plan);             /* kernels launched per run */
+double v2v_plan_conv_macs(const v2v_plan* plan);            /* algorithmic conv MACs per run (dense, unpadded) */
+int64_t v2v_plan_workspace_bytes(const v2v_plan* plan);
+/* Writes a JSON description of the lowered plan (buffers, tiles, tap groups) into buf; returns needed size. */
+int64_t v2v_plan_describe(const v2v_plan* plan, char* buf, int64_t cap);
+
+/* Host-only: the tap-group table the kernel would use for a convolution (pure function; no GPU).
+ * Each group g: plane[g], dy[g], dx[g], tap0[g]; R taps per group; phase p covers groups
+ * [phase_begin[p], phase_begin[p+1]); per-phase output offsets oy_add/ox_add; buffer padding pads[4] =
+ * {top, left, bottom, right}; parity; grid_h/grid_w; out_h/out_w.  Arrays must hold 64 / 5 / 4 entries. */
+int v2v_conv_tap_table(const v2v_conv_desc* conv, int H, int W, int allow_reuse, int* n_groups, int* R, int* plane,
+                       int* dy, int* dx, int* tap0, int* n_phases, int* phase_begin, int* oy_add, int* ox_add,
+                       int* pads, int* parity, int* grid_hw, int* out_hw, int* mul);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* V2V_B200_H */

@@ -1,0 +1,157 @@
+"""CPU-only checks of the host side: C-ABI surface, conv lowering (tap groups / padding / parity /
+transposed phases) emulated in numpy against torch convolutions, algorithmic MAC counts against
+BASELINE.md, and state_dict compatibility with the reference.  No compute call touches a GPU."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import cases
+from vid2vid_b200 import _lib as L
+from vid2vid_b200 import networks as NW
+from vid2vid_b200.utils import make_opt
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'v2v_b200.h')).read()
+    declared = set(re.findall(r'\b(v2v_[a-z0-9_]+)\s*\(', hdr))
+    lib = L.lib()
+    for name in declared:
+        assert hasattr(lib, name), 'symbol %s declared in include/v2v_b200.h is not exported' % name
+    assert declared == set(L.SYMBOLS), declared ^ set(L.SYMBOLS)
+    assert lib.v2v_version() >= 100
+
+
+def _tap_table(desc, H, W, reuse):
+    ia = lambda n: (C.c_int * n)()
+    ng, R, nph, par, mul = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    plane, dy, dx, tap0 = ia(64), ia(64), ia(64), ia(64)
+    pb, oya, oxa, pads, ghw, ohw = ia(5), ia(4), ia(4), ia(4), ia(2), ia(2)
+    L.check(L.lib().v2v_conv_tap_table(C.byref(desc), H, W, int(reuse), C.byref(ng), C.byref(R), plane, dy, dx, tap0,
+                                       C.byref(nph), pb, oya, oxa, pads, C.byref(par), ghw, ohw, C.byref(mul)))
+    return dict(groups=[(plane[i], dy[i], dx[i], tap0[i]) for i in range(ng.value)], R=R.value,
+                phases=[(pb[i], pb[i + 1], oya[i], oxa[i]) for i in range(nph.value)], pads=list(pads), parity=par.value,
+                grid=tuple(ghw), out=tuple(ohw), mul=mul.value)
+
+
+def _emulate(x, w, t, kh, kw, transposed, reflect):
+    """What the kernel computes from a tap table: x (C,H,W), w torch-layout weights."""
+    Cin, H, W = x.shape
+    pt, pl, pb, pr = t['pads']
+    xp = np.pad(x, ((0, 0), (pt, pb), (pl, pr)), mode='reflect' if reflect else 'constant')
+    if t['parity']:
+        Hp, Wp = (xp.shape[1] + 1) // 2, (xp.shape[2] + 1) // 2
+        planes = np.zeros((4, Cin, Hp + 8, Wp + 8), np.float64)
+        for py in range(2):
+            for px in range(2):
+                s = xp[:, py::2, px::2]
+                planes[py * 2 + px, :, :s.shape[1], :s.shape[2]] = s
+    else:
+        planes = np.zeros((1, Cin, xp.shape[1] + 8, xp.shape[2] + 8), np.float64)
+        planes[0, :, :xp.shape[1], :xp.shape[2]] = xp
+    Cout = w.shape[1] if transposed else w.shape[0]
+    gh, gw = t['grid']
+    out = np.zeros((Cout, t['out'][0], t['out'][1]))
+    for (b, e, oya, oxa) in t['phases']:
+        acc = np.zeros((Cout, gh, gw))
+        for (plane, dy, dx, tap0) in t['groups'][b:e]:
+            for r in range(t['R']):
+                ky, kx = divmod(tap0 + r, kw)
+                a = planes[plane, :, dy:dy + gh, dx + r:dx + r + gw]
+                wk = w[:, :, ky, kx].T if transposed else w[:, :, ky, kx]      # (Cout, Cin)
+                acc += np.einsum('oc,chw->ohw', wk, a)
+        out[:, oya::t['mul'], oxa::t['mul']] = acc
+    return out
+
+
+@pytest.mark.parametrize('kh,stride,pad,reflect,transposed,op,H,W,reuse', [
+    (3, 1, 1, True, False, 0, 6, 10, True),
+    (3, 1, 1, True, False, 0, 5, 130, True),     # row tiles: taps served from one patch (R = 3)
+    (7, 1, 3, True, False, 0, 9, 140, True),     # R = 7
+    (7, 1, 3, True, False, 0, 9, 140, False),
+    (3, 2, 1, False, False, 0, 8, 12, True),
+    (3, 2, 1, False, False, 0, 7, 9, True),      # odd extents
+    (4, 2, 2, False, False, 0, 8, 10, True),     # discriminator
+    (4, 1, 2, False, False, 0, 5, 6, True),
+    (5, 2, 2, False, False, 0, 8, 8, True),      # FlowNet2
+    (1, 1, 0, False, False, 0, 4, 4, True),
+    (3, 2, 1, False, True, 1, 5, 7, True),       # generator deconv
+    (4, 2, 1, False, True, 0, 4, 6, True),       # FlowNet2 deconv
+])
+def test_tap_table_matches_torch_conv(kh, stride, pad, reflect, transposed, op, H, W, reuse):
+    g = torch.Generator().manual_seed(kh * 100 + stride * 10 + pad)
+    Cin, Cout = 3, 4
+    x = torch.randn(1, Cin, H, W, generator=g, dtype=torch.float64)
+    d = L.ConvDesc()
+    d.Cin, d.Cout, d.kh, d.kw, d.stride, d.pad = Cin, Cout, kh, kh, stride, pad
+    d.pad_mode = L.PAD_REFLECT if reflect else L.PAD_ZERO
+    d.transposed, d.output_padding = int(transposed), op
+    t = _tap_table(d, H, W, reuse)
+    if transposed:
+        w = torch.randn(Cin, Cout, kh, kh, generator=g, dtype=torch.float64)
+        ref = F.conv_transpose2d(x, w, stride=stride, padding=pad, output_padding=op)
+    else:
+        w = torch.randn(Cout, Cin, kh, kh, generator=g, dtype=torch.float64)
+        xin = F.pad(x, (pad,) * 4, mode='reflect') if reflect else x
+        ref = F.conv2d(xin, w, stride=stride, padding=0 if reflect else pad)
+    assert tuple(ref.shape[2:]) == t['out']
+    if reuse and not transposed and stride == 1 and W > 64 and kh > 1:
+        assert t['R'] == kh
+    out = _emulate(x[0].numpy(), w.numpy(), t, kh, kh, transposed, reflect)
+    np.testing.assert_allclose(out, ref[0].numpy(), rtol=1e-10, atol=1e-10)
+
+
+# ---- algorithmic MACs -------------------------------------------
+def _street_opt(**kw):
+    return make_opt(label_nc=35, use_instance=True, fg=True, gpu_ids=[], **kw)
+
+
+def test_conv_macs_match_baseline():
+    opt = _street_opt(n_scales_spatial=3)
+    g0, g1, g2 = (NW.build_netG(opt, s) for s in range(3))
+    assert g0.conv_macs(1, 128, 256) == 264373272576                          # cfg1
+    m0 = g0.conv_macs(1, 256, 512)
+    assert m0 == 1057493090304                                                # cfg2 / cfg4-G0
+    m1 = g1.conv_macs(1, 512, 1024)
+    m2 = g2.conv_macs(1, 1024, 2048)
+    assert m1 == 592957145088 and m2 == 881508483072
+    assert m0 + m1 + m2 == 2531958718464                                      # cfg4 frame
+    assert g0.conv_macs(1, 256, 512) + g1.conv_macs(1, 512, 1024) == 1650450235392   # cfg3 (S=2)
+
+
+def test_conv_macs_first_frame_generators():
+    opt = make_opt(gpu_ids=[])
+    g512 = NW.define_G(35, 3, 0, 64, 'global', 3, 'instance', 0, [], opt)
+    g2048 = NW.define_G(35, 3, 0, 32, 'local', 4, 'instance', 0, [], opt)
+    assert abs(g512.conv_macs(1, 256, 512) / 1e9 - 117.1) < 0.1
+    assert abs(g2048.conv_macs(1, 1024, 2048) / 1e9 - 743.0) < 0.1
+
+
+# ---- state_dict compatibility ------------------------------------------------------------------------
+def test_state_dict_keys_match_reference_fixture():
+    gold = json.load(open(os.path.join(ROOT, 'tests', 'golden', 'state_dict_keys.json')))
+    for name, c in cases.KEY_CASES.items():
+        ours = [[k, list(v.shape)] for k, v in cases.build_module(c).state_dict().items()]
+        assert ours == gold[name], name
+
+
+def test_plan_describe_layouts():
+    opt = _street_opt()
+    g0 = NW.build_netG(opt, 0)
+    from vid2vid_b200.plan import Plan
+    p = Plan(0)
+    g0._describe(p, 1, 256, 512)
+    d = p.describe()
+    assert d['conv_macs'] == 1057493090304
+    # every value consumed by a stride-2 conv is parity split; reflect-3 layouts feed the 7x7 convs
+    convs = d['convs']
+    assert sum(1 for c in convs if c['k'] == [7, 7]) == 3 + 4          # stems + heads
+    assert all(c['TH'] * c['TW'] == 128 for c in convs)
+    assert any(c['R'] == 7 for c in convs) and any(c['phases'] == 4 for c in convs)

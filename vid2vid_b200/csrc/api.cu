@@ -1,0 +1,114 @@
+// extern "C" entry points of the stand-alone operators (group (1) of include/v2v_b200.h).
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#include "../../include/v2v_b200.h"
+#include "v2v_internal.h"
+
+namespace v2v {
+void set_error(const char* fmt, ...);
+cudaError_t launch_correlation(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
+cudaError_t launch_resample2d(const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+cudaError_t launch_channelnorm(const float*, float*, int, int, int, int, int, cudaStream_t);
+cudaError_t launch_resample(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+cudaError_t launch_onehot_edges(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
+cudaError_t launch_avgpool3s2(const float*, float*, int, int, int, cudaStream_t);
+struct FgLabels { int v[16]; };
+cudaError_t launch_fg_mask(const float*, float*, int, int, int, int, int, int, FgLabels, int, cudaStream_t);
+}  // namespace v2v
+
+using namespace v2v;
+
+#define API_CUDA(expr)                                                         \
+  do {                                                                         \
+    cudaError_t e__ = (expr);                                                  \
+    if (e__ != cudaSuccess) {                                                  \
+      set_error("%s failed: %s", #expr, cudaGetErrorString(e__));              \
+      return (int)e__;                                                         \
+    }                                                                          \
+  } while (0)
+#define API_REQUIRE(cond, ...)     \
+  do {                             \
+    if (!(cond)) {                 \
+      set_error(__VA_ARGS__);      \
+      return V2V_ERR_INVALID;      \
+    }                              \
+  } while (0)
+
+extern "C" {
+
+int v2v_correlation_out_shape(int H, int W, int pad_size, int kernel_size, int max_displacement, int stride1,
+                              int stride2, int* outC, int* outH, int* outW) {
+  API_REQUIRE(outC && outH && outW && stride1 > 0 && stride2 > 0 && kernel_size > 0, "bad correlation arguments");
+  // correlation_cuda.cc:25-38
+  const int kernel_radius = (kernel_size - 1) / 2;
+  const int border_radius = kernel_radius + max_displacement;
+  const int d = (max_displacement / stride2) * 2 + 1;
+  *outC = d * d;
+  *outH = (int)std::ceil((float)(H + 2 * pad_size - 2 * border_radius) / (float)stride1);
+  *outW = (int)std::ceil((float)(W + 2 * pad_size - 2 * border_radius) / (float)stride1);
+  return 0;
+}
+
+int v2v_correlation_forward(const float* in1, const float* in2, float* out, int N, int C, int H, int W, int pad_size,
+                            int kernel_size, int max_displacement, int stride1, int stride2, int corr_type_multiply,
+                            v2v_stream_t stream) {
+  API_REQUIRE(in1 && in2 && out && N > 0 && C > 0 && H > 0 && W > 0, "null tensor or empty shape");
+  API_REQUIRE(kernel_size == 1, "correlation: kernel_size %d unsupported (FlowNetC uses 1)", kernel_size);
+  API_REQUIRE(corr_type_multiply == 1, "correlation: only the multiplicative type exists in the reference");
+  API_CUDA(launch_correlation(in1, in2, out, N, C, H, W, pad_size, kernel_size, max_displacement, stride1, stride2,
+                              reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int v2v_resample2d_forward(const float* in1, const float* flow, float* out, int N, int C, int H, int W, int inH,
+                           int inW, int kernel_size, v2v_stream_t stream) {
+  API_REQUIRE(in1 && flow && out && N > 0 && C > 0 && H > 0 && W > 0, "null tensor or empty shape");
+  API_REQUIRE(kernel_size == 1, "resample2d: kernel_size %d unsupported", kernel_size);
+  API_CUDA(launch_resample2d(in1, flow, out, N, C, H, W, inH, inW, kernel_size, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int v2v_channelnorm_forward(const float* in, float* out, int N, int C, int H, int W, int norm_deg, v2v_stream_t stream) {
+  API_REQUIRE(in && out && N > 0 && C > 0 && H > 0 && W > 0, "null tensor or empty shape");
+  API_REQUIRE(norm_deg == 2, "channelnorm: norm_deg %d unsupported", norm_deg);
+  API_CUDA(launch_channelnorm(in, out, N, C, H, W, norm_deg, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int v2v_resample_forward(const float* image, const float* flow, float* out, int N, int C, int H, int W, int align_corners,
+                         v2v_stream_t stream) {
+  API_REQUIRE(image && flow && out && N > 0 && C > 0 && H > 1 && W > 1, "null tensor or degenerate shape");
+  API_CUDA(launch_resample(image, flow, out, N, C, H, W, align_corners, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int v2v_onehot_edges(const float* labels, const float* inst, float* out, int F, int label_nc, int use_instance, int H, int W,
+                     v2v_stream_t stream) {
+  API_REQUIRE(labels && out && F > 0 && label_nc > 0 && H > 0 && W > 0, "null tensor or empty shape");
+  API_REQUIRE(!use_instance || inst, "use_instance set but inst is null");
+  API_CUDA(launch_onehot_edges(labels, inst, out, F, label_nc, use_instance, H, W, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int v2v_avgpool3s2(const float* in, float* out, int P, int H, int W, v2v_stream_t stream) {
+  API_REQUIRE(in && out && P > 0 && H > 0 && W > 0, "null tensor or empty shape");
+  API_CUDA(launch_avgpool3s2(in, out, P, H, W, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int v2v_fg_mask(const float* real_A, float* mask, int B, int T, int C, int H, int W, int t, const int* fg_labels, int n_labels,
+                v2v_stream_t stream) {
+  API_REQUIRE(real_A && mask && fg_labels && n_labels > 0 && n_labels <= 16, "bad fg_mask arguments");
+  API_REQUIRE(t >= 0 && t < T, "frame index out of range");
+  FgLabels l{};
+  for (int i = 0; i < n_labels; ++i) {
+    API_REQUIRE(fg_labels[i] >= 0 && fg_labels[i] < C, "fg label %d out of range for %d channels", fg_labels[i], C);
+    l.v[i] = fg_labels[i];
+  }
+  API_CUDA(launch_fg_mask(real_A, mask, B, T, C, H, W, t, l, n_labels, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,758 @@
+// Plan runtime: lowers a graph of logical values / convolution units (described through the C ABI in
+// include/v2v_b200.h) to halo-padded NHWC bf16 buffers, TMA tensor maps, packed weight matrices and a
+// flat kernel sequence, captures the sequence in a CUDA graph and replays it per frame.
+// This is the B200-native counterpart of the nn.Module surface the reference's Vid2VidModelG calls
+// (netG.forward, models/vid2vid_model_G.py:225-226; module bodies models/networks.py:117-419,634-725).
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/v2v_b200.h"
+#include "v2v_internal.h"
+
+namespace v2v {
+
+thread_local std::string g_last_error;
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+}
+
+#define V2V_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__);   \
+      return (int)e__;                                                                          \
+    }                                                                                           \
+  } while (0)
+#define V2V_REQUIRE(cond, code, ...) \
+  do {                               \
+    if (!(cond)) {                   \
+      set_error(__VA_ARGS__);        \
+      return code;                   \
+    }                                \
+  } while (0)
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static inline size_t round_up_sz(size_t a, size_t b) { return (a + b - 1) / b * b; }
+
+// ------------------------------------------------------------------------------ conv geometry
+struct ConvGeom {
+  int pads[4];            // top, left, bottom, right of the input buffer
+  int parity;
+  int grid_h, grid_w;     // grid the kernel iterates over
+  int out_h, out_w;       // conv output extent
+  int mul;                // output coord = grid coord * mul + phase add
+  int TH, TW, R;
+  int n_groups, n_phases;
+  ConvGroup groups[V2V_MAX_TAPS];
+  ConvPhase phases[V2V_MAX_PHASES];
+};
+
+static int conv_geometry(const v2v_conv_desc& c, int H, int W, bool allow_reuse, ConvGeom* g) {
+  memset(g, 0, sizeof(*g));
+  V2V_REQUIRE(c.kh >= 1 && c.kw >= 1 && c.kh * c.kw <= V2V_MAX_TAPS, V2V_ERR_UNSUPPORTED, "kernel %dx%d unsupported",
+              c.kh, c.kw);
+  V2V_REQUIRE(c.stride == 1 || c.stride == 2, V2V_ERR_UNSUPPORTED, "stride %d unsupported", c.stride);
+  if (!c.transposed) {
+    g->out_h = (H + 2 * c.pad - c.kh) / c.stride + 1;
+    g->out_w = (W + 2 * c.pad - c.kw) / c.stride + 1;
+    V2V_REQUIRE(g->out_h > 0 && g->out_w > 0, V2V_ERR_INVALID, "empty conv output");
+    g->grid_h = g->out_h; g->grid_w = g->out_w; g->mul = 1;
+    g->pads[0] = g->pads[1] = g->pads[2] = g->pads[3] = c.pad;
+    g->parity = (c.stride == 2);
+  } else {
+    V2V_REQUIRE(c.stride == 2, V2V_ERR_UNSUPPORTED, "transposed conv needs stride 2");
+    g->out_h = (H - 1) * 2 - 2 * c.pad + c.kh + c.output_padding;
+    g->out_w = (W - 1) * 2 - 2 * c.pad + c.kw + c.output_padding;
+    V2V_REQUIRE(g->out_h == 2 * H && g->out_w == 2 * W, V2V_ERR_UNSUPPORTED,
+                "transposed conv must exactly double the extent (got %dx%d from %dx%d)", g->out_h, g->out_w, H, W);
+    g->grid_h = H; g->grid_w = W; g->mul = 2; g->parity = 0;
+  }
+  g->TW = g->grid_w > 64 ? 128 : 8;
+  while (g->TW < g->grid_w && g->TW < 128) g->TW *= 2;
+  g->TH = 128 / g->TW;
+  g->R = 1;
+  int ng = 0;
+  if (!c.transposed && c.stride == 1) {
+    g->n_phases = 1;
+    if (allow_reuse && g->TH == 1 && c.kw > 1) {
+      g->R = c.kw;
+      for (int ky = 0; ky < c.kh; ++ky) g->groups[ng++] = ConvGroup{0, (int8_t)ky, 0, 0, (int16_t)(ky * c.kw), 0};
+    } else {
+      for (int ky = 0; ky < c.kh; ++ky)
+        for (int kx = 0; kx < c.kw; ++kx)
+          g->groups[ng++] = ConvGroup{0, (int8_t)ky, (int8_t)kx, 0, (int16_t)(ky * c.kw + kx), 0};
+    }
+    g->phases[0] = ConvPhase{0, ng, 0, 0};
+  } else if (!c.transposed) {   // stride 2: parity-split planes, tap (ky,kx) -> plane (ky&1, kx&1), offset (ky>>1, kx>>1)
+    g->n_phases = 1;
+    for (int ky = 0; ky < c.kh; ++ky)
+      for (int kx = 0; kx < c.kw; ++kx)
+        g->groups[ng++] = ConvGroup{(int8_t)(((ky & 1) << 1) | (kx & 1)), (int8_t)(ky >> 1), (int8_t)(kx >> 1), 0,
+                                    (int16_t)(ky * c.kw + kx), 0};
+    g->phases[0] = ConvPhase{0, ng, 0, 0};
+  } else {
+    // sub-pixel phases of the stride-2 transposed conv: out(2i+a, 2j+b) gathers input (i+dy, j+dx) for the
+    // taps with (a + pad - ky) even, dy = (a + pad - ky) / 2 (same in x)
+    int dmin = 0, dmax = 0;
+    for (int a = 0; a < 2; ++a)
+      for (int k = 0; k < std::max(c.kh, c.kw); ++k)
+        if (((a + c.pad - k) % 2) == 0) { int d = (a + c.pad - k) / 2; dmin = std::min(dmin, d); dmax = std::max(dmax, d); }
+    g->pads[0] = g->pads[1] = -dmin; g->pads[2] = g->pads[3] = dmax;
+    g->n_phases = 4;
+    for (int a = 0; a < 2; ++a)
+      for (int b = 0; b < 2; ++b) {
+        const int begin = ng;
+        for (int ky = 0; ky < c.kh; ++ky) {
+          if ((a + c.pad - ky) % 2 != 0) continue;
+          for (int kx = 0; kx < c.kw; ++kx) {
+            if ((b + c.pad - kx) % 2 != 0) continue;
+            const int dy = (a + c.pad - ky) / 2 - dmin, dx = (b + c.pad - kx) / 2 - dmin;
+            V2V_REQUIRE(ng < V2V_MAX_TAPS, V2V_ERR_UNSUPPORTED, "too many taps");
+            g->groups[ng++] = ConvGroup{0, (int8_t)dy, (int8_t)dx, 0, (int16_t)(ky * c.kw + kx), 0};
+          }
+        }
+        g->phases[a * 2 + b] = ConvPhase{begin, ng, a, b};
+      }
+  }
+  g->n_groups = ng;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ graph description
+struct Req { int mode, pads[4], parity; };
+static bool same_req(const Req& a, const Req& b) {
+  return a.mode == b.mode && a.parity == b.parity && !memcmp(a.pads, b.pads, sizeof(a.pads));
+}
+
+struct Value {
+  int N, H, W, C;
+  std::vector<Req> reqs;
+  std::vector<int> bufs;     // index into Plan::acts, one per req
+  bool interior_use = false;
+};
+struct Raw {
+  int N, H, W, C;
+  int conv_op = -1;          // index of producing graph op
+  RawDesc desc{};
+  float* stats = nullptr; int stats_rows = 0;
+  float* scale = nullptr; float* shift = nullptr;
+  int tiles_per_img = 0, num_phases = 1;
+};
+
+enum GKind { G_INPUT, G_CONV, G_NORM_ACT, G_CONV_ACT, G_HEAD, G_EXPORT, G_COMPOSITE };
+struct GOp {
+  GKind kind;
+  // input
+  int slot = -1, C_src = 0, c_off = 0;
+  int value_in = -1, value_out = -1, raw = -1;
+  v2v_conv_desc conv{};
+  ConvGeom geom{};
+  int req_index = -1;        // which materialisation of value_in this conv reads
+  v2v_norm_desc norm{};
+  int act = 0; float slope = 0.f;
+  int add[2] = {-1, -1};
+  v2v_head_channel head[V2V_MAX_HEAD];
+  CompositeParams comp{};
+  // lowered
+  bf16* wpacked = nullptr; int Ktotal = 0, Cp = 0;
+  CUtensorMap tmA{}, tmB{};
+  ConvKernelParams kp{};
+};
+
+enum XKind { X_IMPORT, X_CONV, X_RAWSTATS, X_FINALIZE, X_APPLY, X_EXPORT, X_COMPOSITE };
+struct XOp {
+  XKind kind;
+  int gop = -1;
+  ImportParams imp{};
+  ExportParams exp{};
+  FinalizeParams fin{};
+  ApplyParams app{};
+  CompositeParams comp{};
+  RawDesc rawd{}; float* stats = nullptr; int stats_C = 0;
+};
+
+}  // namespace v2v
+
+using namespace v2v;
+
+struct v2v_plan {
+  int device = 0;
+  int impl = V2V_IMPL_UMMA;
+  bool allow_reuse = true;
+  bool lowered = false, finalized = false;
+  std::vector<Value> values;
+  std::vector<Raw> raws;
+  std::vector<GOp> gops;
+  std::vector<ActDesc> acts;
+  std::vector<int> act_pad_mode;
+  std::vector<XOp> xops;
+  int n_slots = 0;
+  double conv_macs = 0.0;
+  // device
+  void* arena = nullptr; size_t arena_bytes = 0;
+  void** io_dev = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t graph_stream = nullptr;
+};
+
+namespace v2v {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+static int make_tmap_act(CUtensorMap* tm, const ActDesc& a, int box_w, int box_h) {
+  EncodeTiledFn fn = get_encode_fn();
+  V2V_REQUIRE(fn, V2V_ERR_STATE, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[5] = {(cuuint64_t)a.C, (cuuint64_t)a.Wp, (cuuint64_t)a.Hp, (cuuint64_t)a.P, (cuuint64_t)a.N};
+  cuuint64_t strides[4] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.Wp * a.C * 2, (cuuint64_t)a.Hp * a.Wp * a.C * 2,
+                           (cuuint64_t)a.P * a.Hp * a.Wp * a.C * 2};
+  cuuint32_t box[5] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, a.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  V2V_REQUIRE(r == CUDA_SUCCESS, V2V_ERR_STATE, "cuTensorMapEncodeTiled(A) failed: %d (C=%d Wp=%d Hp=%d P=%d N=%d box %dx%d)",
+              (int)r, a.C, a.Wp, a.Hp, a.P, a.N, box_w, box_h);
+  return 0;
+}
+
+static int make_tmap_w(CUtensorMap* tm, bf16* w, int Ktotal, int Cout, int BN) {
+  EncodeTiledFn fn = get_encode_fn();
+  V2V_REQUIRE(fn, V2V_ERR_STATE, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)Ktotal, (cuuint64_t)Cout};
+  cuuint64_t strides[1] = {(cuuint64_t)Ktotal * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)BN};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  V2V_REQUIRE(r == CUDA_SUCCESS, V2V_ERR_STATE, "cuTensorMapEncodeTiled(B) failed: %d (K=%d Cout=%d BN=%d)", (int)r, Ktotal,
+              Cout, BN);
+  return 0;
+}
+
+static ActDesc make_act(const Value& v, const Req& r) {
+  ActDesc a{};
+  a.base = nullptr;
+  a.N = v.N; a.H = v.H; a.W = v.W; a.Cvalid = v.C; a.C = round_up(v.C, 64);
+  a.pad_t = r.pads[0]; a.pad_l = r.pads[1]; a.pad_b = r.pads[2]; a.pad_r = r.pads[3];
+  a.parity = r.parity;
+  const int Hpad = v.H + a.pad_t + a.pad_b, Wpad = v.W + a.pad_l + a.pad_r;
+  if (a.parity) { a.P = 4; a.Hp = (Hpad + 1) / 2; a.Wp = (Wpad + 1) / 2; }
+  else { a.P = 1; a.Hp = Hpad; a.Wp = Wpad; }
+  return a;
+}
+
+static int add_req(Value& v, const Req& r) {
+  for (size_t i = 0; i < v.reqs.size(); ++i)
+    if (same_req(v.reqs[i], r)) return (int)i;
+  v.reqs.push_back(r);
+  return (int)v.reqs.size() - 1;
+}
+
+static Req conv_req(const v2v_conv_desc& c, const ConvGeom& g) {
+  Req r{};
+  r.mode = c.transposed ? PAD_ZERO : (c.pad == 0 ? PAD_ZERO : c.pad_mode);
+  memcpy(r.pads, g.pads, sizeof(r.pads));
+  r.parity = g.parity;
+  return r;
+}
+
+// Host-only lowering: requirements, buffer descriptors (no addresses), kernel parameter skeletons.
+static int lower(v2v_plan* P) {
+  if (P->lowered) return 0;
+  // pass 1: consumer requirements
+  for (auto& op : P->gops) {
+    if (op.kind == G_CONV || op.kind == G_CONV_ACT || op.kind == G_HEAD) {
+      Value& vin = P->values[op.value_in];
+      int rc = conv_geometry(op.conv, vin.H, vin.W, P->allow_reuse, &op.geom);
+      if (rc) return rc;
+      op.req_index = add_req(vin, conv_req(op.conv, op.geom));
+      const v2v_conv_desc& c = op.conv;
+      const double px = op.conv.transposed ? (double)vin.N * vin.H * vin.W : (double)vin.N * op.geom.out_h * op.geom.out_w;
+      P->conv_macs += px * c.Cin * c.Cout * c.kh * c.kw;
+    } else if (op.kind == G_NORM_ACT) {
+      for (int k = 0; k < 2; ++k) if (op.add[k] >= 0) P->values[op.add[k]].interior_use = true;
+    } else if (op.kind == G_EXPORT) {
+      P->values[op.value_in].interior_use = true;
+    }
+  }
+  for (auto& v : P->values) {
+    if (v.reqs.empty()) { Req r{}; r.mode = PAD_NONE; v.reqs.push_back(r); }
+    v.bufs.clear();
+    for (auto& r : v.reqs) {
+      P->acts.push_back(make_act(v, r));
+      P->act_pad_mode.push_back(r.mode);
+      v.bufs.push_back((int)P->acts.size() - 1);
+    }
+  }
+  P->lowered = true;
+  return 0;
+}
+
+static void fill_conv_params(v2v_plan* P, GOp& op) {
+  const Value& vin = P->values[op.value_in];
+  const ConvGeom& g = op.geom;
+  ConvKernelParams& kp = op.kp;
+  memset(&kp, 0, sizeof(kp));
+  kp.N = vin.N; kp.TH = g.TH; kp.TW = g.TW;
+  kp.tiles_x = (g.grid_w + g.TW - 1) / g.TW; kp.tiles_y = (g.grid_h + g.TH - 1) / g.TH;
+  kp.grid_h = g.grid_h; kp.grid_w = g.grid_w;
+  kp.Cout = op.conv.Cout;
+  kp.BN = op.kind == G_HEAD ? 16 : std::min(128, round_up(op.conv.Cout, 32));
+  kp.Cp = round_up(op.conv.Cin, 64); kp.cblocks = kp.Cp / 64;
+  kp.R = g.R;
+  kp.a_slot_bytes = round_up((g.TW + g.R - 1) * g.TH * 128, 1024);
+  kp.b_slot_bytes = kp.BN * 128;
+  const int budget = 200 * 1024;
+  if (g.R == 1) {
+    int s = budget / (kp.a_slot_bytes + kp.b_slot_bytes);
+    s = std::max(2, std::min(8, s));
+    kp.SA = kp.SB = s;
+  } else {
+    kp.SA = 3;
+    kp.SB = std::max(2, std::min(8, (budget - kp.SA * kp.a_slot_bytes) / kp.b_slot_bytes));
+  }
+  kp.num_phases = g.n_phases;
+  memcpy(kp.phases, g.phases, sizeof(kp.phases));
+  memcpy(kp.groups, g.groups, sizeof(kp.groups));
+  kp.oy_mul = kp.ox_mul = g.mul;
+  kp.out_H = g.out_h; kp.out_W = g.out_w;
+  kp.bias = op.conv.bias;
+  kp.lrelu_slope = op.slope;
+  kp.act = op.act;
+  op.Cp = kp.Cp; op.Ktotal = op.conv.kh * op.conv.kw * kp.Cp;
+}
+
+static int pack_one(const GOp& op, cudaStream_t stream) {
+  PackParams pp{};
+  pp.w = op.conv.weight; pp.transposed = op.conv.transposed;
+  pp.Cout = op.conv.Cout; pp.Cin = op.conv.Cin; pp.kh = op.conv.kh; pp.kw = op.conv.kw;
+  pp.Cp = op.Cp; pp.ntaps = op.conv.kh * op.conv.kw;
+  for (int ky = 0; ky < op.conv.kh; ++ky)
+    for (int kx = 0; kx < op.conv.kw; ++kx) { pp.tap_ky[ky * op.conv.kw + kx] = (int8_t)ky; pp.tap_kx[ky * op.conv.kw + kx] = (int8_t)kx; }
+  pp.out = op.wpacked;
+  V2V_CUDA(launch_pack_weights(pp, stream));
+  return 0;
+}
+
+static int run_xop(v2v_plan* P, const XOp& x, cudaStream_t s) {
+  switch (x.kind) {
+    case X_IMPORT: V2V_CUDA(launch_import_nchw(x.imp, s)); break;
+    case X_EXPORT: V2V_CUDA(launch_export_nchw(x.exp, s)); break;
+    case X_FINALIZE: V2V_CUDA(launch_stats_finalize(x.fin, s)); break;
+    case X_APPLY: V2V_CUDA(launch_norm_apply(x.app, s)); break;
+    case X_COMPOSITE: V2V_CUDA(launch_composite(x.comp, s)); break;
+    case X_RAWSTATS: V2V_CUDA(launch_raw_stats(x.rawd, x.stats, x.stats_C, s)); break;
+    case X_CONV: {
+      const GOp& op = P->gops[x.gop];
+      if (P->impl == V2V_IMPL_UMMA) V2V_CUDA(launch_conv_umma(op.tmA, op.tmB, op.kp, s));
+      else V2V_CUDA(launch_conv_simt(P->acts[P->values[op.value_in].bufs[op.req_index]], op.wpacked, op.Ktotal, op.kp, s));
+      break;
+    }
+  }
+  return 0;
+}
+
+}  // namespace v2v
+
+// =============================================================================================== C ABI
+extern "C" {
+
+int v2v_version(void) { return 100; }
+const char* v2v_last_error(void) { return g_last_error.c_str(); }
+
+int v2v_plan_create(int device, int conv_impl, v2v_plan** out) {
+  V2V_REQUIRE(out, V2V_ERR_INVALID, "null out");
+  v2v_plan* p = new v2v_plan();
+  p->device = device;
+  p->impl = conv_impl;
+  const char* e = getenv("V2V_TAP_REUSE");
+  p->allow_reuse = !(e && e[0] == '0');
+  const char* ei = getenv("V2V_CONV_IMPL");
+  if (ei && !strcmp(ei, "simt")) p->impl = V2V_IMPL_SIMT;
+  *out = p;
+  return 0;
+}
+
+int v2v_plan_destroy(v2v_plan* p) {
+  if (!p) return 0;
+  if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+  if (p->arena) cudaFree(p->arena);
+  if (p->io_dev) cudaFree(p->io_dev);
+  delete p;
+  return 0;
+}
+
+static int new_value(v2v_plan* p, int N, int H, int W, int C) {
+  Value v; v.N = N; v.H = H; v.W = W; v.C = C;
+  p->values.push_back(v);
+  return (int)p->values.size() - 1;
+}
+
+int v2v_g_input(v2v_plan* p, int slot, int N, int C_src, int c_off, int C, int H, int W, int* value_out) {
+  V2V_REQUIRE(p && !p->lowered && value_out, V2V_ERR_STATE, "plan already lowered or null");
+  V2V_REQUIRE(slot >= 0 && N > 0 && C > 0 && c_off >= 0 && c_off + C <= C_src && H > 0 && W > 0, V2V_ERR_INVALID,
+              "bad input description");
+  GOp op; op.kind = G_INPUT; op.slot = slot; op.C_src = C_src; op.c_off = c_off;
+  op.value_out = new_value(p, N, H, W, C);
+  p->n_slots = std::max(p->n_slots, slot + 1);
+  p->gops.push_back(op);
+  *value_out = op.value_out;
+  return 0;
+}
+
+static int check_conv(v2v_plan* p, int value_in, const v2v_conv_desc* c) {
+  V2V_REQUIRE(p && !p->lowered && c, V2V_ERR_STATE, "plan already lowered or null");
+  V2V_REQUIRE(value_in >= 0 && value_in < (int)p->values.size(), V2V_ERR_INVALID, "bad value id %d", value_in);
+  V2V_REQUIRE(c->Cin == p->values[value_in].C, V2V_ERR_INVALID, "conv Cin %d != value channels %d", c->Cin,
+              p->values[value_in].C);
+  V2V_REQUIRE(c->Cout > 0, V2V_ERR_INVALID, "bad Cout");
+  return 0;
+}
+
+int v2v_g_conv(v2v_plan* p, int value_in, const v2v_conv_desc* c, int* raw_out) {
+  int rc = check_conv(p, value_in, c); if (rc) return rc;
+  V2V_REQUIRE(raw_out, V2V_ERR_INVALID, "null raw_out");
+  ConvGeom g; rc = conv_geometry(*c, p->values[value_in].H, p->values[value_in].W, p->allow_reuse, &g); if (rc) return rc;
+  GOp op; op.kind = G_CONV; op.value_in = value_in; op.conv = *c;
+  Raw r{}; r.N = p->values[value_in].N; r.H = g.out_h; r.W = g.out_w; r.C = c->Cout; r.conv_op = (int)p->gops.size();
+  p->raws.push_back(r);
+  op.raw = (int)p->raws.size() - 1;
+  p->gops.push_back(op);
+  *raw_out = op.raw;
+  return 0;
+}
+
+int v2v_g_norm_act(v2v_plan* p, int raw_in, const v2v_norm_desc* norm, int act, float slope, int add0, int add1,
+                   int* value_out) {
+  V2V_REQUIRE(p && !p->lowered && norm && value_out, V2V_ERR_STATE, "plan already lowered or null");
+  V2V_REQUIRE(raw_in >= 0 && raw_in < (int)p->raws.size(), V2V_ERR_INVALID, "bad raw id");
+  const Raw& r = p->raws[raw_in];
+  GOp op; op.kind = G_NORM_ACT; op.raw = raw_in; op.norm = *norm; op.act = act; op.slope = slope;
+  op.add[0] = add0; op.add[1] = add1;
+  for (int k = 0; k < 2; ++k)
+    if (op.add[k] >= 0) {
+      V2V_REQUIRE(op.add[k] < (int)p->values.size(), V2V_ERR_INVALID, "bad addend id");
+      const Value& a = p->values[op.add[k]];
+      V2V_REQUIRE(a.N == r.N && a.H == r.H && a.W == r.W && a.C == r.C, V2V_ERR_INVALID,
+                  "addend shape (%d,%d,%d,%d) != raw shape (%d,%d,%d,%d)", a.N, a.C, a.H, a.W, r.N, r.C, r.H, r.W);
+    }
+  op.value_out = new_value(p, r.N, r.H, r.W, r.C);
+  p->gops.push_back(op);
+  *value_out = op.value_out;
+  return 0;
+}
+
+int v2v_g_conv_act(v2v_plan* p, int value_in, const v2v_conv_desc* c, int act, float slope, int* value_out) {
+  int rc = check_conv(p, value_in, c); if (rc) return rc;
+  V2V_REQUIRE(value_out, V2V_ERR_INVALID, "null value_out");
+  ConvGeom g; rc = conv_geometry(*c, p->values[value_in].H, p->values[value_in].W, p->allow_reuse, &g); if (rc) return rc;
+  GOp op; op.kind = G_CONV_ACT; op.value_in = value_in; op.conv = *c; op.act = act; op.slope = slope;
+  op.value_out = new_value(p, p->values[value_in].N, g.out_h, g.out_w, c->Cout);
+  p->gops.push_back(op);
+  *value_out = op.value_out;
+  return 0;
+}
+
+int v2v_g_head(v2v_plan* p, int value_in, const v2v_conv_desc* c, const v2v_head_channel* ch) {
+  int rc = check_conv(p, value_in, c); if (rc) return rc;
+  V2V_REQUIRE(ch && c->Cout <= V2V_MAX_HEAD && !c->transposed && c->stride == 1, V2V_ERR_UNSUPPORTED,
+              "head conv must be stride-1 with Cout <= %d", V2V_MAX_HEAD);
+  GOp op; op.kind = G_HEAD; op.value_in = value_in; op.conv = *c;
+  for (int j = 0; j < c->Cout; ++j) { op.head[j] = ch[j]; p->n_slots = std::max(p->n_slots, ch[j].slot + 1); }
+  p->gops.push_back(op);
+  return 0;
+}
+
+int v2v_g_export(v2v_plan* p, int value, int slot) {
+  V2V_REQUIRE(p && !p->lowered, V2V_ERR_STATE, "plan already lowered or null");
+  V2V_REQUIRE(value >= 0 && value < (int)p->values.size() && slot >= 0, V2V_ERR_INVALID, "bad export");
+  GOp op; op.kind = G_EXPORT; op.value_in = value; op.slot = slot;
+  p->n_slots = std::max(p->n_slots, slot + 1);
+  p->gops.push_back(op);
+  return 0;
+}
+
+int v2v_g_composite(v2v_plan* p, int s_raw, int s_flow, int s_weight, int s_prev, int prev_C, int s_fg, int s_mask,
+                    int s_final, int N, int H, int W, int use_warp, int align_corners) {
+  V2V_REQUIRE(p && !p->lowered, V2V_ERR_STATE, "plan already lowered or null");
+  V2V_REQUIRE(s_raw >= 0 && s_final >= 0, V2V_ERR_INVALID, "composite needs raw and final slots");
+  V2V_REQUIRE(!use_warp || (s_flow >= 0 && s_weight >= 0 && s_prev >= 0 && prev_C >= 3), V2V_ERR_INVALID,
+              "warp needs flow, weight and prev");
+  V2V_REQUIRE((s_fg >= 0) == (s_mask >= 0), V2V_ERR_INVALID, "fg and mask go together");
+  GOp op; op.kind = G_COMPOSITE;
+  CompositeParams& c = op.comp;
+  c.s_raw = s_raw; c.s_flow = s_flow; c.s_weight = s_weight; c.s_prev = s_prev; c.s_fg = s_fg; c.s_mask = s_mask;
+  c.s_final = s_final; c.prev_C = prev_C; c.N = N; c.H = H; c.W = W; c.align_corners = align_corners; c.use_warp = use_warp;
+  int m = std::max({s_raw, s_flow, s_weight, s_prev, s_fg, s_mask, s_final});
+  p->n_slots = std::max(p->n_slots, m + 1);
+  p->gops.push_back(op);
+  return 0;
+}
+
+int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  V2V_REQUIRE(P && !P->finalized, V2V_ERR_STATE, "plan null or already finalized");
+  int rc = lower(P); if (rc) return rc;
+  V2V_CUDA(cudaSetDevice(P->device));
+
+  // ---- size the arena
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = round_up_sz(off + bytes, 1024); return o; };
+  std::vector<size_t> act_off(P->acts.size());
+  for (size_t i = 0; i < P->acts.size(); ++i) act_off[i] = take(P->acts[i].elems() * sizeof(bf16));
+  struct RawOff { size_t raw, stats, scale, shift; };
+  std::vector<RawOff> raw_off(P->raws.size());
+  std::vector<size_t> w_off(P->gops.size(), 0);
+  for (size_t i = 0; i < P->gops.size(); ++i) {
+    GOp& op = P->gops[i];
+    if (op.kind == G_CONV || op.kind == G_CONV_ACT || op.kind == G_HEAD) {
+      fill_conv_params(P, op);
+      w_off[i] = take((size_t)op.conv.Cout * op.Ktotal * sizeof(bf16));
+      if (op.kind == G_CONV) {
+        Raw& r = P->raws[op.raw];
+        r.desc.N = r.N; r.desc.H = r.H; r.desc.W = r.W; r.desc.Cvalid = r.C; r.desc.C = round_up(r.C, 8);
+        if (P->impl == V2V_IMPL_UMMA) { r.tiles_per_img = op.kp.tiles_x * op.kp.tiles_y; r.num_phases = op.kp.num_phases; }
+        else { r.tiles_per_img = 1; r.num_phases = 1; }
+        r.stats_rows = r.num_phases * r.N * r.tiles_per_img;
+        raw_off[op.raw].raw = take(r.desc.elems() * sizeof(bf16));
+        raw_off[op.raw].stats = take((size_t)r.stats_rows * 2 * r.C * sizeof(float));
+        raw_off[op.raw].scale = take((size_t)r.N * r.C * sizeof(float));
+        raw_off[op.raw].shift = take((size_t)r.N * r.C * sizeof(float));
+      }
+    }
+  }
+  P->arena_bytes = off;
+  V2V_CUDA(cudaMalloc(&P->arena, P->arena_bytes));
+  V2V_CUDA(cudaMemsetAsync(P->arena, 0, P->arena_bytes, stream));
+  V2V_CUDA(cudaMalloc(reinterpret_cast<void**>(&P->io_dev), sizeof(void*) * std::max(1, P->n_slots)));
+  uint8_t* base = reinterpret_cast<uint8_t*>(P->arena);
+  for (size_t i = 0; i < P->acts.size(); ++i) P->acts[i].base = reinterpret_cast<bf16*>(base + act_off[i]);
+  for (size_t i = 0; i < P->raws.size(); ++i) {
+    Raw& r = P->raws[i];
+    r.desc.base = reinterpret_cast<bf16*>(base + raw_off[i].raw);
+    r.stats = reinterpret_cast<float*>(base + raw_off[i].stats);
+    r.scale = reinterpret_cast<float*>(base + raw_off[i].scale);
+    r.shift = reinterpret_cast<float*>(base + raw_off[i].shift);
+  }
+
+  // ---- emit executable ops
+  for (size_t i = 0; i < P->gops.size(); ++i) {
+    GOp& op = P->gops[i];
+    switch (op.kind) {
+      case G_INPUT: {
+        const Value& v = P->values[op.value_out];
+        for (size_t m = 0; m < v.bufs.size(); ++m) {
+          XOp x; x.kind = X_IMPORT; x.gop = (int)i;
+          x.imp.io = reinterpret_cast<const void* const*>(P->io_dev); x.imp.slot = op.slot;
+          x.imp.c_off = op.c_off; x.imp.C_src = op.C_src;
+          x.imp.out = P->acts[v.bufs[m]]; x.imp.pad_mode = P->act_pad_mode[v.bufs[m]];
+          P->xops.push_back(x);
+        }
+        break;
+      }
+      case G_CONV: case G_CONV_ACT: case G_HEAD: {
+        const Value& vin = P->values[op.value_in];
+        const ActDesc& ain = P->acts[vin.bufs[op.req_index]];
+        op.wpacked = reinterpret_cast<bf16*>(base + w_off[i]);
+        ConvKernelParams& kp = op.kp;
+        kp.io = P->io_dev;
+        if (op.kind == G_CONV) {
+          Raw& r = P->raws[op.raw];
+          kp.epi = EPI_RAW_STATS; kp.out = r.desc.base; kp.out_C = r.desc.C;
+          kp.stats = r.stats; kp.stats_C = r.C; kp.bias = nullptr;
+        } else if (op.kind == G_CONV_ACT) {
+          const Value& vo = P->values[op.value_out];
+          V2V_REQUIRE(vo.bufs.size() == 1 && P->act_pad_mode[vo.bufs[0]] != PAD_REFLECT, V2V_ERR_UNSUPPORTED,
+                      "conv_act output needs a single zero/none-padded consumer layout");
+          kp.epi = EPI_ACT_BF16; kp.out_act = P->acts[vo.bufs[0]]; kp.out_C = kp.out_act.C;
+        } else {
+          kp.epi = EPI_HEAD_F32;
+          for (int j = 0; j < op.conv.Cout; ++j) {
+            kp.head_slot[j] = op.head[j].slot;
+            kp.head_off[j] = (long long)op.head[j].channel * op.geom.out_h * op.geom.out_w;
+            kp.head_bstride[j] = (long long)op.head[j].dst_C * op.geom.out_h * op.geom.out_w;
+            kp.head_act[j] = op.head[j].act; kp.head_scale[j] = op.head[j].scale;
+          }
+        }
+        if (P->impl == V2V_IMPL_UMMA) {
+          rc = make_tmap_act(&op.tmA, ain, op.geom.TW + op.geom.R - 1, op.geom.TH); if (rc) return rc;
+          rc = make_tmap_w(&op.tmB, op.wpacked, op.Ktotal, op.conv.Cout, kp.BN); if (rc) return rc;
+        }
+        rc = pack_one(op, stream); if (rc) return rc;
+        XOp x; x.kind = X_CONV; x.gop = (int)i;
+        P->xops.push_back(x);
+        if (op.kind == G_CONV && P->impl == V2V_IMPL_SIMT) {
+          XOp s; s.kind = X_RAWSTATS; s.rawd = P->raws[op.raw].desc; s.stats = P->raws[op.raw].stats; s.stats_C = P->raws[op.raw].C;
+          P->xops.push_back(s);
+        }
+        break;
+      }
+      case G_NORM_ACT: {
+        Raw& r = P->raws[op.raw];
+        const GOp& cop = P->gops[r.conv_op];
+        if (op.norm.kind != V2V_NORM_NONE) {
+          XOp f; f.kind = X_FINALIZE;
+          FinalizeParams& fp = f.fin;
+          fp.stats = r.stats; fp.Cs = r.C; fp.C = r.C; fp.N = r.N; fp.tiles_per_img = r.tiles_per_img; fp.num_phases = r.num_phases;
+          fp.count = (double)r.H * r.W; fp.instance = (op.norm.kind == V2V_NORM_INSTANCE);
+          fp.gamma = op.norm.gamma; fp.beta = op.norm.beta; fp.conv_bias = cop.conv.bias;
+          fp.running_mean = op.norm.running_mean; fp.running_var = op.norm.running_var;
+          fp.num_batches_tracked = reinterpret_cast<long long*>(op.norm.num_batches_tracked);
+          fp.momentum = op.norm.momentum; fp.eps = op.norm.eps; fp.scale = r.scale; fp.shift = r.shift;
+          P->xops.push_back(f);
+        } else {
+          V2V_REQUIRE(cop.conv.bias == nullptr, V2V_ERR_UNSUPPORTED, "norm-less conv with bias must use v2v_g_conv_act");
+        }
+        const Value& vo = P->values[op.value_out];
+        for (size_t m = 0; m < vo.bufs.size(); ++m) {
+          XOp a; a.kind = X_APPLY;
+          ApplyParams& ap = a.app;
+          ap.raw = r.desc;
+          ap.scale = op.norm.kind != V2V_NORM_NONE ? r.scale : nullptr; ap.shift = r.shift;
+          ap.act = op.act; ap.slope = op.slope;
+          ap.n_add = 0;
+          for (int k = 0; k < 2; ++k) if (op.add[k] >= 0) ap.add[ap.n_add++] = P->acts[P->values[op.add[k]].bufs[0]];
+          ap.out = P->acts[vo.bufs[m]]; ap.pad_mode = P->act_pad_mode[vo.bufs[m]];
+          P->xops.push_back(a);
+        }
+        break;
+      }
+      case G_EXPORT: {
+        XOp x; x.kind = X_EXPORT; x.exp.io = P->io_dev; x.exp.slot = op.slot; x.exp.in = P->acts[P->values[op.value_in].bufs[0]];
+        P->xops.push_back(x);
+        break;
+      }
+      case G_COMPOSITE: {
+        XOp x; x.kind = X_COMPOSITE; x.comp = op.comp; x.comp.io = P->io_dev;
+        P->xops.push_back(x);
+        break;
+      }
+    }
+  }
+  V2V_CUDA(cudaStreamSynchronize(stream));
+  P->finalized = true;
+  return 0;
+}
+
+int v2v_plan_repack(v2v_plan* P, v2v_stream_t stream_) {
+  V2V_REQUIRE(P && P->finalized, V2V_ERR_STATE, "plan not finalized");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  for (auto& op : P->gops)
+    if (op.kind == G_CONV || op.kind == G_CONV_ACT || op.kind == G_HEAD) { int rc = pack_one(op, stream); if (rc) return rc; }
+  return 0;
+}
+
+int v2v_plan_run(v2v_plan* P, void* const* io_ptrs, int n_io, int use_graph, v2v_stream_t stream_) {
+  V2V_REQUIRE(P && P->finalized, V2V_ERR_STATE, "plan not finalized");
+  V2V_REQUIRE(n_io >= P->n_slots && io_ptrs, V2V_ERR_INVALID, "need %d io pointers, got %d", P->n_slots, n_io);
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  V2V_CUDA(cudaMemcpyAsync(P->io_dev, io_ptrs, sizeof(void*) * P->n_slots, cudaMemcpyHostToDevice, stream));
+  if (!use_graph) {
+    for (const XOp& x : P->xops) { int rc = run_xop(P, x, stream); if (rc) return rc; }
+    return 0;
+  }
+  if (!P->graph_exec) {
+    cudaGraph_t graph;
+    V2V_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    for (const XOp& x : P->xops) { rc = run_xop(P, x, stream); if (rc) break; }
+    cudaError_t e = cudaStreamEndCapture(stream, &graph);
+    if (rc) return rc;
+    V2V_CUDA(e);
+    V2V_CUDA(cudaGraphInstantiate(&P->graph_exec, graph, 0));
+    V2V_CUDA(cudaGraphDestroy(graph));
+  }
+  V2V_CUDA(cudaGraphLaunch(P->graph_exec, stream));
+  return 0;
+}
+
+int v2v_plan_num_kernels(const v2v_plan* P) { return P ? (int)P->xops.size() : 0; }
+double v2v_plan_conv_macs(const v2v_plan* P) {
+  if (!P) return 0.0;
+  if (!P->lowered) lower(const_cast<v2v_plan*>(P));
+  return P->conv_macs;
+}
+int64_t v2v_plan_workspace_bytes(const v2v_plan* P) { return P ? (int64_t)P->arena_bytes : 0; }
+
+int64_t v2v_plan_describe(const v2v_plan* P_, char* buf, int64_t cap) {
+  v2v_plan* P = const_cast<v2v_plan*>(P_);
+  if (!P) return 0;
+  if (!P->lowered && lower(P)) return -1;
+  std::string s = "{\"values\":[";
+  char t[512];
+  for (size_t i = 0; i < P->values.size(); ++i) {
+    const Value& v = P->values[i];
+    snprintf(t, sizeof(t), "%s{\"id\":%zu,\"N\":%d,\"C\":%d,\"H\":%d,\"W\":%d,\"layouts\":[", i ? "," : "", i, v.N, v.C, v.H, v.W);
+    s += t;
+    for (size_t m = 0; m < v.reqs.size(); ++m) {
+      const Req& r = v.reqs[m];
+      snprintf(t, sizeof(t), "%s{\"mode\":%d,\"pads\":[%d,%d,%d,%d],\"parity\":%d}", m ? "," : "", r.mode, r.pads[0], r.pads[1],
+               r.pads[2], r.pads[3], r.parity);
+      s += t;
+    }
+    s += "]}";
+  }
+  s += "],\"convs\":[";
+  bool first = true;
+  for (const GOp& op : P->gops) {
+    if (!(op.kind == G_CONV || op.kind == G_CONV_ACT || op.kind == G_HEAD)) continue;
+    const ConvGeom& g = op.geom;
+    snprintf(t, sizeof(t),
+             "%s{\"kind\":%d,\"Cin\":%d,\"Cout\":%d,\"k\":[%d,%d],\"stride\":%d,\"transposed\":%d,\"in\":%d,\"TH\":%d,\"TW\":%d,"
+             "\"R\":%d,\"groups\":%d,\"phases\":%d,\"grid\":[%d,%d],\"out\":[%d,%d]}",
+             first ? "" : ",", (int)op.kind, op.conv.Cin, op.conv.Cout, op.conv.kh, op.conv.kw, op.conv.stride, op.conv.transposed,
+             op.value_in, g.TH, g.TW, g.R, g.n_groups, g.n_phases, g.grid_h, g.grid_w, g.out_h, g.out_w);
+    s += t;
+    first = false;
+  }
+  snprintf(t, sizeof(t), "],\"conv_macs\":%.0f,\"n_slots\":%d}", P->conv_macs, P->n_slots);
+  s += t;
+  if (buf && cap > 0) {
+    size_t n = std::min((size_t)cap - 1, s.size());
+    memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  return (int64_t)s.size() + 1;
+}
+
+int v2v_conv_tap_table(const v2v_conv_desc* conv, int H, int W, int allow_reuse, int* n_groups, int* R, int* plane,
+                       int* dy, int* dx, int* tap0, int* n_phases, int* phase_begin, int* oy_add, int* ox_add,
+                       int* pads, int* parity, int* grid_hw, int* out_hw, int* mul) {
+  V2V_REQUIRE(conv, V2V_ERR_INVALID, "null conv");
+  ConvGeom g;
+  int rc = conv_geometry(*conv, H, W, allow_reuse != 0, &g);
+  if (rc) return rc;
+  *n_groups = g.n_groups; *R = g.R; *n_phases = g.n_phases; *parity = g.parity; *mul = g.mul;
+  for (int i = 0; i < g.n_groups; ++i) { plane[i] = g.groups[i].plane; dy[i] = g.groups[i].dy; dx[i] = g.groups[i].dx; tap0[i] = g.groups[i].tap0; }
+  for (int i = 0; i < g.n_phases; ++i) { phase_begin[i] = g.phases[i].group_begin; oy_add[i] = g.phases[i].oy_add; ox_add[i] = g.phases[i].ox_add; }
+  phase_begin[g.n_phases] = g.n_groups;
+  memcpy(pads, g.pads, sizeof(g.pads));
+  grid_hw[0] = g.grid_h; grid_hw[1] = g.grid_w; out_hw[0] = g.out_h; out_hw[1] = g.out_w;
+  return 0;
+}
+
+}  // extern "C"

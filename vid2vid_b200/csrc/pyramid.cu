@@ -1,0 +1,104 @@
+// HBM-bound helpers of the Vid2VidModelG level (fp32 NCHW, coalesced along x):
+//   onehot_edges : label ids + instance ids -> one-hot(+edge) input tensor
+//                  (Vid2VidModelG.encode_input, models/vid2vid_model_G.py:86-112; BaseModel.get_edges,
+//                   models/base_model.py:146-152)
+//   avgpool3s2   : AvgPool2d(3, stride 2, pad 1, count_include_pad=False) pyramid level
+//                  (BaseModel.build_pyr, models/base_model.py:122-134; networks.py:400,652)
+//   fg_mask      : clamp(sum of fg label channels, 0, 1)  (compute_mask, vid2vid_model_G.py:322-330)
+#include "ptx.cuh"
+#include "v2v_internal.h"
+
+namespace v2v {
+
+// out (F, label_nc + use_inst, H, W) ; labels / inst (F, H, W) float ids ; F = b * t frames
+__global__ void onehot_edges_kernel(const float* __restrict__ labels, const float* __restrict__ inst,
+                                    float* __restrict__ out, int F, int label_nc, int use_inst, int H, int W) {
+  const size_t HW = (size_t)H * W, total = (size_t)F * HW;
+  const int Cout = label_nc + (use_inst ? 1 : 0);
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int f = (int)(idx / HW);
+    const size_t pix = idx - (size_t)f * HW;
+    const int y = (int)(pix / W), x = (int)(pix - (size_t)y * W);
+    const int lab = (int)labels[idx];
+    float* o = out + (size_t)f * Cout * HW + pix;
+    for (int c = 0; c < label_nc; ++c) o[(size_t)c * HW] = (c == lab) ? 1.f : 0.f;
+    if (use_inst) {
+      const float* ip = inst + (size_t)f * HW;
+      const float v = ip[pix];
+      bool e = false;
+      if (x > 0) e |= (ip[pix - 1] != v);
+      if (x < W - 1) e |= (ip[pix + 1] != v);
+      if (y > 0) e |= (ip[pix - W] != v);
+      if (y < H - 1) e |= (ip[pix + W] != v);
+      o[(size_t)label_nc * HW] = e ? 1.f : 0.f;
+    }
+  }
+}
+
+// in (P, H, W) -> out (P, H/2, W/2) planes
+__global__ void avgpool3s2_kernel(const float* __restrict__ in, float* __restrict__ out, int P, int H, int W) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const size_t total = (size_t)P * Ho * Wo;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int xo = (int)(idx % Wo);
+    const int yo = (int)((idx / Wo) % Ho);
+    const size_t pl = idx / ((size_t)Wo * Ho);
+    const float* ip = in + pl * (size_t)H * W;
+    float s = 0.f;
+    int cnt = 0;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y = 2 * yo + dy;
+      if (y < 0 || y >= H) continue;
+#pragma unroll
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int x = 2 * xo + dx;
+        if (x < 0 || x >= W) continue;
+        s += ip[(size_t)y * W + x];
+        ++cnt;
+      }
+    }
+    out[idx] = s / (float)cnt;
+  }
+}
+
+// real_A (B, T, C, H, W) -> mask (B, 1, H, W) for frame index t
+struct FgLabels { int v[16]; };
+__global__ void fg_mask_kernel(const float* __restrict__ real_A, float* __restrict__ mask, int B, int T, int C, int H,
+                               int W, int t, FgLabels labels, int n_labels) {
+  const size_t HW = (size_t)H * W, total = (size_t)B * HW;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int b = (int)(idx / HW);
+    const size_t pix = idx - (size_t)b * HW;
+    float s = 0.f;
+    for (int i = 0; i < n_labels; ++i) s += real_A[(((size_t)b * T + t) * C + labels.v[i]) * HW + pix];
+    mask[idx] = fminf(fmaxf(s, 0.f), 1.f);
+  }
+}
+
+static inline int grid1d(size_t total) {
+  size_t b = (total + 255) / 256;
+  const size_t cap = 148 * 16;
+  return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+cudaError_t launch_onehot_edges(const float* labels, const float* inst, float* out, int F, int label_nc, int use_inst,
+                                int H, int W, cudaStream_t s) {
+  onehot_edges_kernel<<<grid1d((size_t)F * H * W), 256, 0, s>>>(labels, inst, out, F, label_nc, use_inst, H, W);
+  return cudaGetLastError();
+}
+cudaError_t launch_avgpool3s2(const float* in, float* out, int P, int H, int W, cudaStream_t s) {
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  avgpool3s2_kernel<<<grid1d((size_t)P * Ho * Wo), 256, 0, s>>>(in, out, P, H, W);
+  return cudaGetLastError();
+}
+cudaError_t launch_fg_mask(const float* real_A, float* mask, int B, int T, int C, int H, int W, int t,
+                           FgLabels labels, int n_labels, cudaStream_t s) {
+  fg_mask_kernel<<<grid1d((size_t)B * H * W), 256, 0, s>>>(real_A, mask, B, T, C, H, W, t, labels, n_labels);
+  return cudaGetLastError();
+}
+
+}  // namespace v2v

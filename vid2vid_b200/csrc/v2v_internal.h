@@ -1,0 +1,175 @@
+// Internal (non-ABI) declarations shared by the kernels and the plan runtime.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+namespace v2v {
+
+typedef __nv_bfloat16 bf16;
+
+// ---------------------------------------------------------------------------------------
+// Activation buffer: NHWC bf16 with a materialised halo, optionally split into the four
+// (row parity, column parity) planes so that a stride-2 consumer reads unit-stride boxes.
+//   padded coords  yp = y + pad_t, xp = x + pad_l   (y, x may lie in the halo)
+//   parity == 0 :  [n][0][yp][xp][c]          plane dims Hp x Wp
+//   parity == 1 :  [n][(yp&1)*2 + (xp&1)][yp>>1][xp>>1][c]   plane dims Hp x Wp (= ceil(padded/2))
+// C is the padded channel count (multiple of 64; channels >= Cvalid are zero).
+struct ActDesc {
+  bf16* base;
+  int N, H, W;          // logical (unpadded) extent
+  int C;                // padded channels (multiple of 64)
+  int Cvalid;
+  int pad_t, pad_l, pad_b, pad_r;
+  int parity;           // 0 / 1
+  int P, Hp, Wp;        // planes and plane extent
+  __host__ __device__ size_t elems() const { return (size_t)N * P * Hp * Wp * C; }
+  __host__ __device__ size_t offset(int n, int y, int x) const {   // element offset of channel 0
+    int yp = y + pad_t, xp = x + pad_l;
+    if (parity) {
+      int pl = ((yp & 1) << 1) | (xp & 1);
+      return ((((size_t)n * 4 + pl) * Hp + (yp >> 1)) * Wp + (xp >> 1)) * C;
+    }
+    return (((size_t)n * Hp + yp) * Wp + xp) * C;
+  }
+};
+
+// Raw conv output: dense NHWC bf16, C = channel stride (multiple of 8).
+struct RawDesc {
+  bf16* base;
+  int N, H, W, C, Cvalid;
+  __host__ __device__ size_t elems() const { return (size_t)N * H * W * C; }
+};
+
+enum PadMode { PAD_NONE = 0, PAD_ZERO = 1, PAD_REFLECT = 2 };
+enum ActKind { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };
+enum EpiMode { EPI_RAW_STATS = 0, EPI_HEAD_F32 = 1, EPI_ACT_BF16 = 2 };
+
+#define V2V_MAX_TAPS 64
+#define V2V_MAX_PHASES 4
+#define V2V_MAX_HEAD 16
+
+// One "patch group": an A box (plane, dy, dx) that serves `R` consecutive taps (shifted by one
+// pixel = one 128-byte smem row each).  tap0 = index of the first tap in the packed weight matrix.
+struct ConvGroup {
+  int8_t plane, dy, dx, pad_;
+  int16_t tap0, pad2_;
+};
+
+struct ConvPhase {
+  int group_begin, group_end;   // range in ConvKernelParams::groups
+  int oy_add, ox_add;           // output coordinate offset (transposed-conv sub-pixel phase)
+};
+
+struct ConvKernelParams {
+  // problem
+  int N, tiles_x, tiles_y, TH, TW;   // M tile = TH x TW output-grid pixels (TH*TW == 128)
+  int grid_h, grid_w;                // extent of the output grid this launch iterates over
+  int Cout, BN;                      // valid output channels, N tile (16/32/64/128)
+  int Cp, cblocks;                   // padded input channels, Cp/64
+  int R;                             // taps served per A patch (1 = none)
+  int a_slot_bytes, b_slot_bytes, SA, SB;
+  int num_phases;
+  ConvPhase phases[V2V_MAX_PHASES];
+  ConvGroup groups[V2V_MAX_TAPS];
+  // epilogue
+  int epi;                           // EpiMode
+  int oy_mul, ox_mul;                // output coord = grid coord * mul + phase add
+  int out_H, out_W, out_C;           // destination extent / channel stride
+  void* out;                         // EPI_RAW_STATS: bf16 NHWC raw; EPI_ACT_BF16: ActDesc base (see out_act)
+  ActDesc out_act;                   // EPI_ACT_BF16 destination
+  float* stats;                      // [tile rows][2][stats_C] partial (sum, sumsq); may be null
+  int stats_C;
+  const float* bias;                 // may be null
+  // EPI_HEAD_F32: per output channel destination = io[head_slot] + head_off (+ n * head_bstride),
+  // activation and scale.  Caller pointers are read from the device IO table at run time.
+  void* const* io;
+  int head_slot[V2V_MAX_HEAD];
+  long long head_off[V2V_MAX_HEAD];
+  long long head_bstride[V2V_MAX_HEAD];
+  int head_act[V2V_MAX_HEAD];
+  float head_scale[V2V_MAX_HEAD];
+  float lrelu_slope;
+  int act;                           // EPI_ACT_BF16 activation
+};
+
+// kernel launchers (defined in the .cu files); all enqueue on `stream` and return cudaError_t
+cudaError_t launch_conv_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p,
+                             cudaStream_t stream);
+cudaError_t launch_conv_simt(const ActDesc& in, const bf16* wpacked, int Ktotal, const ConvKernelParams& p,
+                             cudaStream_t stream);
+
+
+// ---------------------------------------------------------------------------------------
+struct FinalizeParams {
+  const float* stats;      // [rows][2][Cs]
+  int Cs, C;               // stats channel stride, channels
+  int N, tiles_per_img, num_phases;
+  double count;            // elements per channel per image
+  int instance;            // 0 = batch statistics over N, 1 = per-image statistics
+  const float* gamma;      // may be null (-> 1)
+  const float* beta;       // may be null (-> 0)
+  const float* conv_bias;  // folded into running_mean only (cancels in the normalised output)
+  float* running_mean;     // may be null
+  float* running_var;
+  long long* num_batches_tracked;
+  float momentum, eps;
+  float* scale;            // [N][C]
+  float* shift;            // [N][C]
+};
+
+struct ApplyParams {
+  RawDesc raw;
+  const float* scale;      // [N][raw.Cvalid]  (null -> identity)
+  const float* shift;
+  int act; float slope;
+  int n_add;
+  ActDesc add[2];          // interior is read (any padding / parity)
+  ActDesc out;
+  int pad_mode;            // PadMode of out's halo
+};
+
+// fp32 NCHW (caller tensor, read through the IO table) -> halo-padded NHWC bf16
+struct ImportParams {
+  const void* const* io;   // device IO pointer table
+  int slot;
+  int c_off, C_src;        // channel window [c_off, c_off + out.Cvalid) of a tensor with C_src channels
+  ActDesc out;
+  int pad_mode;
+};
+// halo-padded NHWC bf16 interior -> fp32 NCHW (caller tensor)
+struct ExportParams {
+  void* const* io;
+  int slot;
+  ActDesc in;
+};
+
+struct PackParams {
+  const float* w;          // torch layout: conv [Cout][Cin][kh][kw]; transposed conv [Cin][Cout][kh][kw]
+  int transposed;
+  int Cout, Cin, kh, kw;
+  int Cp, ntaps;
+  int8_t tap_ky[V2V_MAX_TAPS], tap_kx[V2V_MAX_TAPS];   // filter coordinates of packed tap t
+  bf16* out;               // [Cout][ntaps * Cp]
+};
+
+// fused warp + soft-mask blend + fg composite (models/networks.py:219-221,228-230)
+struct CompositeParams {
+  void* const* io;
+  int s_raw, s_flow, s_weight, s_prev, s_fg, s_mask, s_final;   // IO slots; -1 = absent
+  int prev_C;              // img_prev channel count (last 3 are warped)
+  int N, H, W;
+  int align_corners;
+  int use_warp;            // 0: img_final = img_raw (use_raw_only / no_flow)
+};
+
+cudaError_t launch_raw_stats(const RawDesc& raw, float* stats, int stats_C, cudaStream_t stream);
+cudaError_t launch_stats_finalize(const FinalizeParams& p, cudaStream_t stream);
+cudaError_t launch_norm_apply(const ApplyParams& p, cudaStream_t stream);
+cudaError_t launch_import_nchw(const ImportParams& p, cudaStream_t stream);
+cudaError_t launch_export_nchw(const ExportParams& p, cudaStream_t stream);
+cudaError_t launch_pack_weights(const PackParams& p, cudaStream_t stream);
+cudaError_t launch_composite(const CompositeParams& p, cudaStream_t stream);
+
+}  // namespace v2v

@@ -1,0 +1,137 @@
+"""Vid2VidModelG on the B200 engine: same public methods and per-clip state as
+models/vid2vid_model_G.py (initialize / encode_input / inference / generate_frame_infer /
+generate_first_frame / compute_mask / build_pyr), with every tensor op routed to libv2v_b200.so.
+
+Inference only in this round (the reference's own `inference` runs under torch.no_grad,
+vid2vid_model_G.py:199); the training forward needs the backward kernels.
+"""
+import os
+
+import torch
+import torch.nn as nn
+
+from . import networks, ops
+
+
+class Vid2VidModelG(nn.Module):
+    def name(self):
+        return 'Vid2VidModelG'
+
+    def initialize(self, opt):
+        """vid2vid_model_G.py:19-53 (inference branch)."""
+        self.opt = opt
+        self.gpu_ids = opt.gpu_ids
+        self.isTrain = opt.isTrain
+        self.n_scales = opt.n_scales_spatial
+        self.use_single_G = opt.use_single_G
+        if getattr(opt, 'openpose_only', False):
+            opt.no_flow = True
+        dev = torch.device('cuda', self.gpu_ids[0] if len(self.gpu_ids) else torch.cuda.current_device())
+        self.device_ = dev
+        for s in range(self.n_scales):
+            setattr(self, 'netG' + str(s), networks.build_netG(opt, s).to(dev))
+        self.netG_i = self.load_single_G() if self.use_single_G else None
+        self.fake_B_prev = None
+        return self
+
+    # ------------------------------------------------------------------ first-frame generator
+    def load_single_G(self):
+        """vid2vid_model_G.py:261-288.  The architecture per loadSize is the reference's; weights are
+        loaded from checkpoints/label2city_single/ when that file exists, else left at their random
+        initialisation (synthetic benchmarking has no checkpoints)."""
+        opt = self.opt
+        if 'City' not in opt.dataroot:
+            raise ValueError('Single image generator does not exist')
+        single_path = 'checkpoints/label2city_single/'
+        if opt.loadSize == 512:
+            load_path, netG = single_path + 'latest_net_G_512.pth', networks.define_G(35, 3, 0, 64, 'global', 3, 'instance', 0, [], opt)
+        elif opt.loadSize == 1024:
+            load_path, netG = single_path + 'latest_net_G_1024.pth', networks.define_G(35, 3, 0, 64, 'global', 4, 'instance', 0, [], opt)
+        elif opt.loadSize == 2048:
+            load_path, netG = single_path + 'latest_net_G_2048.pth', networks.define_G(35, 3, 0, 32, 'local', 4, 'instance', 0, [], opt)
+        else:
+            raise ValueError('Single image generator does not exist')
+        if os.path.exists(load_path):
+            netG.load_state_dict(torch.load(load_path))
+        return netG.to(self.device_)
+
+    # ------------------------------------------------------------------ tensor helpers (CUDA kernels)
+    def encode_input(self, input_map, real_image, inst_map=None):
+        """vid2vid_model_G.py:86-112."""
+        size = input_map.size()
+        self.bs, tG, self.height, self.width = size[0], size[1], size[3], size[4]
+        input_map = input_map.to(self.device_, torch.float32)
+        if self.opt.label_nc != 0:
+            inst = inst_map.to(self.device_, torch.float32) if self.opt.use_instance else None
+            input_map = ops.onehot_edges(input_map, inst, self.opt.label_nc, self.opt.use_instance)
+        elif self.opt.use_instance:
+            raise NotImplementedError('use_instance without label_nc')
+        if real_image is not None:
+            real_image = real_image.to(self.device_, torch.float32)
+        return input_map, real_image, None
+
+    def build_pyr(self, tensor):
+        """base_model.py:122-134."""
+        if tensor is None:
+            return [None] * self.n_scales
+        pyr = [tensor]
+        for _ in range(1, self.n_scales):
+            pyr.append(ops.avgpool3s2(pyr[-1]))
+        return pyr
+
+    def compute_mask(self, real_As, ts, te=None):
+        """vid2vid_model_G.py:322-330 (single frame)."""
+        assert te is None or te == ts + 1
+        return ops.fg_mask(real_As, ts, list(self.opt.fg_labels))
+
+    # ------------------------------------------------------------------ inference
+    def inference(self, input_A, input_B, inst_A):
+        """vid2vid_model_G.py:198-209."""
+        with torch.no_grad():
+            real_A, real_B, _ = self.encode_input(input_A, input_B, inst_A)
+            self.is_first_frame = self.fake_B_prev is None
+            if self.is_first_frame:
+                self.fake_B_prev = self.generate_first_frame(real_A, real_B)
+            real_A = self.build_pyr(real_A)
+            self.fake_B_feat = self.flow_feat = self.fake_B_fg_feat = None
+            for s in range(self.n_scales):
+                fake_B = self.generate_frame_infer(real_A[self.n_scales - 1 - s], s)
+        return fake_B, real_A[0][0, -1]
+
+    def generate_frame_infer(self, real_A, s):
+        """vid2vid_model_G.py:211-229."""
+        tG = self.opt.n_frames_G
+        _, _, _, h, w = real_A.size()
+        si = self.n_scales - 1 - s
+        netG_s = getattr(self, 'netG' + str(s))
+        real_As_reshaped = real_A[0, :tG].reshape(1, -1, h, w)
+        fake_B_prevs_reshaped = self.fake_B_prev[si].reshape(1, -1, h, w)
+        mask_F = self.compute_mask(real_A, tG - 1)[0] if self.opt.fg else None
+        use_raw_only = self.opt.no_first_img and self.is_first_frame
+        fake_B, flow, weight, fake_B_raw, self.fake_B_feat, self.flow_feat, self.fake_B_fg_feat = netG_s.forward(
+            real_As_reshaped, fake_B_prevs_reshaped, mask_F, self.fake_B_feat, self.flow_feat, self.fake_B_fg_feat,
+            use_raw_only)
+        self.fake_B_prev[si] = torch.cat([self.fake_B_prev[si][1:, ...], fake_B])
+        return fake_B
+
+    def generate_first_frame(self, real_A, real_B, pool_map=None):
+        """vid2vid_model_G.py:231-251."""
+        tG = self.opt.n_frames_G
+        if self.opt.no_first_img:
+            fake_B_prev = torch.zeros(self.bs, tG - 1, self.opt.output_nc, self.height, self.width, device=self.device_)
+        elif self.opt.isTrain or self.opt.use_real_img:
+            fake_B_prev = real_B[:, :(tG - 1), ...]
+        elif self.opt.use_single_G:
+            if self.opt.use_instance:
+                real_A = real_A[:, :, :self.opt.label_nc, :, :]
+            frames = [self.netG_i.forward(real_A[:, i].contiguous(), None).unsqueeze(1) for i in range(tG - 1)]
+            fake_B_prev = torch.cat(frames, dim=1)
+        else:
+            raise ValueError('Please specify the method for generating the first frame')
+        fake_B_prev = self.build_pyr(fake_B_prev)
+        if not self.opt.isTrain:
+            fake_B_prev = [B[0] for B in fake_B_prev]
+        return fake_B_prev
+
+    def forward(self, input_A, input_B, inst_A, fake_B_prev, dummy_bs=0):
+        raise NotImplementedError('training forward needs the backward kernels (round 2); no PyTorch fallback')

@@ -1,0 +1,567 @@
+"""B200 drop-ins for the generator / discriminator modules of models/networks.py.
+
+Each class keeps the reference's constructor signature, attribute names and state_dict keys
+(index-based Sequential keys included, e.g. `model_down_img.4.weight`), so reference checkpoints load
+unchanged (models/base_model.py:63-107) -- the torch.nn layers below are *parameter containers*
+only.  forward() never calls them: it describes the network once per input shape to the plan
+runtime (vid2vid_b200/plan.py -> libv2v_b200.so), which runs hand-written sm_100a kernels.
+There is no PyTorch/cuDNN fallback.
+
+Norm semantics: Batch/InstanceNorm always use the statistics of the current
+tensor, as the reference does at inference because it never calls .eval() on G/D.
+"""
+import copy
+import functools
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from .plan import Plan, conv_desc, norm_desc
+
+
+# ------------------------------------------------------------------------------------ init / factories
+def weights_init(m):
+    """models/networks.py:15-21."""
+    name = m.__class__.__name__
+    if name.find('Conv') != -1 and hasattr(m, 'weight'):
+        m.weight.data.normal_(0.0, 0.02)
+    elif name.find('BatchNorm2d') != -1:
+        m.weight.data.normal_(1.0, 0.02)
+        m.bias.data.fill_(0)
+
+
+def get_norm_layer(norm_type='instance'):
+    """models/networks.py:23-30."""
+    if norm_type == 'batch':
+        return functools.partial(nn.BatchNorm2d, affine=True)
+    if norm_type == 'instance':
+        return functools.partial(nn.InstanceNorm2d, affine=False, track_running_stats=True)
+    raise NotImplementedError('normalization layer [%s] is not found' % norm_type)
+
+
+def define_G(input_nc, output_nc, prev_output_nc, ngf, which_model_netG, n_downsampling, norm, scale, gpu_ids=[],
+             opt=[]):
+    """models/networks.py:32-59 (face-only `*_with_features` / `encoder` variants are out of scope)."""
+    norm_layer = get_norm_layer(norm_type=norm)
+    if which_model_netG == 'global':
+        netG = GlobalGenerator(input_nc, output_nc, ngf, n_downsampling, opt.n_blocks, norm_layer)
+    elif which_model_netG == 'local':
+        netG = LocalEnhancer(input_nc, output_nc, ngf, n_downsampling, opt.n_blocks, opt.n_local_enhancers,
+                             opt.n_blocks_local, norm_layer)
+    elif which_model_netG == 'composite':
+        netG = CompositeGenerator(opt, input_nc, output_nc, prev_output_nc, ngf, n_downsampling, opt.n_blocks,
+                                  opt.fg, opt.no_flow, norm_layer)
+    elif which_model_netG == 'compositeLocal':
+        netG = CompositeLocalGenerator(opt, input_nc, output_nc, prev_output_nc, ngf, n_downsampling,
+                                       opt.n_blocks_local, opt.fg, opt.no_flow, norm_layer, scale=scale)
+    else:
+        raise NotImplementedError('Generator model name [%s] is not recognized' % which_model_netG)
+    if len(gpu_ids) > 0:
+        netG.cuda(gpu_ids[0])
+    netG.apply(weights_init)
+    return netG
+
+
+def define_D(input_nc, ndf, n_layers_D, norm='instance', num_D=1, getIntermFeat=False, gpu_ids=[]):
+    """models/networks.py:61-68."""
+    netD = MultiscaleDiscriminator(input_nc, ndf, n_layers_D, get_norm_layer(norm), num_D, getIntermFeat)
+    if len(gpu_ids) > 0:
+        netD.cuda(gpu_ids[0])
+    netD.apply(weights_init)
+    return netD
+
+
+# ------------------------------------------------------------------------------------ layer containers
+def _stem(cin, cout, norm_layer):
+    return [nn.ReflectionPad2d(3), nn.Conv2d(cin, cout, kernel_size=7, padding=0), norm_layer(cout), nn.ReLU(True)]
+
+
+def _down(cin, cout, norm_layer):
+    return [nn.Conv2d(cin, cout, kernel_size=3, stride=2, padding=1), norm_layer(cout), nn.ReLU(True)]
+
+
+def _up(cin, cout, norm_layer):
+    return [nn.ConvTranspose2d(cin, cout, kernel_size=3, stride=2, padding=1, output_padding=1), norm_layer(cout),
+            nn.ReLU(True)]
+
+
+def _head(cin, cout, act=None):
+    return [nn.ReflectionPad2d(3), nn.Conv2d(cin, cout, kernel_size=7, padding=0)] + ([act] if act else [])
+
+
+class ResnetBlock(nn.Module):
+    """Parameter container with the keys of models/networks.py:554-593 (`conv_block.{1,2,5,6}`)."""
+
+    def __init__(self, dim, padding_type, norm_layer, activation=nn.ReLU(True), use_dropout=False):
+        super().__init__()
+        if padding_type != 'reflect' or use_dropout:
+            raise NotImplementedError('only reflect padding without dropout is used by vid2vid')
+        self.conv_block = nn.Sequential(nn.ReflectionPad2d(1), nn.Conv2d(dim, dim, kernel_size=3, padding=0),
+                                        norm_layer(dim), activation,
+                                        nn.ReflectionPad2d(1), nn.Conv2d(dim, dim, kernel_size=3, padding=0),
+                                        norm_layer(dim))
+
+
+# ------------------------------------------------------------------------------------ lowering helpers
+_ACTS = {nn.ReLU: (L.ACT_RELU, 0.0), nn.Tanh: (L.ACT_TANH, 0.0), nn.Sigmoid: (L.ACT_SIGMOID, 0.0)}
+
+
+def _act_of(m):
+    if isinstance(m, nn.LeakyReLU):
+        return L.ACT_LRELU, m.negative_slope
+    for k, v in _ACTS.items():
+        if isinstance(m, k):
+            return v
+    return None
+
+
+def _units(mods):
+    """Group a flat layer list into units: ('conv', conv, pad_mode, pad, norm, act, slope) | ('res', block)."""
+    units, i, pend = [], 0, None
+    mods = list(mods)
+    while i < len(mods):
+        m = mods[i]
+        if isinstance(m, nn.ReflectionPad2d):
+            pend = m.padding[0]
+            i += 1
+        elif isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+            norm, act, slope = None, L.ACT_NONE, 0.0
+            j = i + 1
+            if j < len(mods) and isinstance(mods[j], (nn.BatchNorm2d, nn.InstanceNorm2d)):
+                norm = mods[j]
+                j += 1
+            if j < len(mods) and _act_of(mods[j]) is not None:
+                act, slope = _act_of(mods[j])
+                j += 1
+            if pend is not None:
+                units.append(('conv', m, L.PAD_REFLECT, pend, norm, act, slope))
+            else:
+                units.append(('conv', m, L.PAD_ZERO, None, norm, act, slope))
+            pend, i = None, j
+        elif isinstance(m, ResnetBlock):
+            units.append(('res', m))
+            i += 1
+        else:
+            raise NotImplementedError('cannot lower layer %r' % (m,))
+    return units
+
+
+def emit_seq(plan, mods, v, final_adds=(), defer_last=False):
+    """Describe a Sequential on `plan` starting from value `v`.  `final_adds` are value ids summed
+    into the last unit's output (branch merges / coarse-feature skips are fused into that unit's
+    normalise pass).  With defer_last the last unit's normalise step is returned as a closure
+    finish(adds) -> value so the caller can emit it more than once with different addends."""
+    units = _units(mods)
+    finish = None
+    for k, u in enumerate(units):
+        last = k == len(units) - 1
+        adds = tuple(final_adds) if last else ()
+        if u[0] == 'conv':
+            _, conv, pmode, pad, norm, act, slope = u
+            desc = conv_desc(conv, pmode, pad)
+            if norm is None:
+                if adds or (last and defer_last):
+                    raise NotImplementedError('addends need a normalised unit')
+                v = plan.conv_act(v, desc, act, slope)
+            else:
+                raw = plan.conv(v, desc)
+                nd = norm_desc(norm)
+                if last and defer_last:
+                    finish = (lambda raw=raw, nd=nd, act=act, slope=slope: (lambda a: plan.norm_act(raw, nd, act, slope, a)))()
+                else:
+                    v = plan.norm_act(raw, nd, act, slope, adds)
+        else:
+            cb = u[1].conv_block
+            raw1 = plan.conv(v, conv_desc(cb[1], L.PAD_REFLECT, 1))
+            h = plan.norm_act(raw1, norm_desc(cb[2]), L.ACT_RELU, 0.0)
+            raw2 = plan.conv(h, conv_desc(cb[5], L.PAD_REFLECT, 1))
+            nd = norm_desc(cb[6])
+            if last and defer_last:
+                finish = (lambda raw2=raw2, nd=nd, v0=v: (lambda a: plan.norm_act(raw2, nd, L.ACT_NONE, 0.0, (v0,) + tuple(a))))()
+            else:
+                v = plan.norm_act(raw2, nd, L.ACT_NONE, 0.0, (v,) + adds)
+    if defer_last:
+        if finish is None:
+            raise NotImplementedError('defer_last on an empty sequence')
+        return finish
+    return v
+
+
+def emit_head(plan, mods, v, dst):
+    """[ReflectionPad2d(3), Conv2d 7x7, (Tanh|Sigmoid)] -> fp32 NCHW planes of caller tensor slot `dst`
+    = (slot, dst_C, scale)."""
+    (u,) = _units(mods)
+    _, conv, pmode, pad, norm, act, slope = u
+    assert norm is None
+    slot, dst_c, scale = dst
+    plan.head(v, conv_desc(conv, pmode, pad), [(slot, j, dst_c, act, scale) for j in range(conv.out_channels)])
+
+
+class _Planned(nn.Module):
+    """Caches one plan per input-shape key; re-packs weights when parameters were modified in place
+    and rebuilds when their storage moved (.cuda(), .to())."""
+
+    align_corners = False   # installed-PyTorch grid_sample default; True = PyTorch-0.4 semantics (App. B #2)
+    use_cuda_graph = True
+
+    def _plans(self):
+        if '_plan_cache' not in self.__dict__:
+            self.__dict__['_plan_cache'] = {}
+        return self.__dict__['_plan_cache']
+
+    def _signature(self):
+        ptrs, ver = 0, 0
+        for t in list(self.parameters()) + list(self.buffers()):
+            ptrs = (ptrs * 1000003 + t.data_ptr()) & 0xFFFFFFFFFFFF
+            ver += t._version
+        return ptrs, ver
+
+    def _get_plan(self, key, device, build):
+        ptrs, ver = self._signature()
+        ent = self._plans().get(key)
+        if ent is not None and ent['ptrs'] != ptrs:
+            ent = None
+        if ent is None:
+            plan = Plan(device.index if device.index is not None else torch.cuda.current_device())
+            build(plan)
+            plan.finalize()
+            ent = {'plan': plan, 'ptrs': ptrs, 'ver': ver}
+            self._plans()[key] = ent
+        elif ent['ver'] != ver:
+            ent['plan'].repack()
+            ent['ver'] = ver
+        return ent['plan']
+
+    def _bump_versions_done(self, key):
+        # running stats are updated in place by our kernels (not through torch), versions unchanged
+        pass
+
+    @staticmethod
+    def _require_cuda(*ts):
+        for t in ts:
+            if t is not None and (not t.is_cuda or t.dtype != torch.float32):
+                raise RuntimeError('vid2vid_b200 modules run on CUDA fp32 tensors only (no CPU fallback)')
+
+    def conv_macs(self, *shape_key):
+        """Algorithmic conv MACs of one forward for the given input shape (host-only; no GPU needed)."""
+        plan = Plan(0)
+        self._describe(plan, *shape_key)
+        return plan.conv_macs
+
+
+# IO slots of the composite generators
+S_IN, S_PREV, S_MASK, S_FINAL, S_FLOW, S_W, S_RAW, S_IMGF, S_FLOWF, S_FGF, S_FG, S_CI, S_CF, S_CG = range(14)
+
+
+class CompositeGenerator(_Planned):
+    """models/networks.py:117-232."""
+
+    def __init__(self, opt, input_nc, output_nc, prev_output_nc, ngf, n_downsampling, n_blocks, use_fg_model=False,
+                 no_flow=False, norm_layer=nn.BatchNorm2d, padding_type='reflect'):
+        assert n_blocks >= 0
+        super().__init__()
+        self.opt = opt
+        self.n_downsampling = n_downsampling
+        self.use_fg_model = use_fg_model
+        self.no_flow = no_flow
+        self.input_nc, self.output_nc, self.prev_output_nc = input_nc, output_nc, prev_output_nc
+        nd, mult = n_downsampling, 2 ** n_downsampling
+        rb = lambda c: ResnetBlock(c, padding_type=padding_type, activation=nn.ReLU(True), norm_layer=norm_layer)
+
+        if use_fg_model:
+            c = ngf // 2 if nd > 2 else ngf
+            indv_down = _stem(input_nc, c, norm_layer)
+            for i in range(nd):
+                indv_down += _down(c * 2 ** i, c * 2 ** (i + 1), norm_layer)
+            indv_up = []
+            for i in range(nd):
+                indv_up += _up(c * 2 ** (nd - i), c * 2 ** (nd - i) // 2, norm_layer)
+            self.indv_down = nn.Sequential(*indv_down)
+            self.indv_res = nn.Sequential(*[rb(c * mult) for _ in range(n_blocks)])
+            self.indv_up = nn.Sequential(*indv_up)
+            self.indv_final = nn.Sequential(*_head(c, output_nc, nn.Tanh()))
+
+        down_seg = _stem(input_nc, ngf, norm_layer)
+        for i in range(nd):
+            down_seg += _down(ngf * 2 ** i, ngf * 2 ** (i + 1), norm_layer)
+        down_seg += [rb(ngf * mult) for _ in range(n_blocks - n_blocks // 2)]
+        down_img = _stem(prev_output_nc, ngf, norm_layer) + copy.deepcopy(down_seg[4:])
+        res_img = [rb(ngf * mult) for _ in range(n_blocks // 2)]
+        up_img = []
+        for i in range(nd):
+            up_img += _up(ngf * 2 ** (nd - i), ngf * 2 ** (nd - i) // 2, norm_layer)
+
+        self.model_down_seg = nn.Sequential(*down_seg)
+        self.model_down_img = nn.Sequential(*down_img)
+        self.model_res_img = nn.Sequential(*res_img)
+        self.model_up_img = nn.Sequential(*up_img)
+        self.model_final_img = nn.Sequential(*_head(ngf, output_nc, nn.Tanh()))
+        if not no_flow:
+            self.model_res_flow = copy.deepcopy(self.model_res_img)
+            self.model_up_flow = copy.deepcopy(self.model_up_img)
+            self.model_final_flow = nn.Sequential(*_head(ngf, 2))
+            self.model_final_w = nn.Sequential(*_head(ngf, 1, nn.Sigmoid()))
+
+    flow_multiplier = 20.0
+
+    def _describe(self, plan, N, H, W, use_raw_only=False):
+        v_in = plan.input(S_IN, N, self.input_nc, 0, self.input_nc, H, W)
+        v_prev = plan.input(S_PREV, N, self.prev_output_nc, 0, self.prev_output_nc, H, W)
+        seg = emit_seq(plan, self.model_down_seg, v_in)
+        down = emit_seq(plan, self.model_down_img, v_prev, final_adds=(seg,))              # networks.py:204
+        img_feat = emit_seq(plan, self.model_up_img, emit_seq(plan, self.model_res_img, down))   # :205
+        plan.export(img_feat, S_IMGF)
+        emit_head(plan, self.model_final_img, img_feat, (S_RAW, self.output_nc, 1.0))     # :206
+        if not self.no_flow:
+            flow_feat = emit_seq(plan, self.model_up_flow, emit_seq(plan, self.model_res_flow, down))   # :210-211
+            plan.export(flow_feat, S_FLOWF)
+            emit_head(plan, self.model_final_flow, flow_feat, (S_FLOW, 2, self.flow_multiplier))        # :212
+            emit_head(plan, self.model_final_w, flow_feat, (S_W, 1, 1.0))                               # :213
+        if self.use_fg_model:
+            fg_feat = emit_seq(plan, self.indv_up, emit_seq(plan, self.indv_res, emit_seq(plan, self.indv_down, v_in)))
+            plan.export(fg_feat, S_FGF)                                                    # :225
+            emit_head(plan, self.indv_final, fg_feat, (S_FG, self.output_nc, 1.0))         # :226
+        self._emit_composite(plan, N, H, W, use_raw_only)
+
+    def _emit_composite(self, plan, N, H, W, use_raw_only):
+        warp = not (use_raw_only or self.no_flow)
+        plan.composite(S_RAW, S_FLOW if warp else -1, S_W if warp else -1, S_PREV if warp else -1, self.prev_output_nc,
+                       S_FG if self.use_fg_model else -1, S_MASK if self.use_fg_model else -1, S_FINAL, N, H, W, warp,
+                       self.align_corners)                                                 # :216-230
+
+    def _run(self, key, coarse, input, img_prev, mask, use_raw_only):
+        self._require_cuda(input, img_prev, mask, *coarse)
+        input, img_prev = input.contiguous(), img_prev.contiguous()
+        N, _, H, W = input.shape
+        plan = self._get_plan(key + (N, H, W, bool(use_raw_only), bool(self.align_corners)), input.device,
+                              lambda p: self._describe(p, N, H, W, use_raw_only))
+        new = lambda c: torch.empty((N, c, H, W), device=input.device, dtype=torch.float32)
+        io = [None] * 14
+        io[S_IN], io[S_PREV] = input, img_prev
+        io[S_FINAL], io[S_RAW], io[S_IMGF] = new(self.output_nc), new(self.output_nc), new(self._feat_c())
+        if not self.no_flow:
+            io[S_FLOW], io[S_W], io[S_FLOWF] = new(2), new(1), new(self._feat_c())
+        if self.use_fg_model:
+            io[S_MASK] = mask.contiguous()
+            io[S_FGF], io[S_FG] = new(self._fg_feat_c()), new(self.output_nc)
+        for s, t in zip((S_CI, S_CF, S_CG), coarse):
+            io[s] = t.contiguous() if t is not None else None
+        plan.run(io, self.use_cuda_graph)
+        return io[S_FINAL], io[S_FLOW], io[S_W], io[S_RAW], io[S_IMGF], io[S_FLOWF], io[S_FGF]
+
+    def _feat_c(self):
+        return self.model_final_img[1].in_channels
+
+    def _fg_feat_c(self):
+        return self.indv_final[1].in_channels
+
+    def forward(self, input, img_prev, mask, img_feat_coarse, flow_feat_coarse, img_fg_feat_coarse, use_raw_only):
+        return self._run(('G',), (), input, img_prev, mask, use_raw_only)
+
+
+class CompositeLocalGenerator(CompositeGenerator):
+    """models/networks.py:234-325."""
+
+    def __init__(self, opt, input_nc, output_nc, prev_output_nc, ngf, n_downsampling, n_blocks_local,
+                 use_fg_model=False, no_flow=False, norm_layer=nn.BatchNorm2d, padding_type='reflect', scale=1):
+        _Planned.__init__(self)
+        self.opt = opt
+        self.use_fg_model = use_fg_model
+        self.no_flow = no_flow
+        self.scale = scale
+        self.input_nc, self.output_nc, self.prev_output_nc = input_nc, output_nc, prev_output_nc
+        rb = lambda c: ResnetBlock(c, padding_type=padding_type, activation=nn.ReLU(True), norm_layer=norm_layer)
+        if use_fg_model:
+            c = ngf // 2 if n_downsampling > 2 else ngf
+            self.indv_down = nn.Sequential(*(_stem(input_nc, c, norm_layer) + _down(c, c * 2, norm_layer)))
+            self.indv_up = nn.Sequential(*([rb(c * 2) for _ in range(n_blocks_local)] + _up(c * 2, c, norm_layer)))
+            self.indv_final = nn.Sequential(*_head(c, output_nc, nn.Tanh()))
+        self.model_down_seg = nn.Sequential(*(_stem(input_nc, ngf, norm_layer) + _down(ngf, ngf * 2, norm_layer)))
+        self.model_down_img = nn.Sequential(*(_stem(prev_output_nc, ngf, norm_layer) + _down(ngf, ngf * 2, norm_layer)))
+        self.model_up_img = nn.Sequential(*([rb(ngf * 2) for _ in range(n_blocks_local)] + _up(ngf * 2, ngf, norm_layer)))
+        self.model_final_img = nn.Sequential(*_head(ngf, output_nc, nn.Tanh()))
+        if not no_flow:
+            self.model_up_flow = copy.deepcopy(self.model_up_img)
+            self.model_final_flow = nn.Sequential(*_head(ngf, 2))
+            self.model_final_w = nn.Sequential(*_head(ngf, 1, nn.Sigmoid()))
+
+    def _describe(self, plan, N, H, W, use_raw_only=False):
+        h2, w2 = H // 2, W // 2
+        c2 = self.model_down_seg[4].out_channels
+        v_in = plan.input(S_IN, N, self.input_nc, 0, self.input_nc, H, W)
+        v_prev = plan.input(S_PREV, N, self.prev_output_nc, 0, self.prev_output_nc, H, W)
+        ci = plan.input(S_CI, N, c2, 0, c2, h2, w2)
+        seg = emit_seq(plan, self.model_down_seg, v_in)
+        fin = emit_seq(plan, self.model_down_img, v_prev, defer_last=True)      # down_img = seg + img (:298)
+        img_feat = emit_seq(plan, self.model_up_img, fin((seg, ci)))             # :299
+        plan.export(img_feat, S_IMGF)
+        emit_head(plan, self.model_final_img, img_feat, (S_RAW, self.output_nc, 1.0))
+        if not self.no_flow:
+            cf = plan.input(S_CF, N, c2, 0, c2, h2, w2)
+            flow_feat = emit_seq(plan, self.model_up_flow, fin((seg, cf)))       # :305
+            plan.export(flow_feat, S_FLOWF)
+            emit_head(plan, self.model_final_flow, flow_feat, (S_FLOW, 2, 20.0 * (2 ** self.scale)))   # :297,306
+            emit_head(plan, self.model_final_w, flow_feat, (S_W, 1, 1.0))
+        if self.use_fg_model:
+            cg_c = self.indv_down[4].out_channels
+            cg = plan.input(S_CG, N, cg_c, 0, cg_c, h2, w2)
+            fg_feat = emit_seq(plan, self.indv_up, emit_seq(plan, self.indv_down, v_in, final_adds=(cg,)))   # :319
+            plan.export(fg_feat, S_FGF)
+            emit_head(plan, self.indv_final, fg_feat, (S_FG, self.output_nc, 1.0))
+        self._emit_composite(plan, N, H, W, use_raw_only)
+
+    def forward(self, input, img_prev, mask, img_feat_coarse, flow_feat_coarse, img_fg_feat_coarse, use_raw_only):
+        return self._run(('GL',), (img_feat_coarse, flow_feat_coarse, img_fg_feat_coarse), input, img_prev, mask,
+                         use_raw_only)
+
+
+class GlobalGenerator(_Planned):
+    """models/networks.py:327-359 (first-frame generator under --use_single_G)."""
+
+    def __init__(self, input_nc, output_nc, ngf=64, n_downsampling=3, n_blocks=9, norm_layer=nn.BatchNorm2d,
+                 padding_type='reflect'):
+        assert n_blocks >= 0
+        super().__init__()
+        cm = lambda c: min(1024, c)
+        self.input_nc, self.output_nc = input_nc, output_nc
+        model = _stem(input_nc, ngf, norm_layer)
+        for i in range(n_downsampling):
+            model += _down(cm(ngf * 2 ** i), cm(ngf * 2 ** (i + 1)), norm_layer)
+        model += [ResnetBlock(cm(ngf * 2 ** n_downsampling), padding_type=padding_type, activation=nn.ReLU(True),
+                              norm_layer=norm_layer) for _ in range(n_blocks)]
+        for i in range(n_downsampling):
+            m = 2 ** (n_downsampling - i)
+            model += _up(cm(ngf * m), cm(int(ngf * m / 2)), norm_layer)
+        model += _head(ngf, output_nc, nn.Tanh())
+        self.model = nn.Sequential(*model)
+
+    def _describe(self, plan, N, H, W):
+        v = plan.input(0, N, self.input_nc, 0, self.input_nc, H, W)
+        mods = list(self.model)
+        v = emit_seq(plan, mods[:-3], v)
+        emit_head(plan, mods[-3:], v, (1, self.output_nc, 1.0))
+
+    def forward(self, input, feat=None):
+        if feat is not None:
+            input = torch.cat([input, feat], dim=1)
+        self._require_cuda(input)
+        input = input.contiguous()
+        N, _, H, W = input.shape
+        plan = self._get_plan(('GG', N, H, W), input.device, lambda p: self._describe(p, N, H, W))
+        out = torch.empty((N, self.output_nc, H, W), device=input.device, dtype=torch.float32)
+        plan.run([input, out], self.use_cuda_graph)
+        return out
+
+
+class LocalEnhancer(_Planned):
+    """models/networks.py:361-419."""
+
+    def __init__(self, input_nc, output_nc, ngf=32, n_downsample_global=3, n_blocks_global=9, n_local_enhancers=1,
+                 n_blocks_local=3, norm_layer=nn.BatchNorm2d, padding_type='reflect'):
+        super().__init__()
+        self.n_local_enhancers = n_local_enhancers
+        self.input_nc, self.output_nc = input_nc, output_nc
+        g = GlobalGenerator(input_nc, output_nc, ngf * (2 ** n_local_enhancers), n_downsample_global, n_blocks_global,
+                            norm_layer).model
+        self.model = nn.Sequential(*[g[i] for i in range(len(g) - 3)])
+        for n in range(1, n_local_enhancers + 1):
+            c = ngf * (2 ** (n_local_enhancers - n))
+            down = _stem(input_nc, c, norm_layer) + _down(c, c * 2, norm_layer)
+            up = [ResnetBlock(c * 2, padding_type=padding_type, norm_layer=norm_layer) for _ in range(n_blocks_local)]
+            up += _up(c * 2, c, norm_layer)
+            if n == n_local_enhancers:
+                up += _head(ngf, output_nc, nn.Tanh())
+            setattr(self, 'model%d_1' % n, nn.Sequential(*down))
+            setattr(self, 'model%d_2' % n, nn.Sequential(*up))
+        self.downsample = nn.AvgPool2d(3, stride=2, padding=[1, 1], count_include_pad=False)
+
+    def _describe(self, plan, N, H, W):
+        # pyramid level i of the input arrives in IO slot i (built by forward with the avg-pool kernel)
+        L_ = self.n_local_enhancers
+        dims = [(H, W)]
+        for _ in range(L_):
+            dims.append(((dims[-1][0] - 1) // 2 + 1, (dims[-1][1] - 1) // 2 + 1))
+        out = emit_seq(plan, self.model, plan.input(L_, N, self.input_nc, 0, self.input_nc, *dims[L_]))
+        for n in range(1, L_ + 1):
+            lvl = L_ - n
+            x = emit_seq(plan, getattr(self, 'model%d_1' % n),
+                         plan.input(lvl, N, self.input_nc, 0, self.input_nc, *dims[lvl]), final_adds=(out,))
+            mods = list(getattr(self, 'model%d_2' % n))
+            if n == L_:
+                out = emit_seq(plan, mods[:-3], x)
+                emit_head(plan, mods[-3:], out, (L_ + 1, self.output_nc, 1.0))
+            else:
+                out = emit_seq(plan, mods, x)
+
+    def forward(self, input, feat_map=None):
+        from . import ops
+        if feat_map is not None:
+            input = torch.cat([input, feat_map], dim=1)
+        self._require_cuda(input)
+        pyr = [input.contiguous()]
+        for _ in range(self.n_local_enhancers):
+            pyr.append(ops.avgpool3s2(pyr[-1]))
+        N, _, H, W = input.shape
+        plan = self._get_plan(('LE', N, H, W), input.device, lambda p: self._describe(p, N, H, W))
+        out = torch.empty((N, self.output_nc, H, W), device=input.device, dtype=torch.float32)
+        plan.run(pyr + [out], self.use_cuda_graph)
+        return out
+
+
+# ------------------------------------------------------------------------------------ discriminators
+class NLayerDiscriminator(nn.Module):
+    """Parameter container with the keys of models/networks.py:679-725."""
+
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=nn.BatchNorm2d, getIntermFeat=False):
+        super().__init__()
+        self.getIntermFeat, self.n_layers = getIntermFeat, n_layers
+        kw, padw = 4, 2
+        seq = [[nn.Conv2d(input_nc, ndf, kernel_size=kw, stride=2, padding=padw), nn.LeakyReLU(0.2, True)]]
+        nf = ndf
+        for n in range(1, n_layers):
+            nf_prev, nf = nf, min(nf * 2, 512)
+            seq += [[nn.Conv2d(nf_prev, nf, kernel_size=kw, stride=2, padding=padw), norm_layer(nf),
+                     nn.LeakyReLU(0.2, True)]]
+        nf_prev, nf = nf, min(nf * 2, 512)
+        seq += [[nn.Conv2d(nf_prev, nf, kernel_size=kw, stride=1, padding=padw), norm_layer(nf), nn.LeakyReLU(0.2, True)]]
+        seq += [[nn.Conv2d(nf, 1, kernel_size=kw, stride=1, padding=padw)]]
+        if getIntermFeat:
+            for n in range(len(seq)):
+                setattr(self, 'model' + str(n), nn.Sequential(*seq[n]))
+        else:
+            self.model = nn.Sequential(*[m for s in seq for m in s])
+
+
+class MultiscaleDiscriminator(nn.Module):
+    """Parameter container with the keys of models/networks.py:634-675.  The tcgen05 forward of the
+    discriminator towers is scheduled after the generator path (DESIGN.md scope table)."""
+
+    def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=nn.BatchNorm2d, num_D=3, getIntermFeat=False):
+        super().__init__()
+        self.num_D, self.n_layers, self.getIntermFeat = num_D, n_layers, getIntermFeat
+        for i in range(num_D):
+            netD = NLayerDiscriminator(input_nc, min(64, ndf * (2 ** (num_D - 1 - i))), n_layers, norm_layer,
+                                       getIntermFeat)
+            if getIntermFeat:
+                for j in range(n_layers + 2):
+                    setattr(self, 'scale%d_layer%d' % (i, j), getattr(netD, 'model' + str(j)))
+            else:
+                setattr(self, 'layer' + str(i), netD.model)
+        self.downsample = nn.AvgPool2d(3, stride=2, padding=[1, 1], count_include_pad=False)
+
+    def forward(self, input):
+        raise NotImplementedError('MultiscaleDiscriminator.forward on sm_100a is not built yet (round 2); '
+                                  'there is deliberately no PyTorch fallback')
+
+
+def build_netG(opt, s):
+    """netG{s} exactly as Vid2VidModelG.initialize builds it (models/vid2vid_model_G.py:30-43)."""
+    input_nc = opt.label_nc if opt.label_nc != 0 else opt.input_nc
+    netG_input_nc = input_nc * opt.n_frames_G + (opt.n_frames_G if opt.use_instance else 0)
+    prev_output_nc = (opt.n_frames_G - 1) * opt.output_nc
+    if s == 0:
+        return define_G(netG_input_nc, opt.output_nc, prev_output_nc, opt.ngf, opt.netG, opt.n_downsample_G, opt.norm,
+                        0, [], opt)
+    return define_G(netG_input_nc, opt.output_nc, prev_output_nc, opt.ngf // (2 ** s), opt.netG + 'Local',
+                    opt.n_downsample_G, opt.norm, s, [], opt)
