@@ -152,6 +152,11 @@ int v2v_plan_repack(v2v_plan* plan, v2v_stream_t stream);
 /* Run once.  io_ptrs[slot] = device pointer of the caller tensor bound to that slot. */
 int v2v_plan_run(v2v_plan* plan, void* const* io_ptrs, int n_io, int use_graph, v2v_stream_t stream);
 
+/* Runs the plan once eagerly with a CUDA event after every kernel: kinds[i] (0 import, 1 conv, 2 raw-stats,
+ * 3 stats-finalize, 4 norm-apply, 5 export, 6 composite), ms[i] device time, macs[i] algorithmic conv MACs. */
+int v2v_plan_profile(v2v_plan* plan, void* const* io_ptrs, int n_io, v2v_stream_t stream, int max_ops, int* kinds,
+                     float* ms, double* macs, int* n_ops);
+
 /* Introspection (host logic tests, bench accounting). */
 int v2v_plan_num_kernels(const v2v_plan* plan);             /* kernels launched per run */
 double v2v_plan_conv_macs(const v2v_plan* plan);            /* algorithmic conv MACs per run (dense, unpadded) */

@@ -1,0 +1,120 @@
+"""GPU parity of the convolution path, one unit at a time, through the C-ABI plan runtime.
+Reference = PyTorch fp32 with bf16 rounding at the points where the CUDA path stores bf16
+(tests/bf16_emul.py); agreement must be within ~1 bf16 ulp (tolerance written below)."""
+import os
+
+import pytest
+import torch
+import torch.nn as nn
+
+import bf16_emul as E
+from vid2vid_b200 import networks as NW
+from vid2vid_b200.utils import det_fill_
+
+pytestmark = pytest.mark.gpu
+
+BN = NW.get_norm_layer('batch')
+IN = NW.get_norm_layer('instance')
+
+
+def _check(out, ref, name, ulps=2.0, mean_tol=2e-3):
+    out, ref = out.float().cpu(), ref.float().cpu()
+    assert out.shape == ref.shape, (out.shape, ref.shape)
+    assert torch.isfinite(out).all(), name + ': non-finite output'
+    diff = (out - ref).abs()
+    tol = ulps * (2.0 ** -8) * torch.clamp(ref.abs(), min=1.0)     # bf16 has 8 significand bits
+    worst = (diff / tol).max().item()
+    print('%-28s max|d|=%.3e mean|d|=%.3e worst/tol=%.2f' % (name, diff.max().item(), diff.mean().item(), worst))
+    assert diff.mean().item() < mean_tol, name
+    frac_bad = (diff > tol).float().mean().item()
+    assert frac_bad < 1e-3, '%s: %.4f%% of elements beyond %.1f bf16 ulp' % (name, 100 * frac_bad, ulps)
+
+
+def _run(mods, x, head=None, head_scale=1.0, seed=1):
+    runner = det_fill_(NW.SequentialRunner(mods, head, head_scale), seed=seed).cuda()
+    xd = x.cuda()
+    with torch.no_grad():
+        out = runner(xd)
+        out2 = runner(xd)          # second call replays the CUDA graph
+        xr = E.r16(xd)
+        ref = E.run_units(list(runner.seq), xr)
+        if head is not None:
+            ref = E.run_head(list(runner.head), ref, head_scale)
+    assert torch.equal(out, out2), 'graph replay differs from eager run'
+    return out, ref
+
+
+def _x(n, c, h, w, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(n, c, h, w, generator=g)
+
+
+CASES = [
+    # name, layer list builder, input shape
+    ('c3s1_reflect_64_128_32x64', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(64, 128, 3), BN(128), nn.ReLU(True)], (1, 64, 32, 64)),
+    ('c3s1_rowtile_R3_8x160', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(64, 64, 3), BN(64), nn.ReLU(True)], (1, 64, 8, 160)),
+    ('c7_stem_R7_108_32', lambda: NW._stem(108, 32, BN), (1, 108, 12, 136)),
+    ('c7_stem_small_map', lambda: NW._stem(6, 32, BN), (1, 6, 16, 32)),
+    ('c3s2_zero_64_128', lambda: NW._down(64, 128, BN), (1, 64, 32, 64)),
+    ('c3s2_odd_extent', lambda: NW._down(32, 64, BN), (1, 32, 18, 30)),
+    ('deconv_128_64', lambda: NW._up(128, 64, BN), (1, 128, 16, 32)),
+    ('deconv_wide', lambda: NW._up(64, 32, BN), (1, 64, 8, 80)),
+    ('resblock_128', lambda: [NW.ResnetBlock(128, 'reflect', BN)], (1, 128, 16, 32)),
+    ('resblock_x2_instance', lambda: [NW.ResnetBlock(64, 'reflect', IN), NW.ResnetBlock(64, 'reflect', IN)], (2, 64, 16, 16)),
+    ('batch2_bn', lambda: NW._down(64, 64, BN) + [NW.ResnetBlock(64, 'reflect', BN)], (2, 64, 16, 32)),
+    ('cout_16_cin_16', lambda: NW._stem(16, 16, BN) + NW._down(16, 32, BN), (1, 16, 16, 40)),
+    ('d_first_layer_lrelu', lambda: [nn.Conv2d(39, 64, 4, stride=2, padding=2), nn.LeakyReLU(0.2, True)], (2, 39, 32, 48)),
+    ('c3_1024_1024_32x64', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(1024, 1024, 3), BN(1024), nn.ReLU(True)], (1, 1024, 32, 64)),
+    ('c3_512_512_16x32', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(512, 512, 3), BN(512), nn.ReLU(True)], (1, 512, 16, 32)),
+]
+
+
+@pytest.mark.parametrize('name,build,shape', CASES, ids=[c[0] for c in CASES])
+def test_conv_unit(name, build, shape):
+    out, ref = _run(build(), _x(*shape))
+    _check(out, ref, name)
+
+
+HEADS = [
+    ('head_tanh_64_3', lambda: NW._stem(32, 64, BN), lambda: NW._head(64, 3, nn.Tanh()), 1.0, (1, 32, 12, 136)),
+    ('head_flow_x20', lambda: NW._stem(32, 64, BN), lambda: NW._head(64, 2), 20.0, (1, 32, 16, 32)),
+    ('head_sigmoid', lambda: NW._stem(32, 32, BN), lambda: NW._head(32, 1, nn.Sigmoid()), 1.0, (2, 32, 16, 140)),
+]
+
+
+@pytest.mark.parametrize('name,build,head,scale,shape', HEADS, ids=[c[0] for c in HEADS])
+def test_head(name, build, head, scale, shape):
+    out, ref = _run(build(), _x(*shape), head(), scale)
+    # head outputs are fp32; inputs differ by <= 1 bf16 ulp of the previous activation
+    _check(out, ref, name, ulps=4.0 * max(1.0, scale), mean_tol=5e-3 * max(1.0, scale))
+
+
+def test_running_stats_side_effect():
+    """nn.BatchNorm2d in train mode updates running_mean/var/num_batches_tracked."""
+    mods = [nn.Conv2d(64, 64, 3, padding=1), BN(64), nn.ReLU(True)]
+    runner = det_fill_(NW.SequentialRunner(mods), seed=3).cuda()
+    x = _x(2, 64, 16, 16).cuda()
+    ref_conv, ref_bn = nn.Conv2d(64, 64, 3, padding=1).cuda(), nn.BatchNorm2d(64).cuda()
+    ref_conv.load_state_dict(runner.seq[0].state_dict())
+    ref_bn.load_state_dict(runner.seq[1].state_dict())
+    with torch.no_grad():
+        runner(x)
+        ref_bn.train()
+        ref_bn(ref_conv(x))
+    torch.cuda.synchronize()
+    assert int(runner.seq[1].num_batches_tracked.item()) == 1
+    assert torch.allclose(runner.seq[1].running_mean, ref_bn.running_mean, atol=2e-3)
+    assert torch.allclose(runner.seq[1].running_var, ref_bn.running_var, rtol=2e-2, atol=1e-3)
+
+
+def test_repack_after_weight_update():
+    mods = [nn.ReflectionPad2d(1), nn.Conv2d(64, 64, 3), BN(64), nn.ReLU(True)]
+    runner = det_fill_(NW.SequentialRunner(mods), seed=4).cuda()
+    x = _x(1, 64, 16, 32).cuda()
+    with torch.no_grad():
+        a = runner(x)
+        runner.seq[1].weight.mul_(-1.0)          # in-place update, as an optimiser step would do
+        b = runner(x)
+        ref = E.run_units(list(runner.seq), E.r16(x))
+    assert not torch.equal(a, b)
+    _check(b, ref, 'after_repack')

@@ -1,0 +1,108 @@
+"""GPU parity of the generator modules (the nn.Module boundary) through the C-ABI plan
+runtime: against the committed reference fixtures (tests/golden, fp32 reference outputs), against the
+oracle on the same seeded inputs, and against the bf16-rounding emulation (kernel exactness)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import cases as C
+from oracle.make_golden import coarse_feats
+from vid2vid_b200.utils import det_fill_, synth_label_sequence
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+
+# Stated tolerance of the bf16-operand / fp32-accumulate path against the fp32 reference:
+# images and masks live in [-1,1] / [0,1]; flow is in pixels (x20 head scale); features are O(1).
+TOL = {
+    'img_final': (0.12, 0.015), 'img_raw': (0.12, 0.015), 'weight': (0.08, 0.01), 'flow': (2.0, 0.2),
+    'img_feat': (0.5, 0.03), 'flow_feat': (0.5, 0.03), 'img_fg_feat': (0.5, 0.03), 'out': (0.12, 0.015),
+}
+
+
+def load(name):
+    return dict(np.load(os.path.join(GOLD, name + '.npz')))
+
+
+def report(name, key, out, gold):
+    d = np.abs(out - gold)
+    print('%-12s %-12s max|d|=%.4f mean|d|=%.5f  ref rms=%.3f' % (name, key, d.max(), d.mean(), np.sqrt((gold ** 2).mean())))
+    return d.max(), d.mean()
+
+
+@pytest.mark.parametrize('name', ['g0_small', 'g0_small_ac', 'g0_nofg_nd2', 'g0_noflow', 'gl_small_s1', 'gl_small_s2'])
+def test_generator_vs_reference_fixture(name):
+    c = C.CASES[name]
+    gold = load(name)
+    net = det_fill_(C.build_module(c), seed=c['seed']).cuda()
+    net.align_corners = c.get('align_corners', False)
+    inp, img_prev, mask = (t.cuda() for t in C.gen_inputs(c['label_nc'], c['h'], c['w'], c['seed'], block=c.get('block', 4)))
+    coarse = tuple(t.cuda() for t in coarse_feats(c)) if c['kind'] == 'compositeLocal' else (None, None, None)
+    with torch.no_grad():
+        out = net(inp, img_prev, mask, *coarse, False)
+    bad = []
+    for key, t in zip(C.GEN_OUT_NAMES, out):
+        if t is None:
+            assert key not in gold
+            continue
+        assert torch.isfinite(t).all(), key
+        mx, mn = report(name, key, t.cpu().numpy(), gold[key])
+        if mx > TOL[key][0] or mn > TOL[key][1]:
+            bad.append((key, mx, mn))
+    assert not bad, bad
+
+
+def test_cfg1_full_width_generator():
+    """BASELINE config 1: CompositeGenerator(ngf 128, nd 3, 9 blocks, fg) at 256x128."""
+    c = C.CASES['cfg1']
+    gold = load('cfg1')
+    net = det_fill_(C.build_module(c), seed=c['seed']).cuda()
+    inp, img_prev, mask = (t.cuda() for t in C.gen_inputs(c['label_nc'], c['h'], c['w'], c['seed'], block=c['block']))
+    with torch.no_grad():
+        out = net(inp, img_prev, mask, None, None, None, False)
+    ss = c['subsample']
+    bad = []
+    for key, t in zip(C.GEN_OUT_NAMES, out):
+        t = t.cpu()
+        if key + '_sub' in gold:
+            mx, mn = report('cfg1', key, t[:, :, ::ss, ::ss].numpy(), gold[key + '_sub'])
+            cm = np.abs(t.mean(dim=(2, 3)).numpy() - gold[key + '_cmean']).max()
+            assert cm < 0.02, (key, cm)
+        else:
+            mx, mn = report('cfg1', key, t.numpy(), gold[key])
+        if mx > TOL[key][0] or mn > TOL[key][1]:
+            bad.append((key, mx, mn))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize('name', ['global_small', 'local_small'])
+def test_first_frame_generators(name):
+    c = C.CASES[name]
+    net = det_fill_(C.build_module(c), seed=c['seed']).cuda()
+    lab = synth_label_sequence(1, c['h'], c['w'], label_nc=c['input_nc'], block=4, seed=c['seed'])
+    x = torch.zeros(1, c['input_nc'], c['h'], c['w']).scatter_(1, lab[:, 0].long(), 1.0).cuda()
+    with torch.no_grad():
+        out = net(x)
+    mx, mn = report(name, 'out', out.cpu().numpy(), load(name)['out'])
+    assert mx <= TOL['out'][0] and mn <= TOL['out'][1]
+
+
+def test_generator_simt_vs_umma_same_plan():
+    """The tcgen05 kernel and the SIMT cross-check kernel evaluate the same lowered plan."""
+    c = C.CASES['g0_small']
+    inp, img_prev, mask = (t.cuda() for t in C.gen_inputs(c['label_nc'], c['h'], c['w'], c['seed']))
+    outs = []
+    for impl in ('umma', 'simt'):
+        os.environ['V2V_CONV_IMPL'] = impl
+        try:
+            net = det_fill_(C.build_module(c), seed=c['seed']).cuda()
+            with torch.no_grad():
+                outs.append(net(inp, img_prev, mask, None, None, None, False))
+        finally:
+            os.environ.pop('V2V_CONV_IMPL', None)
+    for key, a, b in zip(C.GEN_OUT_NAMES, *outs):
+        d = (a - b).abs()
+        print('%-12s umma-vs-simt max|d|=%.4f mean|d|=%.5f' % (key, d.max().item(), d.mean().item()))
+        assert d.mean().item() < 5e-3, key

@@ -32,6 +32,7 @@ class HeadChannel(C.Structure):
 
 
 _lib = None
+LAUNCHES = [0]      # kernels launched through this binding (bench.py's gpu_launches)
 
 # every symbol include/v2v_b200.h declares (tests/test_abi.py checks the list against the header)
 SYMBOLS = [
@@ -40,7 +41,7 @@ SYMBOLS = [
     'v2v_resample_forward', 'v2v_onehot_edges', 'v2v_avgpool3s2', 'v2v_fg_mask',
     'v2v_plan_create', 'v2v_plan_destroy', 'v2v_g_input', 'v2v_g_conv', 'v2v_g_norm_act', 'v2v_g_conv_act',
     'v2v_g_head', 'v2v_g_export', 'v2v_g_composite', 'v2v_plan_finalize', 'v2v_plan_repack', 'v2v_plan_run',
-    'v2v_plan_num_kernels', 'v2v_plan_conv_macs', 'v2v_plan_workspace_bytes', 'v2v_plan_describe',
+    'v2v_plan_profile', 'v2v_plan_num_kernels', 'v2v_plan_conv_macs', 'v2v_plan_workspace_bytes', 'v2v_plan_describe',
     'v2v_conv_tap_table',
 ]
 
@@ -71,6 +72,8 @@ def lib():
     l.v2v_plan_finalize.argtypes = [C.c_void_p, C.c_void_p]
     l.v2v_plan_repack.argtypes = [C.c_void_p, C.c_void_p]
     l.v2v_plan_run.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]
+    l.v2v_plan_profile.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int),
+                                   C.POINTER(C.c_float), C.POINTER(C.c_double), C.POINTER(C.c_int)]
     l.v2v_plan_num_kernels.argtypes = [C.c_void_p]
     l.v2v_plan_conv_macs.argtypes = [C.c_void_p]
     l.v2v_plan_workspace_bytes.argtypes = [C.c_void_p]

@@ -131,7 +131,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t b_base = smem_u32(sB + (size_t)sb * p.b_slot_bytes);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {      // 4 x (K = 16 bf16 = 32 bytes) per 128-byte swizzle row
-          const uint64_t adesc = make_sw128_kmajor_desc(a_base + r * 128 + k * 32);
+          const uint64_t adesc = make_sw128_kmajor_desc(a_base + r * 128 + k * 32, p.desc_mode);
           const uint64_t bdesc = make_sw128_kmajor_desc(b_base + k * 32);
           umma_bf16(tmem_base, adesc, bdesc, idesc, acc);
           acc = 1;

@@ -166,6 +166,7 @@ struct GOp {
   CompositeParams comp{};
   // lowered
   bf16* wpacked = nullptr; int Ktotal = 0, Cp = 0;
+  double macs = 0.0;
   CUtensorMap tmA{}, tmB{};
   ConvKernelParams kp{};
 };
@@ -292,7 +293,8 @@ static int lower(v2v_plan* P) {
       op.req_index = add_req(vin, conv_req(op.conv, op.geom));
       const v2v_conv_desc& c = op.conv;
       const double px = op.conv.transposed ? (double)vin.N * vin.H * vin.W : (double)vin.N * op.geom.out_h * op.geom.out_w;
-      P->conv_macs += px * c.Cin * c.Cout * c.kh * c.kw;
+      op.macs = px * c.Cin * c.Cout * c.kh * c.kw;
+      P->conv_macs += op.macs;
     } else if (op.kind == G_NORM_ACT) {
       for (int k = 0; k < 2; ++k) if (op.add[k] >= 0) P->values[op.add[k]].interior_use = true;
     } else if (op.kind == G_EXPORT) {
@@ -343,6 +345,7 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   kp.bias = op.conv.bias;
   kp.lrelu_slope = op.slope;
   kp.act = op.act;
+  { const char* dm = getenv("V2V_DESC_MODE"); kp.desc_mode = (dm && dm[0] == '1') ? 1 : 0; }
   op.Cp = kp.Cp; op.Ktotal = op.conv.kh * op.conv.kw * kp.Cp;
 }
 
@@ -687,6 +690,32 @@ int v2v_plan_run(v2v_plan* P, void* const* io_ptrs, int n_io, int use_graph, v2v
     V2V_CUDA(cudaGraphDestroy(graph));
   }
   V2V_CUDA(cudaGraphLaunch(P->graph_exec, stream));
+  return 0;
+}
+
+int v2v_plan_profile(v2v_plan* P, void* const* io_ptrs, int n_io, v2v_stream_t stream_, int max_ops, int* kinds,
+                     float* ms, double* macs, int* n_ops) {
+  V2V_REQUIRE(P && P->finalized, V2V_ERR_STATE, "plan not finalized");
+  V2V_REQUIRE(n_io >= P->n_slots && io_ptrs && kinds && ms && macs && n_ops, V2V_ERR_INVALID, "bad profile arguments");
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  V2V_CUDA(cudaMemcpyAsync(P->io_dev, io_ptrs, sizeof(void*) * P->n_slots, cudaMemcpyHostToDevice, stream));
+  const int n = std::min<int>(max_ops, (int)P->xops.size());
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) V2V_CUDA(cudaEventCreate(&e));
+  V2V_CUDA(cudaEventRecord(ev[0], stream));
+  for (int i = 0; i < (int)P->xops.size(); ++i) {
+    int rc = run_xop(P, P->xops[i], stream);
+    if (rc) return rc;
+    if (i < n) V2V_CUDA(cudaEventRecord(ev[i + 1], stream));
+  }
+  V2V_CUDA(cudaStreamSynchronize(stream));
+  for (int i = 0; i < n; ++i) {
+    V2V_CUDA(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    kinds[i] = (int)P->xops[i].kind;
+    macs[i] = (P->xops[i].kind == X_CONV) ? P->gops[P->xops[i].gop].macs : 0.0;
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  *n_ops = n;
   return 0;
 }
 

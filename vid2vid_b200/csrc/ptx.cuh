@@ -137,13 +137,13 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
 //   bits [32,46) stride byte offset >> 4   bits [46,48) version = 1 (Blackwell)
 //   bits [49,52) base offset = (addr >> 7) & 7 when the start is not 1024 B aligned
 //   bits [61,64) layout type: 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr, int zero_base_offset = 0) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>(1) << 16;
   d |= static_cast<uint64_t>(1024 >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>((smem_addr >> 7) & 7) << 49;
+  if (!zero_base_offset) d |= static_cast<uint64_t>((smem_addr >> 7) & 7) << 49;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }

@@ -92,6 +92,7 @@ struct ConvKernelParams {
   float head_scale[V2V_MAX_HEAD];
   float lrelu_slope;
   int act;                           // EPI_ACT_BF16 activation
+  int desc_mode;                     // debug: 0 = smem descriptor base_offset per PTX doc, 1 = always 0
 };
 
 // kernel launchers (defined in the .cu files); all enqueue on `stream` and return cudaError_t

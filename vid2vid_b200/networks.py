@@ -565,3 +565,41 @@ def build_netG(opt, s):
                         0, [], opt)
     return define_G(netG_input_nc, opt.output_nc, prev_output_nc, opt.ngf // (2 ** s), opt.netG + 'Local',
                     opt.n_downsample_G, opt.norm, s, [], opt)
+
+
+class SequentialRunner(_Planned):
+    """Runs a list of supported layer containers (conv / norm / activation units, ResnetBlocks, transposed
+    convs; optionally a trailing small-Cout head) through the plan runtime: fp32 NCHW in -> fp32 NCHW out.
+    Used by the per-kernel parity tests and handy for porting other vid2vid sub-networks."""
+
+    def __init__(self, mods, head_mods=None, head_scale=1.0):
+        super().__init__()
+        self.seq = nn.Sequential(*mods)
+        self.head = nn.Sequential(*head_mods) if head_mods else None
+        self.head_scale = head_scale
+
+    def _describe(self, plan, N, C, H, W):
+        v = plan.input(0, N, C, 0, C, H, W)
+        v = emit_seq(plan, self.seq, v)
+        if self.head is not None:
+            emit_head(plan, self.head, v, (1, self.head[1].out_channels, self.head_scale))
+        else:
+            plan.export(v, 1)
+
+    def forward(self, x):
+        self._require_cuda(x)
+        x = x.contiguous()
+        N, C, H, W = x.shape
+        key = ('SR', N, C, H, W)
+        plan = self._get_plan(key, x.device, lambda p: self._describe(p, N, C, H, W))
+        if self.head is not None:
+            oc, oh, ow = self.head[1].out_channels, H, W
+            if len(self.seq):
+                last = plan.describe()['values'][-1]
+                oh, ow = last['H'], last['W']
+        else:
+            last = plan.describe()['values'][-1]
+            oc, oh, ow = last['C'], last['H'], last['W']
+        out = torch.empty((N, oc, oh, ow), device=x.device, dtype=torch.float32)
+        plan.run([x, out], self.use_cuda_graph)
+        return out

@@ -26,6 +26,11 @@ def _chk(*ts):
             raise RuntimeError('vid2vid_b200 ops need contiguous tensors')   # resample2d.py:9-10, channelnorm.py:9
 
 
+def _ck(rc):
+    L.check(rc)
+    L.LAUNCHES[0] += 1
+
+
 def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
 
@@ -40,7 +45,7 @@ def correlation(input1, input2, pad_size=20, kernel_size=1, max_displacement=20,
                                               C.byref(oc), C.byref(oh), C.byref(ow)))
     out = torch.empty((n, oc.value, oh.value, ow.value), device=input1.device, dtype=torch.float32)
     with torch.cuda.device_of(input1):
-        L.check(L.lib().v2v_correlation_forward(_p(input1), _p(input2), _p(out), n, c, h, w, pad_size, kernel_size,
+        _ck(L.lib().v2v_correlation_forward(_p(input1), _p(input2), _p(out), n, c, h, w, pad_size, kernel_size,
                                                 max_displacement, stride1, stride2, corr_multiply,
                                                 L.current_stream_ptr()))
     return out
@@ -66,7 +71,7 @@ def resample2d(input1, input2, kernel_size=1):
     b, _, h, w = input2.shape
     out = torch.empty((b, d, h, w), device=input1.device, dtype=torch.float32)
     with torch.cuda.device_of(input1):
-        L.check(L.lib().v2v_resample2d_forward(_p(input1), _p(input2), _p(out), b, d, h, w, ih, iw, kernel_size,
+        _ck(L.lib().v2v_resample2d_forward(_p(input1), _p(input2), _p(out), b, d, h, w, ih, iw, kernel_size,
                                                L.current_stream_ptr()))
     return out
 
@@ -88,7 +93,7 @@ def channelnorm(input1, norm_deg=2):
     b, c, h, w = input1.shape
     out = torch.empty((b, 1, h, w), device=input1.device, dtype=torch.float32)
     with torch.cuda.device_of(input1):
-        L.check(L.lib().v2v_channelnorm_forward(_p(input1), _p(out), b, c, h, w, norm_deg, L.current_stream_ptr()))
+        _ck(L.lib().v2v_channelnorm_forward(_p(input1), _p(out), b, c, h, w, norm_deg, L.current_stream_ptr()))
     return out
 
 
@@ -109,7 +114,7 @@ def resample(image, flow, align_corners=False):
     _chk(image, flow)
     b, c, h, w = image.shape
     out = torch.empty_like(image)
-    L.check(L.lib().v2v_resample_forward(_p(image), _p(flow), _p(out), b, c, h, w, int(align_corners),
+    _ck(L.lib().v2v_resample_forward(_p(image), _p(flow), _p(out), b, c, h, w, int(align_corners),
                                          L.current_stream_ptr()))
     return out
 
@@ -122,7 +127,7 @@ def onehot_edges(label_map, inst_map, label_nc, use_instance):
     _chk(label_map, inst)
     b, t, _, h, w = label_map.shape
     out = torch.empty((b, t, label_nc + int(bool(use_instance)), h, w), device=label_map.device, dtype=torch.float32)
-    L.check(L.lib().v2v_onehot_edges(_p(label_map), _p(inst), _p(out), b * t, label_nc, int(bool(use_instance)), h, w,
+    _ck(L.lib().v2v_onehot_edges(_p(label_map), _p(inst), _p(out), b * t, label_nc, int(bool(use_instance)), h, w,
                                      L.current_stream_ptr()))
     return out
 
@@ -134,7 +139,7 @@ def avgpool3s2(x):
     h, w = x.shape[-2:]
     planes = x.numel() // (h * w)
     out = torch.empty(tuple(x.shape[:-2]) + ((h - 1) // 2 + 1, (w - 1) // 2 + 1), device=x.device, dtype=torch.float32)
-    L.check(L.lib().v2v_avgpool3s2(_p(x), _p(out), planes, h, w, L.current_stream_ptr()))
+    _ck(L.lib().v2v_avgpool3s2(_p(x), _p(out), planes, h, w, L.current_stream_ptr()))
     return out
 
 
@@ -145,5 +150,5 @@ def fg_mask(real_As, ts, fg_labels):
     b, T, c, h, w = real_As.shape
     out = torch.empty((b, 1, h, w), device=real_As.device, dtype=torch.float32)
     arr = (C.c_int * len(fg_labels))(*fg_labels)
-    L.check(L.lib().v2v_fg_mask(_p(real_As), _p(out), b, T, c, h, w, ts, arr, len(fg_labels), L.current_stream_ptr()))
+    _ck(L.lib().v2v_fg_mask(_p(real_As), _p(out), b, T, c, h, w, ts, arr, len(fg_labels), L.current_stream_ptr()))
     return out

@@ -132,7 +132,22 @@ class Plan:
         # the first execution is eager (lazy module loading, attribute setup); graphs from the second on
         g = int(use_graph and self._graph_ok)
         L.check(L.lib().v2v_plan_run(self._h, arr, self.n_slots, g, L.current_stream_ptr()))
+        L.LAUNCHES[0] += self.num_kernels
         self._graph_ok = True
+        self.last_io = io
+
+    def profile(self, io=None):
+        """Eager run with a CUDA event after every kernel -> list of (kind, ms, conv_macs)."""
+        io = io if io is not None else self.last_io
+        arr = (C.c_void_p * self.n_slots)()
+        for i in range(self.n_slots):
+            t = io[i] if i < len(io) else None
+            arr[i] = t.data_ptr() if t is not None else None
+        n = self.num_kernels
+        kinds, ms, macs, cnt = (C.c_int * n)(), (C.c_float * n)(), (C.c_double * n)(), C.c_int()
+        L.check(L.lib().v2v_plan_profile(self._h, arr, self.n_slots, L.current_stream_ptr(), n, kinds, ms, macs,
+                                         C.byref(cnt)))
+        return [(kinds[i], ms[i], macs[i]) for i in range(cnt.value)]
 
     # ---- introspection
     @property
