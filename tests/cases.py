@@ -28,7 +28,9 @@ def onehot_input(label_nc, h, w, seed, block=4, n_frames=3):
 def gen_inputs(label_nc, h, w, seed, fg_label=2, block=4):
     g = torch.Generator().manual_seed(seed + 77)
     inp, lab = onehot_input(label_nc, h, w, seed, block)
-    img_prev = torch.rand(1, 6, h, w, generator=g) * 2 - 1
+    # low-pass noise: coarse U(-1,1) field, bilinearly upsampled
+    coarse = torch.rand(1, 6, max(2, h // 8), max(2, w // 8), generator=g) * 2 - 1
+    img_prev = torch.nn.functional.interpolate(coarse, size=(h, w), mode='bilinear', align_corners=False)
     mask = (lab[:, -1] == fg_label).float()
     return inp, img_prev, mask
 

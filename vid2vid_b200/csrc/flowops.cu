@@ -112,17 +112,19 @@ __global__ void resample2d_kernel(const float* __restrict__ in1, const float* __
     // the reference clamps against the OUTPUT extent (dim_w/dim_h of `output`), :48-51
     const int xL = max(min((int)floorf(xf), W - 1), 0), xR = max(min((int)floorf(xf) + 1, W - 1), 0);
     const int yT = max(min((int)floorf(yf), H - 1), 0), yB = max(min((int)floorf(yf) + 1, H - 1), 0);
-    // weights are formed in double exactly as the reference's `(1. - alpha)*(1. - beta) * v` (:55-58)
-    const double w00 = (1. - alpha) * (1. - beta), w01 = (double)alpha * (1. - beta);
-    const double w10 = (1. - alpha) * (double)beta, w11 = (double)alpha * (double)beta;
+    // weights as the reference forms them (:55-58): the three terms containing `1.` are promoted to double,
+    // `(alpha)*(beta) * v` stays in float; explicit _rn intrinsics keep ptxas from fusing (the oracle is unfused C)
+    const double w00 = __dmul_rn(1. - alpha, 1. - beta), w01 = __dmul_rn((double)alpha, 1. - beta);
+    const double w10 = __dmul_rn(1. - alpha, (double)beta);
+    const float w11 = __fmul_rn(alpha, beta);
     const size_t inHW = (size_t)inH * inW;
     for (int c = 0; c < C; ++c) {
       const float* pl = in1 + ((size_t)n * C + c) * inHW;
       float val = 0.f;
-      val += (float)(w00 * (double)pl[(size_t)yT * inW + xL]);
-      val += (float)(w01 * (double)pl[(size_t)yT * inW + xR]);
-      val += (float)(w10 * (double)pl[(size_t)yB * inW + xL]);
-      val += (float)(w11 * (double)pl[(size_t)yB * inW + xR]);
+      val = __fadd_rn(val, (float)__dmul_rn(w00, (double)pl[(size_t)yT * inW + xL]));
+      val = __fadd_rn(val, (float)__dmul_rn(w01, (double)pl[(size_t)yT * inW + xR]));
+      val = __fadd_rn(val, (float)__dmul_rn(w10, (double)pl[(size_t)yB * inW + xL]));
+      val = __fadd_rn(val, __fmul_rn(w11, pl[(size_t)yB * inW + xR]));
       out[((size_t)n * C + c) * HW + pix] = val;
     }
   }
@@ -138,7 +140,7 @@ __global__ void channelnorm_kernel(const float* __restrict__ in, float* __restri
     float r = 0.f;
     for (int c = 0; c < C; ++c) {
       const float v = in[((size_t)n * C + c) * HW + pix];
-      r += v * v;
+      r = __fadd_rn(r, __fmul_rn(v, v));      // unfused, like the C restatement
     }
     out[idx] = sqrtf(r);
   }

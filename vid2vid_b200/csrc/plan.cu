@@ -393,7 +393,7 @@ int v2v_plan_create(int device, int conv_impl, v2v_plan** out) {
   p->device = device;
   p->impl = conv_impl;
   const char* e = getenv("V2V_TAP_REUSE");
-  p->allow_reuse = !(e && e[0] == '0');
+  p->allow_reuse = (e && e[0] == '1');
   const char* ei = getenv("V2V_CONV_IMPL");
   if (ei && !strcmp(ei, "simt")) p->impl = V2V_IMPL_SIMT;
   *out = p;
@@ -403,6 +403,7 @@ int v2v_plan_create(int device, int conv_impl, v2v_plan** out) {
 int v2v_plan_destroy(v2v_plan* p) {
   if (!p) return 0;
   if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+  if (p->graph_stream) cudaStreamDestroy(p->graph_stream);
   if (p->arena) cudaFree(p->arena);
   if (p->io_dev) cudaFree(p->io_dev);
   delete p;
@@ -679,11 +680,14 @@ int v2v_plan_run(v2v_plan* P, void* const* io_ptrs, int n_io, int use_graph, v2v
     return 0;
   }
   if (!P->graph_exec) {
+    // capture on a plan-owned stream: the caller's stream may be the legacy default stream (PyTorch's
+    // default), which cannot be captured; the instantiated graph is then launched on the caller's stream
     cudaGraph_t graph;
-    V2V_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+    if (!P->graph_stream) V2V_CUDA(cudaStreamCreateWithFlags(&P->graph_stream, cudaStreamNonBlocking));
+    V2V_CUDA(cudaStreamBeginCapture(P->graph_stream, cudaStreamCaptureModeThreadLocal));
     int rc = 0;
-    for (const XOp& x : P->xops) { rc = run_xop(P, x, stream); if (rc) break; }
-    cudaError_t e = cudaStreamEndCapture(stream, &graph);
+    for (const XOp& x : P->xops) { rc = run_xop(P, x, P->graph_stream); if (rc) break; }
+    cudaError_t e = cudaStreamEndCapture(P->graph_stream, &graph);
     if (rc) return rc;
     V2V_CUDA(e);
     V2V_CUDA(cudaGraphInstantiate(&P->graph_exec, graph, 0));
