@@ -61,8 +61,8 @@ CASES = {
     'cfg1': dict(kind='composite', label_nc=35, ngf=128, nd=3, n_blocks=9, fg=True, no_flow=False,
                  h=128, w=256, seed=21, block=8, subsample=8),
     # Vid2VidModelG.inference, 3 scales, --fg --use_single_G, 4 generated frames
-    'infer_s3': dict(kind='inference', label_nc=35, ngf=16, nd=3, n_blocks=4, n_blocks_local=2,
-                     n_scales=3, h=64, w=128, n_gen=4, seed=31),
+    'infer_s3': dict(kind='inference', label_nc=35, ngf=16, nd=2, n_blocks=4, n_blocks_local=2,
+                     n_scales=3, h=128, w=256, n_gen=4, seed=31),
 }
 
 

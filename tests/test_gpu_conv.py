@@ -17,7 +17,12 @@ BN = NW.get_norm_layer('batch')
 IN = NW.get_norm_layer('instance')
 
 
+SIMT = os.environ.get('V2V_CONV_IMPL') == 'simt'   # cross-check kernel: statistics come from the bf16-stored raws
+
+
 def _check(out, ref, name, ulps=2.0, mean_tol=2e-3):
+    if SIMT:
+        ulps, mean_tol = ulps * 3, mean_tol * 3
     out, ref = out.float().cpu(), ref.float().cpu()
     assert out.shape == ref.shape, (out.shape, ref.shape)
     assert torch.isfinite(out).all(), name + ': non-finite output'
@@ -27,7 +32,7 @@ def _check(out, ref, name, ulps=2.0, mean_tol=2e-3):
     print('%-28s max|d|=%.3e mean|d|=%.3e worst/tol=%.2f' % (name, diff.max().item(), diff.mean().item(), worst))
     assert diff.mean().item() < mean_tol, name
     frac_bad = (diff > tol).float().mean().item()
-    assert frac_bad < 1e-3, '%s: %.4f%% of elements beyond %.1f bf16 ulp' % (name, 100 * frac_bad, ulps)
+    assert frac_bad < (2e-2 if SIMT else 1e-3), '%s: %.4f%% of elements beyond %.1f bf16 ulp' % (name, 100 * frac_bad, ulps)
 
 
 def _run(mods, x, head=None, head_scale=1.0, seed=1):

@@ -345,7 +345,10 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   kp.bias = op.conv.bias;
   kp.lrelu_slope = op.slope;
   kp.act = op.act;
-  { const char* dm = getenv("V2V_DESC_MODE"); kp.desc_mode = (dm && dm[0] == '1') ? 1 : 0; }
+  // Measured on B200: the tensor core applies the 128-byte swizzle to the absolute shared-memory address, so a
+  // tap-shifted operand (start address advanced by whole 128-byte rows inside a 1024-byte-aligned patch) needs
+  // base_offset = 0; setting it to (addr >> 7) & 7 gives wrong results.  V2V_DESC_MODE=0 restores that variant.
+  { const char* dm = getenv("V2V_DESC_MODE"); kp.desc_mode = (dm && dm[0] == '0') ? 0 : 1; }
   op.Cp = kp.Cp; op.Ktotal = op.conv.kh * op.conv.kw * kp.Cp;
 }
 
@@ -393,7 +396,7 @@ int v2v_plan_create(int device, int conv_impl, v2v_plan** out) {
   p->device = device;
   p->impl = conv_impl;
   const char* e = getenv("V2V_TAP_REUSE");
-  p->allow_reuse = (e && e[0] == '1');
+  p->allow_reuse = !(e && e[0] == '0');
   const char* ei = getenv("V2V_CONV_IMPL");
   if (ei && !strcmp(ei, "simt")) p->impl = V2V_IMPL_SIMT;
   *out = p;

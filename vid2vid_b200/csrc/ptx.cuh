@@ -135,7 +135,7 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
 // (canonical layout written by a TMA box whose inner extent is 64 bf16 with CU_TENSOR_MAP_SWIZZLE_128B).
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused for SW128 K-major: 1)
 //   bits [32,46) stride byte offset >> 4   bits [46,48) version = 1 (Blackwell)
-//   bits [49,52) base offset = (addr >> 7) & 7 when the start is not 1024 B aligned
+//   bits [49,52) base offset: left 0 (B200 swizzles on absolute smem address bits; see plan.cu desc_mode)
 //   bits [61,64) layout type: 2 = SWIZZLE_128B
 __device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr, int zero_base_offset = 0) {
   uint64_t d = 0;
