@@ -87,6 +87,7 @@ def run_case(name, c):
                 m = ref_shim.make_model_G(opt, single)
                 for s in range(c['n_scales']):
                     det_fill_(getattr(m, 'netG%d' % s), seed=c['seed'] + s)
+                    C.condition_flow_heads(getattr(m, 'netG%d' % s), c['flow_weight_scale'])
                 tG = opt.n_frames_G
                 seq = synth_label_sequence(c['n_gen'] + tG - 1, c['h'], c['w'], label_nc=c['label_nc'], block=8,
                                            seed=c['seed'])

@@ -62,7 +62,7 @@ CASES = {
                  h=128, w=256, seed=21, block=8, subsample=8),
     # Vid2VidModelG.inference, 3 scales, --fg --use_single_G, 4 generated frames
     'infer_s3': dict(kind='inference', label_nc=35, ngf=16, nd=2, n_blocks=4, n_blocks_local=2,
-                     n_scales=3, h=128, w=256, n_gen=4, seed=31),
+                     n_scales=3, h=128, w=256, n_gen=4, seed=31, flow_weight_scale=0.05),
 }
 
 
@@ -101,3 +101,13 @@ KEY_CASES = {
     'single_2048': dict(kind='local', input_nc=35, ngf=32, nd=4, n_blocks=9, n_blocks_local=3),
     'D_img': dict(kind='D', input_nc=39, ndf=64, n_layers=3, num_D=3),
 }
+
+
+def condition_flow_heads(net, scale):
+    """Random N(0,0.02) flow heads times the x20*2^s output scale give noise-like multi-pixel flows, which turn the
+    warp into an error amplifier no trained model has; the inference case shrinks the flow-head weights instead."""
+    import torch
+    with torch.no_grad():
+        if hasattr(net, 'model_final_flow'):
+            net.model_final_flow[1].weight.mul_(scale)
+            net.model_final_flow[1].bias.mul_(scale)

@@ -71,6 +71,15 @@ CASES = [
     ('d_first_layer_lrelu', lambda: [nn.Conv2d(39, 64, 4, stride=2, padding=2), nn.LeakyReLU(0.2, True)], (2, 39, 32, 48)),
     ('c3_1024_1024_32x64', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(1024, 1024, 3), BN(1024), nn.ReLU(True)], (1, 1024, 32, 64)),
     ('c3_512_512_16x32', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(512, 512, 3), BN(512), nn.ReLU(True)], (1, 512, 16, 32)),
+    # persistent paths: more tiles than SMs, resident / streamed weights, weight-set changes inside a CTA
+    ('mt_deconv_resident', lambda: NW._up(64, 32, BN), (1, 64, 64, 320)),
+    ('mt_c3_resident_R3', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(64, 64, 3), BN(64), nn.ReLU(True)], (1, 64, 96, 256)),
+    ('mt_c3_stream_R3', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(128, 128, 3), BN(128), nn.ReLU(True)], (1, 128, 96, 256)),
+    ('mt_c3_two_ntiles_resident', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(64, 256, 3), BN(256), nn.ReLU(True)], (1, 64, 96, 256)),
+    ('mt_s2', lambda: NW._down(32, 64, BN), (1, 32, 160, 512)),
+    ('mt_stem_R7', lambda: NW._stem(108, 32, BN), (1, 108, 80, 256)),
+    ('mt_stem_R7_cout128', lambda: NW._stem(108, 128, BN), (1, 108, 80, 256)),
+    ('mt_batch2_resblock', lambda: [NW.ResnetBlock(64, 'reflect', BN)], (2, 64, 48, 256)),
 ]
 
 
@@ -84,6 +93,7 @@ HEADS = [
     ('head_tanh_64_3', lambda: NW._stem(32, 64, BN), lambda: NW._head(64, 3, nn.Tanh()), 1.0, (1, 32, 12, 136)),
     ('head_flow_x20', lambda: NW._stem(32, 64, BN), lambda: NW._head(64, 2), 20.0, (1, 32, 16, 32)),
     ('head_sigmoid', lambda: NW._stem(32, 32, BN), lambda: NW._head(32, 1, nn.Sigmoid()), 1.0, (2, 32, 16, 140)),
+    ('mt_head', lambda: NW._stem(32, 64, BN), lambda: NW._head(64, 3, nn.Tanh()), 1.0, (1, 32, 80, 256)),
 ]
 
 

@@ -29,6 +29,7 @@ def test_inference_sequence_vs_reference_fixture():
     m.netG_i = det_fill_(NW.define_G(c['label_nc'], 3, 0, 16, 'global', 2, 'instance', 0, [], opt), seed=c['seed'] + 100).cuda()
     for s in range(c['n_scales']):
         det_fill_(getattr(m, 'netG%d' % s), seed=c['seed'] + s)
+        C.condition_flow_heads(getattr(m, 'netG%d' % s), c['flow_weight_scale'])
     tG = opt.n_frames_G
     seq = synth_label_sequence(c['n_gen'] + tG - 1, c['h'], c['w'], label_nc=c['label_nc'], block=8, seed=c['seed'])
     worst = 0.0
@@ -40,7 +41,7 @@ def test_inference_sequence_vs_reference_fixture():
         worst = max(worst, d.mean())
         assert torch.isfinite(fake_B).all()
         # recurrent generation: errors feed back through fake_B_prev; stated tolerance on [-1,1] images
-        assert d.mean() < 0.03 and d.max() < 0.35
+        assert d.mean() < 0.02 and d.max() < 0.35
     for si in range(c['n_scales']):
         d = np.abs(m.fake_B_prev[si].cpu().numpy() - gold['prev_state_%d' % si])
         assert d.mean() < 0.03

@@ -83,7 +83,10 @@ def test_inference_sequence():
     c = C.CASES['infer_s3']
     opt = C.inference_opt(c)
     gold = load('infer_s3')
-    sds = [det_fill_(NW.build_netG(opt, s), seed=c['seed'] + s).state_dict() for s in range(c['n_scales'])]
+    nets = [det_fill_(NW.build_netG(opt, s), seed=c['seed'] + s) for s in range(c['n_scales'])]
+    for n_ in nets:
+        C.condition_flow_heads(n_, c['flow_weight_scale'])
+    sds = [n_.state_dict() for n_ in nets]
     single = det_fill_(NW.GlobalGenerator(c['label_nc'], 3, 16, 2, opt.n_blocks, NW.get_norm_layer('instance')),
                        seed=c['seed'] + 100).state_dict()
     orc = GO.ModelGOracle(opt, sds, single, 'global', 2)

@@ -41,7 +41,7 @@ def main():
                     for b, p in zip(best, prof):
                         b[1] = min(b[1], p[1])
             for kind, ms, macs in best:
-                r = {'scale': s, 'kind': KINDS[kind], 'ms': ms}
+                r = {'scale': s, 'op': KINDS[kind], 'ms': ms}
                 if kind == 1:
                     c = convs[ci]
                     ci += 1
@@ -53,11 +53,11 @@ def main():
     lines = ['total %.3f ms over %d kernels' % (total, len(rows))]
     bykind = {}
     for r in rows:
-        bykind[r['kind']] = bykind.get(r['kind'], 0) + r['ms']
+        bykind[r['op']] = bykind.get(r['op'], 0) + r['ms']
     lines.append('by kind: ' + ', '.join('%s %.3f' % kv for kv in sorted(bykind.items(), key=lambda kv: -kv[1])))
     agg = {}
     for r in rows:
-        if r['kind'] != 'conv':
+        if r['op'] != 'conv':
             continue
         key = (r['scale'], r['Cin'], r['Cout'], tuple(r['k']), r['stride'], r['transposed'], tuple(r['grid']), r['R'], r['TH'], r['TW'])
         a = agg.setdefault(key, [0, 0.0, 0.0])

@@ -327,15 +327,33 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   kp.Cp = round_up(op.conv.Cin, 64); kp.cblocks = kp.Cp / 64;
   kp.R = g.R;
   kp.a_slot_bytes = round_up((g.TW + g.R - 1) * g.TH * 128, 1024);
-  kp.b_slot_bytes = kp.BN * 128;
-  const int budget = 200 * 1024;
-  if (g.R == 1) {
+  // shared-memory budget: 227 KB - stats scratch (8 KB) - alignment slack - barriers
+  const int budget = 212 * 1024;
+  // a weight slot holds the R taps served by one activation patch; keep >= 2 slots + 3 patches in the budget
+  while (g.R > 1 && kp.BN > 32 && 2 * g.R * kp.BN * 128 + 3 * kp.a_slot_bytes > budget) kp.BN /= 2;
+  kp.b_slot_bytes = g.R * kp.BN * 128;
+  kp.n_tiles = (kp.Cout + kp.BN - 1) / kp.BN;
+  kp.m_total = kp.N * kp.tiles_x * kp.tiles_y;
+  kp.total_tiles = kp.m_total * kp.n_tiles * g.n_phases;
+  int max_phase_groups = 0;
+  for (int i = 0; i < g.n_phases; ++i) max_phase_groups = std::max(max_phase_groups, g.phases[i].group_end - g.phases[i].group_begin);
+  const int nB = max_phase_groups * kp.cblocks;                 // weight slots of one (phase, N tile)
+  const char* er = getenv("V2V_B_RESIDENT");
+  const bool allow_res = !(er && er[0] == '0');
+  // resident weights pay off when a CTA walks several M tiles with the same weights
+  const bool many_m = kp.m_total > 148;
+  if (allow_res && many_m && (long long)nB * kp.b_slot_bytes <= 150 * 1024 &&
+      budget - nB * kp.b_slot_bytes >= 2 * kp.a_slot_bytes) {
+    kp.b_resident = 1;
+    kp.SB = nB;
+    kp.SA = std::max(2, std::min(6, (budget - nB * kp.b_slot_bytes) / kp.a_slot_bytes));
+  } else if (g.R == 1) {
     int s = budget / (kp.a_slot_bytes + kp.b_slot_bytes);
     s = std::max(2, std::min(8, s));
     kp.SA = kp.SB = s;
   } else {
     kp.SA = 3;
-    kp.SB = std::max(2, std::min(8, (budget - kp.SA * kp.a_slot_bytes) / kp.b_slot_bytes));
+    kp.SB = std::max(2, std::min(6, (budget - kp.SA * kp.a_slot_bytes) / kp.b_slot_bytes));
   }
   kp.num_phases = g.n_phases;
   memcpy(kp.phases, g.phases, sizeof(kp.phases));
@@ -345,10 +363,6 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   kp.bias = op.conv.bias;
   kp.lrelu_slope = op.slope;
   kp.act = op.act;
-  // Measured on B200: the tensor core applies the 128-byte swizzle to the absolute shared-memory address, so a
-  // tap-shifted operand (start address advanced by whole 128-byte rows inside a 1024-byte-aligned patch) needs
-  // base_offset = 0; setting it to (addr >> 7) & 7 gives wrong results.  V2V_DESC_MODE=0 restores that variant.
-  { const char* dm = getenv("V2V_DESC_MODE"); kp.desc_mode = (dm && dm[0] == '0') ? 0 : 1; }
   op.Cp = kp.Cp; op.Ktotal = op.conv.kh * op.conv.kw * kp.Cp;
 }
 

@@ -51,6 +51,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// One lane of a converged warp; lets ptxas keep the following tcgen05 / TMA instructions on the uniform datapath
+// (a plain `lane == 0` test makes it wrap every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop: measured
+// ~290 cycles per MMA instead of 64).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred != 0;
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ------------------------------------------------------------------ TMA
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
@@ -135,15 +156,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
 // (canonical layout written by a TMA box whose inner extent is 64 bf16 with CU_TENSOR_MAP_SWIZZLE_128B).
 //   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused for SW128 K-major: 1)
 //   bits [32,46) stride byte offset >> 4   bits [46,48) version = 1 (Blackwell)
-//   bits [49,52) base offset: left 0 (B200 swizzles on absolute smem address bits; see plan.cu desc_mode)
+//   bits [49,52) base offset: 0.  Measured on B200: the swizzle is applied to absolute shared-memory address bits,
+//                so an operand whose start is advanced by whole 128-byte rows inside a 1024-byte-aligned patch
+//                (tap reuse) still needs 0; the `(addr >> 7) & 7` variant gives wrong results.
 //   bits [61,64) layout type: 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr, int zero_base_offset = 0) {
+__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>(1) << 16;
   d |= static_cast<uint64_t>(1024 >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  if (!zero_base_offset) d |= static_cast<uint64_t>((smem_addr >> 7) & 7) << 49;
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }

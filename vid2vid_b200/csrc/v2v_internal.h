@@ -70,6 +70,8 @@ struct ConvKernelParams {
   int Cp, cblocks;                   // padded input channels, Cp/64
   int R;                             // taps served per A patch (1 = none)
   int a_slot_bytes, b_slot_bytes, SA, SB;
+  int b_resident;                    // 1: SB == B tiles of one (phase, n-tile): loaded once per key, kept in smem
+  int n_tiles, m_total, total_tiles; // N tiles, M tiles (N * tiles_x * tiles_y), all tiles incl. phases
   int num_phases;
   ConvPhase phases[V2V_MAX_PHASES];
   ConvGroup groups[V2V_MAX_TAPS];
@@ -92,7 +94,6 @@ struct ConvKernelParams {
   float head_scale[V2V_MAX_HEAD];
   float lrelu_slope;
   int act;                           // EPI_ACT_BF16 activation
-  int desc_mode;                     // debug: 0 = smem descriptor base_offset per PTX doc, 1 = always 0
 };
 
 // kernel launchers (defined in the .cu files); all enqueue on `stream` and return cudaError_t
