@@ -105,6 +105,12 @@ typedef struct v2v_conv_desc {
   int output_padding;
   const float* weight; /* conv: [Cout][Cin][kh][kw]; transposed: [Cin][Cout][kh][kw] */
   const float* bias;   /* [Cout] or NULL */
+  /* Optional second parameter set stacked along Cout (heads only): output channels [Cout - Cout2, Cout) come from
+   * weight2 [Cout2][Cin][kh][kw] / bias2.  Lets two reference convs that read the same input (model_final_flow and
+   * model_final_w, models/networks.py:182-183) run as one convolution.  Cout2 == 0: unused. */
+  int Cout2;
+  const float* weight2;
+  const float* bias2;
 } v2v_conv_desc;
 
 typedef struct v2v_norm_desc {

@@ -152,6 +152,6 @@ def test_plan_describe_layouts():
     assert d['conv_macs'] == 1057493090304
     # every value consumed by a stride-2 conv is parity split; reflect-3 layouts feed the 7x7 convs
     convs = d['convs']
-    assert sum(1 for c in convs if c['k'] == [7, 7]) == 3 + 4          # stems + heads
+    assert sum(1 for c in convs if c['k'] == [7, 7]) == 3 + 3          # stems + heads (flow and weight heads fused)
     assert all(c['TH'] * c['TW'] == 128 for c in convs)
     assert any(c['R'] == 7 for c in convs) and any(c['phases'] == 4 for c in convs)

@@ -11,7 +11,7 @@ import bench                                       # noqa: E402
 from vid2vid_b200.model_g import Vid2VidModelG     # noqa: E402
 from vid2vid_b200.utils import synth_label_sequence   # noqa: E402
 
-KINDS = {0: 'import', 1: 'conv', 2: 'rawstats', 3: 'finalize', 4: 'apply', 5: 'export', 6: 'composite'}
+KINDS = {0: 'import', 1: 'conv', 2: 'rawstats', 3: 'finalize', 4: 'apply', 5: 'export', 6: 'composite', 7: 'memset'}
 
 
 def main():

@@ -18,7 +18,8 @@ IMPL_UMMA, IMPL_SIMT = 0, 1
 class ConvDesc(C.Structure):
     _fields_ = [('Cin', C.c_int), ('Cout', C.c_int), ('kh', C.c_int), ('kw', C.c_int), ('stride', C.c_int),
                 ('pad', C.c_int), ('pad_mode', C.c_int), ('transposed', C.c_int), ('output_padding', C.c_int),
-                ('weight', C.c_void_p), ('bias', C.c_void_p)]
+                ('weight', C.c_void_p), ('bias', C.c_void_p), ('Cout2', C.c_int), ('weight2', C.c_void_p),
+                ('bias2', C.c_void_p)]
 
 
 class NormDesc(C.Structure):

@@ -48,7 +48,7 @@ __global__ void conv_simt_kernel(ActDesc in, const bf16* __restrict__ w, int Kto
     }
     const int oy = gy * p.oy_mul + ph.oy_add, ox = gx * p.ox_mul + ph.ox_add;
     if (p.epi == EPI_HEAD_F32) {
-      float v = acc + (p.bias ? p.bias[co] : 0.f);
+      float v = acc + (p.bias ? ((p.bias2 && co >= p.Cout1) ? p.bias2[co - p.Cout1] : p.bias[co]) : 0.f);
       v = simt_act(v, p.head_act[co], p.lrelu_slope) * p.head_scale[co];
       reinterpret_cast<float*>(p.io[p.head_slot[co]])[p.head_off[co] + (size_t)n * p.head_bstride[co] + (size_t)oy * p.out_W + ox] = v;
     } else if (p.epi == EPI_RAW_STATS) {

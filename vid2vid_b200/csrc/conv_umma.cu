@@ -199,12 +199,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tcgen05_fence_after();
           const uint32_t b_base = smem_u32(sB + (size_t)slot * p.b_slot_bytes);
           if (elect_one_sync()) {
+            // descriptors differ only in the 14-bit (address >> 4) field: build once per slot, then add
+            const uint64_t adesc0 = make_sw128_kmajor_desc(a_base), bdesc0 = make_sw128_kmajor_desc(b_base);
             for (int r = 0; r < p.R; ++r) {
+              const uint64_t ad = adesc0 + (uint64_t)(r * 8), bd = bdesc0 + (uint64_t)((r * b_tx) >> 4);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {    // 4 x (K = 16 bf16 = 32 bytes) per 128-byte swizzle row
-                umma_bf16(tmem_d, make_sw128_kmajor_desc(a_base + r * 128 + k * 32),
-                          make_sw128_kmajor_desc(b_base + r * b_tx + k * 32), idesc, (r == 0 && k == 0) ? acc : 1u);
-              }
+              for (int k = 0; k < 4; ++k)      // 4 x (K = 16 bf16 = 32 bytes) per 128-byte swizzle row
+                umma_bf16(tmem_d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (r == 0 && k == 0) ? acc : 1u);
             }
             if (!p.b_resident || last_of_key) umma_commit(&b_empty[slot]);     // weight slot free when these retire
           }
@@ -231,6 +232,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp & 3;
     const int etid = q * 32 + lane;
     int it = 0;
+    // per-CTA running (sum, sumsq) of column n0 + etid; flushed when (phase, N tile, image) changes: one partial
+    // row per (phase, image, CTA) instead of one per tile keeps the finalize pass tiny
+    float s_acc = 0.f, q_acc = 0.f;
+    int acc_key = -1, acc_img = -1, acc_n0 = 0, acc_phase = 0;
     for (int t = t_first; t < p.total_tiles; t += t_step, ++it) {
       const Tile tl = decode_tile(p, t);
       const ConvPhase ph = p.phases[tl.phase];
@@ -260,7 +265,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < V2V_MAX_HEAD; ++j) {
             if (j < p.Cout) {
               float v = __uint_as_float(r[j]);
-              if (p.bias) v += __ldg(p.bias + j);
+              if (p.bias) v += (p.bias2 && j >= p.Cout1) ? __ldg(p.bias2 + j - p.Cout1) : __ldg(p.bias + j);
               v = apply_act(v, p.head_act[j], p.lrelu_slope) * p.head_scale[j];
               reinterpret_cast<float*>(p.io[p.head_slot[j]])[p.head_off[j] + (size_t)n_img * p.head_bstride[j] + pix] = v;
             }
@@ -322,18 +327,29 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         if (do_stats) {
           named_bar_sync(1, kEpiThreads);        // the four epilogue warps only
-          if (etid < p.BN && n0 + etid < p.stats_C) {
-            float s = 0.f, qq = 0.f;
+          if (etid < p.BN) {
+            if (tl.key != acc_key || n_img != acc_img) {
+              if (acc_key >= 0 && acc_n0 + etid < p.stats_C) {
+                const size_t rowi = ((size_t)acc_phase * p.N + acc_img) * gridDim.x + blockIdx.x;
+                p.stats[(rowi * 2 + 0) * p.stats_C + acc_n0 + etid] = s_acc;
+                p.stats[(rowi * 2 + 1) * p.stats_C + acc_n0 + etid] = q_acc;
+              }
+              s_acc = q_acc = 0.f;
+              acc_key = tl.key; acc_img = n_img; acc_n0 = n0; acc_phase = tl.phase;
+            }
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
-              s += redp[(w * 2 + 0) * 128 + etid];
-              qq += redp[(w * 2 + 1) * 128 + etid];
+              s_acc += redp[(w * 2 + 0) * 128 + etid];
+              q_acc += redp[(w * 2 + 1) * 128 + etid];
             }
-            p.stats[((size_t)tl.row * 2 + 0) * p.stats_C + n0 + etid] = s;
-            p.stats[((size_t)tl.row * 2 + 1) * p.stats_C + n0 + etid] = qq;
           }
         }
       }
+    }
+    if (acc_key >= 0 && etid < p.BN && acc_n0 + etid < p.stats_C) {
+      const size_t rowi = ((size_t)acc_phase * p.N + acc_img) * gridDim.x + blockIdx.x;
+      p.stats[(rowi * 2 + 0) * p.stats_C + acc_n0 + etid] = s_acc;
+      p.stats[(rowi * 2 + 1) * p.stats_C + acc_n0 + etid] = q_acc;
     }
   }
 
@@ -342,7 +358,16 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-static int g_sm_count = 0;
+int device_sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
 
 cudaError_t launch_conv_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p,
                              cudaStream_t stream) {
@@ -354,14 +379,7 @@ cudaError_t launch_conv_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  if (!g_sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-    if (g_sm_count <= 0) g_sm_count = 148;
-  }
-  const int grid = p.total_tiles < g_sm_count ? p.total_tiles : g_sm_count;
-  conv_umma_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  conv_umma_kernel<<<p.grid, kThreads, smem, stream>>>(tmA, tmB, p);
   return cudaGetLastError();
 }
 

@@ -81,9 +81,14 @@ __global__ void pack_weights_kernel(PackParams p) {
     float v = 0.f;
     if (c < p.Cin) {
       const int ky = p.tap_ky[t], kx = p.tap_kx[t];
-      const size_t wi = p.transposed ? ((((size_t)c * p.Cout + co) * p.kh + ky) * p.kw + kx)
-                                     : ((((size_t)co * p.Cin + c) * p.kh + ky) * p.kw + kx);
-      v = p.w[wi];
+      if (p.w2 && co >= p.Cout1) {
+        v = p.w2[((((size_t)(co - p.Cout1)) * p.Cin + c) * p.kh + ky) * p.kw + kx];
+      } else {
+        const int co1 = p.w2 ? p.Cout1 : p.Cout;
+        const size_t wi = p.transposed ? ((((size_t)c * co1 + co) * p.kh + ky) * p.kw + kx)
+                                       : ((((size_t)co * p.Cin + c) * p.kh + ky) * p.kw + kx);
+        v = p.w[wi];
+      }
     }
     p.out[idx] = __float2bfloat16_rn(v);
   }

@@ -171,7 +171,7 @@ struct GOp {
   ConvKernelParams kp{};
 };
 
-enum XKind { X_IMPORT, X_CONV, X_RAWSTATS, X_FINALIZE, X_APPLY, X_EXPORT, X_COMPOSITE };
+enum XKind { X_IMPORT, X_CONV, X_RAWSTATS, X_FINALIZE, X_APPLY, X_EXPORT, X_COMPOSITE, X_MEMSET };
 struct XOp {
   XKind kind;
   int gop = -1;
@@ -181,6 +181,7 @@ struct XOp {
   ApplyParams app{};
   CompositeParams comp{};
   RawDesc rawd{}; float* stats = nullptr; int stats_C = 0;
+  void* ms_ptr = nullptr; size_t ms_bytes = 0;
 };
 
 }  // namespace v2v
@@ -355,6 +356,7 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
     kp.SA = 3;
     kp.SB = std::max(2, std::min(6, (budget - kp.SA * kp.a_slot_bytes) / kp.b_slot_bytes));
   }
+  kp.grid = std::min(kp.total_tiles, device_sm_count());
   kp.num_phases = g.n_phases;
   memcpy(kp.phases, g.phases, sizeof(kp.phases));
   memcpy(kp.groups, g.groups, sizeof(kp.groups));
@@ -369,6 +371,7 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
 static int pack_one(const GOp& op, cudaStream_t stream) {
   PackParams pp{};
   pp.w = op.conv.weight; pp.transposed = op.conv.transposed;
+  pp.w2 = op.conv.Cout2 > 0 ? op.conv.weight2 : nullptr; pp.Cout1 = op.conv.Cout - op.conv.Cout2;
   pp.Cout = op.conv.Cout; pp.Cin = op.conv.Cin; pp.kh = op.conv.kh; pp.kw = op.conv.kw;
   pp.Cp = op.Cp; pp.ntaps = op.conv.kh * op.conv.kw;
   for (int ky = 0; ky < op.conv.kh; ++ky)
@@ -386,6 +389,7 @@ static int run_xop(v2v_plan* P, const XOp& x, cudaStream_t s) {
     case X_APPLY: V2V_CUDA(launch_norm_apply(x.app, s)); break;
     case X_COMPOSITE: V2V_CUDA(launch_composite(x.comp, s)); break;
     case X_RAWSTATS: V2V_CUDA(launch_raw_stats(x.rawd, x.stats, x.stats_C, s)); break;
+    case X_MEMSET: V2V_CUDA(cudaMemsetAsync(x.ms_ptr, 0, x.ms_bytes, s)); break;
     case X_CONV: {
       const GOp& op = P->gops[x.gop];
       if (P->impl == V2V_IMPL_UMMA) V2V_CUDA(launch_conv_umma(op.tmA, op.tmB, op.kp, s));
@@ -556,16 +560,21 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
       if (op.kind == G_CONV) {
         Raw& r = P->raws[op.raw];
         r.desc.N = r.N; r.desc.H = r.H; r.desc.W = r.W; r.desc.Cvalid = r.C; r.desc.C = round_up(r.C, 8);
-        if (P->impl == V2V_IMPL_UMMA) { r.tiles_per_img = op.kp.tiles_x * op.kp.tiles_y; r.num_phases = op.kp.num_phases; }
+        if (P->impl == V2V_IMPL_UMMA) { r.tiles_per_img = op.kp.grid; r.num_phases = op.kp.num_phases; }
         else { r.tiles_per_img = 1; r.num_phases = 1; }
         r.stats_rows = r.num_phases * r.N * r.tiles_per_img;
         raw_off[op.raw].raw = take(r.desc.elems() * sizeof(bf16));
-        raw_off[op.raw].stats = take((size_t)r.stats_rows * 2 * r.C * sizeof(float));
         raw_off[op.raw].scale = take((size_t)r.N * r.C * sizeof(float));
         raw_off[op.raw].shift = take((size_t)r.N * r.C * sizeof(float));
       }
     }
   }
+  // all norm-statistics partials live in one contiguous region that is zeroed at the start of every run
+  // (a CTA only writes the (phase, image) rows it actually worked on)
+  const size_t stats_begin = off;
+  for (size_t i = 0; i < P->raws.size(); ++i)
+    if (P->raws[i].conv_op >= 0) raw_off[i].stats = take((size_t)P->raws[i].stats_rows * 2 * P->raws[i].C * sizeof(float));
+  const size_t stats_end = off;
   P->arena_bytes = off;
   V2V_CUDA(cudaMalloc(&P->arena, P->arena_bytes));
   V2V_CUDA(cudaMemsetAsync(P->arena, 0, P->arena_bytes, stream));
@@ -581,6 +590,10 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
   }
 
   // ---- emit executable ops
+  if (stats_end > stats_begin) {
+    XOp m; m.kind = X_MEMSET; m.ms_ptr = base + stats_begin; m.ms_bytes = stats_end - stats_begin;
+    P->xops.push_back(m);
+  }
   for (size_t i = 0; i < P->gops.size(); ++i) {
     GOp& op = P->gops[i];
     switch (op.kind) {
@@ -612,6 +625,7 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
           kp.epi = EPI_ACT_BF16; kp.out_act = P->acts[vo.bufs[0]]; kp.out_C = kp.out_act.C;
         } else {
           kp.epi = EPI_HEAD_F32;
+          kp.bias2 = op.conv.Cout2 > 0 ? op.conv.bias2 : nullptr; kp.Cout1 = op.conv.Cout - op.conv.Cout2;
           for (int j = 0; j < op.conv.Cout; ++j) {
             kp.head_slot[j] = op.head[j].slot;
             kp.head_off[j] = (long long)op.head[j].channel * op.geom.out_h * op.geom.out_w;

@@ -84,6 +84,8 @@ struct ConvKernelParams {
   float* stats;                      // [tile rows][2][stats_C] partial (sum, sumsq); may be null
   int stats_C;
   const float* bias;                 // may be null
+  const float* bias2; int Cout1;     // fused heads: channels >= Cout1 take bias2[j - Cout1]
+  int grid;                          // CTAs launched (persistent); also the stats partial rows per (phase, image)
   // EPI_HEAD_F32: per output channel destination = io[head_slot] + head_off (+ n * head_bstride),
   // activation and scale.  Caller pointers are read from the device IO table at run time.
   void* const* io;
@@ -149,6 +151,7 @@ struct ExportParams {
 
 struct PackParams {
   const float* w;          // torch layout: conv [Cout][Cin][kh][kw]; transposed conv [Cin][Cout][kh][kw]
+  const float* w2; int Cout1;   // optional second source for output channels >= Cout1
   int transposed;
   int Cout, Cin, kh, kw;
   int Cp, ntaps;
@@ -173,5 +176,6 @@ cudaError_t launch_import_nchw(const ImportParams& p, cudaStream_t stream);
 cudaError_t launch_export_nchw(const ExportParams& p, cudaStream_t stream);
 cudaError_t launch_pack_weights(const PackParams& p, cudaStream_t stream);
 cudaError_t launch_composite(const CompositeParams& p, cudaStream_t stream);
+int device_sm_count();
 
 }  // namespace v2v

@@ -198,6 +198,18 @@ def emit_head(plan, mods, v, dst):
     plan.head(v, conv_desc(conv, pmode, pad), [(slot, j, dst_c, act, scale) for j in range(conv.out_channels)])
 
 
+def emit_head_pair(plan, mods_a, dst_a, mods_b, dst_b, v):
+    """Two heads that read the same value (model_final_flow + model_final_w, networks.py:182-183,212-213) as ONE
+    convolution with the weights stacked along Cout: halves the activation traffic of the 7x7 heads."""
+    (ua,), (ub,) = _units(mods_a), _units(mods_b)
+    _, ca, pmode, pad, na, act_a, _ = ua
+    _, cb, pmode_b, pad_b, nb, act_b, _ = ub
+    assert na is None and nb is None and (pmode, pad) == (pmode_b, pad_b)
+    chans = [(dst_a[0], j, dst_a[1], act_a, dst_a[2]) for j in range(ca.out_channels)]
+    chans += [(dst_b[0], j, dst_b[1], act_b, dst_b[2]) for j in range(cb.out_channels)]
+    plan.head(v, conv_desc(ca, pmode, pad, m2=cb), chans)
+
+
 class _Planned(nn.Module):
     """Caches one plan per input-shape key; re-packs weights when parameters were modified in place
     and rebuilds when their storage moved (.cuda(), .to())."""
@@ -316,8 +328,8 @@ class CompositeGenerator(_Planned):
         if not self.no_flow:
             flow_feat = emit_seq(plan, self.model_up_flow, emit_seq(plan, self.model_res_flow, down))   # :210-211
             plan.export(flow_feat, S_FLOWF)
-            emit_head(plan, self.model_final_flow, flow_feat, (S_FLOW, 2, self.flow_multiplier))        # :212
-            emit_head(plan, self.model_final_w, flow_feat, (S_W, 1, 1.0))                               # :213
+            emit_head_pair(plan, self.model_final_flow, (S_FLOW, 2, self.flow_multiplier),               # :212
+                           self.model_final_w, (S_W, 1, 1.0), flow_feat)                                # :213
         if self.use_fg_model:
             fg_feat = emit_seq(plan, self.indv_up, emit_seq(plan, self.indv_res, emit_seq(plan, self.indv_down, v_in)))
             plan.export(fg_feat, S_FGF)                                                    # :225
@@ -401,8 +413,8 @@ class CompositeLocalGenerator(CompositeGenerator):
             cf = plan.input(S_CF, N, c2, 0, c2, h2, w2)
             flow_feat = emit_seq(plan, self.model_up_flow, fin((seg, cf)))       # :305
             plan.export(flow_feat, S_FLOWF)
-            emit_head(plan, self.model_final_flow, flow_feat, (S_FLOW, 2, 20.0 * (2 ** self.scale)))   # :297,306
-            emit_head(plan, self.model_final_w, flow_feat, (S_W, 1, 1.0))
+            emit_head_pair(plan, self.model_final_flow, (S_FLOW, 2, 20.0 * (2 ** self.scale)),         # :297,306
+                           self.model_final_w, (S_W, 1, 1.0), flow_feat)
         if self.use_fg_model:
             cg_c = self.indv_down[4].out_channels
             cg = plan.input(S_CG, N, cg_c, 0, cg_c, h2, w2)

@@ -14,7 +14,7 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
 
 
-def conv_desc(m, pad_mode=L.PAD_ZERO, pad=None):
+def conv_desc(m, pad_mode=L.PAD_ZERO, pad=None, m2=None):
     """v2v_conv_desc for an nn.Conv2d / nn.ConvTranspose2d parameter container.  `pad`/`pad_mode`
     override the module's own zero padding when a ReflectionPad2d precedes it."""
     d = L.ConvDesc()
@@ -29,6 +29,13 @@ def conv_desc(m, pad_mode=L.PAD_ZERO, pad=None):
     d.output_padding = m.output_padding[0] if tr else 0
     d.weight = m.weight.data_ptr()
     d.bias = m.bias.data_ptr() if m.bias is not None else None
+    if m2 is not None:       # second conv with the same geometry stacked along Cout (fused heads)
+        assert (m2.in_channels, m2.kernel_size, m2.stride, m2.padding) == (m.in_channels, m.kernel_size, m.stride, m.padding)
+        assert (m2.bias is None) == (m.bias is None)
+        d.Cout = m.out_channels + m2.out_channels
+        d.Cout2 = m2.out_channels
+        d.weight2 = m2.weight.data_ptr()
+        d.bias2 = m2.bias.data_ptr() if m2.bias is not None else None
     return d
 
 
@@ -143,7 +150,7 @@ class Plan:
         for i in range(self.n_slots):
             t = io[i] if i < len(io) else None
             arr[i] = t.data_ptr() if t is not None else None
-        n = self.num_kernels
+        n = self.num_kernels + 4
         kinds, ms, macs, cnt = (C.c_int * n)(), (C.c_float * n)(), (C.c_double * n)(), C.c_int()
         L.check(L.lib().v2v_plan_profile(self._h, arr, self.n_slots, L.current_stream_ptr(), n, kinds, ms, macs,
                                          C.byref(cnt)))
