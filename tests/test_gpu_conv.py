@@ -80,6 +80,14 @@ CASES = [
     ('mt_stem_R7', lambda: NW._stem(108, 32, BN), (1, 108, 80, 256)),
     ('mt_stem_R7_cout128', lambda: NW._stem(108, 128, BN), (1, 108, 80, 256)),
     ('mt_batch2_resblock', lambda: [NW.ResnetBlock(64, 'reflect', BN)], (2, 64, 48, 256)),
+    # 16- and 32-channel K blocks (32-byte / 64-byte swizzled rows), with and without tap reuse
+    ('kc16_stem_R7', lambda: NW._stem(6, 32, BN), (1, 6, 12, 136)),
+    ('kc16_stem_R7_mt', lambda: NW._stem(6, 32, BN), (1, 6, 80, 256)),
+    ('kc32_c3_R3', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(32, 32, 3), BN(32), nn.ReLU(True)], (1, 32, 8, 160)),
+    ('kc32_resblock_mt', lambda: [NW.ResnetBlock(32, 'reflect', BN)], (1, 32, 96, 256)),
+    ('kc16_s2_then_kc32_deconv', lambda: NW._down(16, 32, BN) + NW._up(32, 16, BN), (1, 16, 32, 64)),
+    ('kc16_resblock_small', lambda: [NW.ResnetBlock(16, 'reflect', BN)], (1, 16, 16, 32)),
+    ('kc32_s2_mt', lambda: NW._down(32, 64, BN), (1, 32, 160, 512)),
 ]
 
 
@@ -94,6 +102,8 @@ HEADS = [
     ('head_flow_x20', lambda: NW._stem(32, 64, BN), lambda: NW._head(64, 2), 20.0, (1, 32, 16, 32)),
     ('head_sigmoid', lambda: NW._stem(32, 32, BN), lambda: NW._head(32, 1, nn.Sigmoid()), 1.0, (2, 32, 16, 140)),
     ('mt_head', lambda: NW._stem(32, 64, BN), lambda: NW._head(64, 3, nn.Tanh()), 1.0, (1, 32, 80, 256)),
+    ('kc32_head_mt', lambda: NW._stem(32, 32, BN), lambda: NW._head(32, 3, nn.Tanh()), 1.0, (1, 32, 80, 256)),
+    ('kc16_head', lambda: NW._stem(32, 16, BN), lambda: NW._head(16, 3, nn.Tanh()), 1.0, (1, 32, 12, 136)),
 ]
 
 

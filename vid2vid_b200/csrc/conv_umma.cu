@@ -1,6 +1,6 @@
 // Implicit-GEMM convolution on tcgen05 tensor cores (sm_100a), persistent and warp-specialised.
 //
-//   D[128 pixels x BN channels] (fp32, TMEM) = sum over (tap, 64-channel block) A[128 x 64] * B[BN x 64]^T
+//   D[128 pixels x BN channels] (fp32, TMEM) = sum over (tap, K block of kc = 16/32/64 channels) A[128 x kc] * B[BN x kc]^T
 //
 // A tiles are boxes of the halo-padded NHWC bf16 activation buffer fetched by TMA (5-D tiled map,
 // 128-byte swizzle): a box of TH x TW pixels x 64 channels lands in shared memory as 128 rows of
@@ -117,8 +117,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int a_tx = (p.TW + p.R - 1) * p.TH * 128;
-  const int b_tx = p.BN * 128;
+  const int a_tx = (p.TW + p.R - 1) * p.TH * p.row_bytes;
+  const int b_tx = p.BN * p.row_bytes;
   const int t_first = blockIdx.x, t_step = gridDim.x;
 
   if (warp == 0) {
@@ -138,7 +138,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int cb = 0; cb < p.cblocks; ++cb) {
             mbar_wait(&a_empty[sa], pa ^ 1);
             mbar_expect_tx(&a_full[sa], a_tx);
-            tma_load_5d(sA + (size_t)sa * p.a_slot_bytes, &tmA, &a_full[sa], cb * 64, tl.x0 + grp.dx, tl.y0 + grp.dy,
+            tma_load_5d(sA + (size_t)sa * p.a_slot_bytes, &tmA, &a_full[sa], cb * p.kc, tl.x0 + grp.dx, tl.y0 + grp.dy,
                         grp.plane, tl.n_img);
             if (++sa == p.SA) { sa = 0; pa ^= 1; }
             if (!load_b) continue;
@@ -150,7 +150,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_expect_tx(&b_full[slot], b_tx * p.R);             // one barrier for the R taps of this patch
             for (int r = 0; r < p.R; ++r)
               tma_load_2d(sB + (size_t)slot * p.b_slot_bytes + (size_t)r * b_tx, &tmB, &b_full[slot],
-                          (grp.tap0 + r) * p.Cp + cb * 64, tl.n0);
+                          (grp.tap0 + r) * p.Cp + cb * p.kc, tl.n0);
             if (!p.b_resident && ++sb == p.SB) { sb = 0; pb ^= 1; }
           }
         }
@@ -200,12 +200,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t b_base = smem_u32(sB + (size_t)slot * p.b_slot_bytes);
           if (elect_one_sync()) {
             // descriptors differ only in the 14-bit (address >> 4) field: build once per slot, then add
-            const uint64_t adesc0 = make_sw128_kmajor_desc(a_base), bdesc0 = make_sw128_kmajor_desc(b_base);
-            for (int r = 0; r < p.R; ++r) {
-              const uint64_t ad = adesc0 + (uint64_t)(r * 8), bd = bdesc0 + (uint64_t)((r * b_tx) >> 4);
-#pragma unroll
-              for (int k = 0; k < 4; ++k)      // 4 x (K = 16 bf16 = 32 bytes) per 128-byte swizzle row
-                umma_bf16(tmem_d, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (r == 0 && k == 0) ? acc : 1u);
+            const uint64_t adesc0 = make_kmajor_desc(a_base, p.sbo_bytes, p.layout_type);
+            const uint64_t bdesc0 = make_kmajor_desc(b_base, p.sbo_bytes, p.layout_type);
+            const uint64_t a_step = (uint64_t)(p.row_bytes >> 4), b_step = (uint64_t)(b_tx >> 4);
+            uint64_t ad = adesc0, bd = bdesc0;
+            uint32_t first = acc;
+            // K = 16 bf16 = 32 bytes per MMA; kc/16 MMAs per smem row (fixed trip counts keep the issue loop tight)
+            if (p.kmma == 4) {
+              for (int r = 0; r < p.R; ++r, ad += a_step, bd += b_step) {
+                umma_bf16(tmem_d, ad, bd, idesc, first);
+                umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
+                umma_bf16(tmem_d, ad + 4, bd + 4, idesc, 1u);
+                umma_bf16(tmem_d, ad + 6, bd + 6, idesc, 1u);
+                first = 1u;
+              }
+            } else if (p.kmma == 2) {
+              for (int r = 0; r < p.R; ++r, ad += a_step, bd += b_step) {
+                umma_bf16(tmem_d, ad, bd, idesc, first);
+                umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
+                first = 1u;
+              }
+            } else {
+              for (int r = 0; r < p.R; ++r, ad += a_step, bd += b_step) {
+                umma_bf16(tmem_d, ad, bd, idesc, first);
+                first = 1u;
+              }
             }
             if (!p.b_resident || last_of_key) umma_commit(&b_empty[slot]);     // weight slot free when these retire
           }

@@ -45,6 +45,7 @@ __global__ void import_nchw_kernel(ImportParams p) {
   for (int px = threadIdx.y; px < 32; px += 8) {
     const int xo = xt + px;
     if (xo >= Wpad) continue;
+    if (cblk + 2 * (int)threadIdx.x >= o.C) continue;      // C may be 16 or 32
     const uint32_t pk = pack_bf16x2(tile[2 * threadIdx.x][px], tile[2 * threadIdx.x + 1][px]);
     *reinterpret_cast<uint32_t*>(o.base + o.offset(n, yp - o.pad_t, xo - o.pad_l) + cblk + 2 * threadIdx.x) = pk;
   }
@@ -97,7 +98,7 @@ __global__ void pack_weights_kernel(PackParams p) {
 cudaError_t launch_import_nchw(const ImportParams& p, cudaStream_t stream) {
   const ActDesc& o = p.out;
   const int Wpad = o.W + o.pad_l + o.pad_r, Hpad = o.H + o.pad_t + o.pad_b;
-  dim3 grid((Wpad + 31) / 32, Hpad * o.N, o.C / 64), block(32, 8);
+  dim3 grid((Wpad + 31) / 32, Hpad * o.N, (o.C + 63) / 64), block(32, 8);
   import_nchw_kernel<<<grid, block, 0, stream>>>(p);
   return cudaGetLastError();
 }

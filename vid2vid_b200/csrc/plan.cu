@@ -44,6 +44,12 @@ void set_error(const char* fmt, ...) {
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline size_t round_up_sz(size_t a, size_t b) { return (a + b - 1) / b * b; }
+// padded channel count of an activation buffer: one K block of min(C,64) channels per shared-memory row
+static inline int pad_channels(int c) {
+  const char* e = getenv("V2V_KC64");
+  if (e && e[0] == '1') return round_up(c, 64);
+  return c <= 16 ? 16 : (c <= 32 ? 32 : round_up(c, 64));
+}
 
 // ------------------------------------------------------------------------------ conv geometry
 struct ConvGeom {
@@ -226,30 +232,34 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int make_tmap_act(CUtensorMap* tm, const ActDesc& a, int box_w, int box_h) {
+static CUtensorMapSwizzle swizzle_for(int kc) {
+  return kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+static int make_tmap_act(CUtensorMap* tm, const ActDesc& a, int box_w, int box_h, int kc) {
   EncodeTiledFn fn = get_encode_fn();
   V2V_REQUIRE(fn, V2V_ERR_STATE, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[5] = {(cuuint64_t)a.C, (cuuint64_t)a.Wp, (cuuint64_t)a.Hp, (cuuint64_t)a.P, (cuuint64_t)a.N};
   cuuint64_t strides[4] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.Wp * a.C * 2, (cuuint64_t)a.Hp * a.Wp * a.C * 2,
                            (cuuint64_t)a.P * a.Hp * a.Wp * a.C * 2};
-  cuuint32_t box[5] = {64, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, a.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   V2V_REQUIRE(r == CUDA_SUCCESS, V2V_ERR_STATE, "cuTensorMapEncodeTiled(A) failed: %d (C=%d Wp=%d Hp=%d P=%d N=%d box %dx%d)",
               (int)r, a.C, a.Wp, a.Hp, a.P, a.N, box_w, box_h);
   return 0;
 }
 
-static int make_tmap_w(CUtensorMap* tm, bf16* w, int Ktotal, int Cout, int BN) {
+static int make_tmap_w(CUtensorMap* tm, bf16* w, int Ktotal, int Cout, int BN, int kc) {
   EncodeTiledFn fn = get_encode_fn();
   V2V_REQUIRE(fn, V2V_ERR_STATE, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)Ktotal, (cuuint64_t)Cout};
   cuuint64_t strides[1] = {(cuuint64_t)Ktotal * 2};
-  cuuint32_t box[2] = {64, (cuuint32_t)BN};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)BN};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  swizzle_for(kc), CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   V2V_REQUIRE(r == CUDA_SUCCESS, V2V_ERR_STATE, "cuTensorMapEncodeTiled(B) failed: %d (K=%d Cout=%d BN=%d)", (int)r, Ktotal,
               Cout, BN);
   return 0;
@@ -258,7 +268,7 @@ static int make_tmap_w(CUtensorMap* tm, bf16* w, int Ktotal, int Cout, int BN) {
 static ActDesc make_act(const Value& v, const Req& r) {
   ActDesc a{};
   a.base = nullptr;
-  a.N = v.N; a.H = v.H; a.W = v.W; a.Cvalid = v.C; a.C = round_up(v.C, 64);
+  a.N = v.N; a.H = v.H; a.W = v.W; a.Cvalid = v.C; a.C = pad_channels(v.C);
   a.pad_t = r.pads[0]; a.pad_l = r.pads[1]; a.pad_b = r.pads[2]; a.pad_r = r.pads[3];
   a.parity = r.parity;
   const int Hpad = v.H + a.pad_t + a.pad_b, Wpad = v.W + a.pad_l + a.pad_r;
@@ -325,14 +335,17 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   kp.grid_h = g.grid_h; kp.grid_w = g.grid_w;
   kp.Cout = op.conv.Cout;
   kp.BN = op.kind == G_HEAD ? 16 : std::min(128, round_up(op.conv.Cout, 32));
-  kp.Cp = round_up(op.conv.Cin, 64); kp.cblocks = kp.Cp / 64;
+  kp.Cp = pad_channels(op.conv.Cin);
+  kp.kc = std::min(kp.Cp, 64); kp.cblocks = kp.Cp / kp.kc;
+  kp.row_bytes = kp.kc * 2; kp.kmma = kp.kc / 16; kp.sbo_bytes = 8 * kp.row_bytes;
+  kp.layout_type = kp.kc == 64 ? 2 : (kp.kc == 32 ? 4 : 6);
   kp.R = g.R;
-  kp.a_slot_bytes = round_up((g.TW + g.R - 1) * g.TH * 128, 1024);
+  kp.a_slot_bytes = round_up((g.TW + g.R - 1) * g.TH * kp.row_bytes, 1024);
   // shared-memory budget: 227 KB - stats scratch (8 KB) - alignment slack - barriers
   const int budget = 212 * 1024;
   // a weight slot holds the R taps served by one activation patch; keep >= 2 slots + 3 patches in the budget
-  while (g.R > 1 && kp.BN > 32 && 2 * g.R * kp.BN * 128 + 3 * kp.a_slot_bytes > budget) kp.BN /= 2;
-  kp.b_slot_bytes = g.R * kp.BN * 128;
+  while (g.R > 1 && kp.BN > 32 && 2 * g.R * kp.BN * kp.row_bytes + 3 * kp.a_slot_bytes > budget) kp.BN /= 2;
+  kp.b_slot_bytes = round_up(g.R * kp.BN * kp.row_bytes, 1024);
   kp.n_tiles = (kp.Cout + kp.BN - 1) / kp.BN;
   kp.m_total = kp.N * kp.tiles_x * kp.tiles_y;
   kp.total_tiles = kp.m_total * kp.n_tiles * g.n_phases;
@@ -347,14 +360,15 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
       budget - nB * kp.b_slot_bytes >= 2 * kp.a_slot_bytes) {
     kp.b_resident = 1;
     kp.SB = nB;
-    kp.SA = std::max(2, std::min(6, (budget - nB * kp.b_slot_bytes) / kp.a_slot_bytes));
+    kp.SA = std::max(2, std::min(24, (budget - nB * kp.b_slot_bytes) / kp.a_slot_bytes));   // small patches: keep many in flight
   } else if (g.R == 1) {
     int s = budget / (kp.a_slot_bytes + kp.b_slot_bytes);
-    s = std::max(2, std::min(8, s));
+    s = std::max(2, std::min(12, s));
     kp.SA = kp.SB = s;
   } else {
-    kp.SA = 3;
-    kp.SB = std::max(2, std::min(6, (budget - kp.SA * kp.a_slot_bytes) / kp.b_slot_bytes));
+    int s = budget / (kp.a_slot_bytes + kp.b_slot_bytes);      // one weight slot (R taps) per activation patch
+    s = std::max(2, std::min(12, s));
+    kp.SA = kp.SB = s;
   }
   kp.grid = std::min(kp.total_tiles, device_sm_count());
   kp.num_phases = g.n_phases;
@@ -634,8 +648,8 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
           }
         }
         if (P->impl == V2V_IMPL_UMMA) {
-          rc = make_tmap_act(&op.tmA, ain, op.geom.TW + op.geom.R - 1, op.geom.TH); if (rc) return rc;
-          rc = make_tmap_w(&op.tmB, op.wpacked, op.Ktotal, op.conv.Cout, kp.BN); if (rc) return rc;
+          rc = make_tmap_act(&op.tmA, ain, op.geom.TW + op.geom.R - 1, op.geom.TH, kp.kc); if (rc) return rc;
+          rc = make_tmap_w(&op.tmB, op.wpacked, op.Ktotal, op.conv.Cout, kp.BN, kp.kc); if (rc) return rc;
         }
         rc = pack_one(op, stream); if (rc) return rc;
         XOp x; x.kind = X_CONV; x.gop = (int)i;

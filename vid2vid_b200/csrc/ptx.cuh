@@ -152,21 +152,22 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
 }
 
 // ------------------------------------------------------------------ descriptors
-// Shared-memory matrix descriptor, K-major, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart
-// (canonical layout written by a TMA box whose inner extent is 64 bf16 with CU_TENSOR_MAP_SWIZZLE_128B).
-//   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused for SW128 K-major: 1)
+// Shared-memory matrix descriptor, K-major, swizzled: rows of 32 / 64 / 128 bytes (one K block of 16 / 32 / 64 bf16),
+// 8-row groups `sbo_bytes` apart -- the canonical layout a TMA box with that inner extent and the matching
+// CU_TENSOR_MAP_SWIZZLE_{32,64,128}B mode writes.
+//   bits [0,14)  start address >> 4        bits [16,30) leading byte offset >> 4 (unused for swizzled K-major: 1)
 //   bits [32,46) stride byte offset >> 4   bits [46,48) version = 1 (Blackwell)
 //   bits [49,52) base offset: 0.  Measured on B200: the swizzle is applied to absolute shared-memory address bits,
-//                so an operand whose start is advanced by whole 128-byte rows inside a 1024-byte-aligned patch
+//                so an operand whose start is advanced by whole rows inside a 1024-byte-aligned patch
 //                (tap reuse) still needs 0; the `(addr >> 7) & 7` variant gives wrong results.
-//   bits [61,64) layout type: 2 = SWIZZLE_128B
-__device__ __forceinline__ uint64_t make_sw128_kmajor_desc(uint32_t smem_addr) {
+//   bits [61,64) layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, int sbo_bytes, int layout_type) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>(1) << 16;
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
 }
 // Instruction descriptor for kind::f16: A,B = bf16 (format 1), D = fp32 (format 1), both K-major.

@@ -15,11 +15,12 @@ typedef __nv_bfloat16 bf16;
 //   padded coords  yp = y + pad_t, xp = x + pad_l   (y, x may lie in the halo)
 //   parity == 0 :  [n][0][yp][xp][c]          plane dims Hp x Wp
 //   parity == 1 :  [n][(yp&1)*2 + (xp&1)][yp>>1][xp>>1][c]   plane dims Hp x Wp (= ceil(padded/2))
-// C is the padded channel count (multiple of 64; channels >= Cvalid are zero).
+// C is the padded channel count (16, 32, or a multiple of 64; channels >= Cvalid are zero): one K block of the
+// implicit GEMM is min(C, 64) channels = one shared-memory row of 32 / 64 / 128 bytes (TMA swizzle 32B / 64B / 128B).
 struct ActDesc {
   bf16* base;
   int N, H, W;          // logical (unpadded) extent
-  int C;                // padded channels (multiple of 64)
+  int C;                // padded channels (16 / 32 / multiple of 64)
   int Cvalid;
   int pad_t, pad_l, pad_b, pad_r;
   int parity;           // 0 / 1
@@ -67,7 +68,9 @@ struct ConvKernelParams {
   int N, tiles_x, tiles_y, TH, TW;   // M tile = TH x TW output-grid pixels (TH*TW == 128)
   int grid_h, grid_w;                // extent of the output grid this launch iterates over
   int Cout, BN;                      // valid output channels, N tile (16/32/64/128)
-  int Cp, cblocks;                   // padded input channels, Cp/64
+  int Cp, cblocks;                   // padded input channels, K blocks per tap (Cp / kc)
+  int kc, row_bytes, kmma;           // channels per K block (16/32/64), smem row bytes (2*kc), MMAs per row (kc/16)
+  int layout_type, sbo_bytes;        // UMMA smem-descriptor swizzle code (6/4/2) and 8-row group stride (8*row_bytes)
   int R;                             // taps served per A patch (1 = none)
   int a_slot_bytes, b_slot_bytes, SA, SB;
   int b_resident;                    // 1: SB == B tiles of one (phase, n-tile): loaded once per key, kept in smem
