@@ -80,6 +80,10 @@ CASES = [
     ('mt_stem_R7', lambda: NW._stem(108, 32, BN), (1, 108, 80, 256)),
     ('mt_stem_R7_cout128', lambda: NW._stem(108, 128, BN), (1, 108, 80, 256)),
     ('mt_batch2_resblock', lambda: [NW.ResnetBlock(64, 'reflect', BN)], (2, 64, 48, 256)),
+    # streamed weights with M blocking (several accumulators per weight pass), incl. a unit that straddles two images
+    ('mg2_stream_c128', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(128, 128, 3), BN(128), nn.ReLU(True)], (1, 128, 160, 512)),
+    ('mg4_stem', lambda: NW._stem(108, 32, BN), (1, 108, 256, 640)),
+    ('mg2_stem_batch2_straddle', lambda: NW._stem(108, 16, BN), (2, 108, 107, 384)),
     # 16- and 32-channel K blocks (32-byte / 64-byte swizzled rows), with and without tap reuse
     ('kc16_stem_R7', lambda: NW._stem(6, 32, BN), (1, 6, 12, 136)),
     ('kc16_stem_R7_mt', lambda: NW._stem(6, 32, BN), (1, 6, 80, 256)),

@@ -30,6 +30,10 @@ static constexpr int kThreads = 192;
 static constexpr int kEpiThreads = 128;
 static constexpr int kRedFloats = 2 * 4 * 2 * 128;   // [parity][warp][sum|sumsq][col]
 
+// V2V_DBG bit2: CTA 0 records clock64() at role events of its first 24 work units and prints them at exit
+__device__ long long g_trace[3][24][8];
+#define TRACE(role, it, ev) do { if ((p.dbg & 4) && blockIdx.x == 0 && (it) < 24) g_trace[role][it][ev] = clock64(); } while (0)
+
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
   switch (act) {
     case ACT_RELU: return fmaxf(v, 0.f);
@@ -56,26 +60,33 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
   return v[0];
 }
 
-struct Tile {
-  int phase, n0, n_img, y0, x0, row;   // row = stats partial row (phase * m_total + m)
-  int key;                             // (phase, N tile): which weights
+// A work unit = MG consecutive M tiles of one (phase, N tile): their accumulators sit side by side in TMEM and every
+// weight tile fetched from L2 is used MG times (the small-N 7x7 stems are otherwise weight-traffic bound).
+struct Unit {
+  int key, phase, n0, m_first, count;
 };
+struct TileXY { int n_img, y0, x0; };
 
-__device__ __forceinline__ Tile decode_tile(const ConvKernelParams& p, int t) {
-  Tile tl;
-  const int m = t % p.m_total;
-  tl.key = t / p.m_total;
-  const int nt = tl.key % p.n_tiles;
-  tl.phase = tl.key / p.n_tiles;
+__device__ __forceinline__ Unit decode_unit(const ConvKernelParams& p, int u) {
+  Unit un;
+  un.key = u / p.mg_total;
+  const int mg = u - un.key * p.mg_total;
+  const int nt = un.key % p.n_tiles;
+  un.phase = un.key / p.n_tiles;
+  un.n0 = nt * p.BN;
+  un.m_first = mg * p.MG;
+  un.count = min(p.MG, p.m_total - un.m_first);
+  return un;
+}
+__device__ __forceinline__ TileXY tile_xy(const ConvKernelParams& p, int m) {
+  TileXY t;
   const int per_img = p.tiles_x * p.tiles_y;
-  tl.n_img = m / per_img;
-  const int r = m - tl.n_img * per_img;
+  t.n_img = m / per_img;
+  const int r = m - t.n_img * per_img;
   const int ty = r / p.tiles_x;
-  tl.y0 = ty * p.TH;
-  tl.x0 = (r - ty * p.tiles_x) * p.TW;
-  tl.n0 = nt * p.BN;
-  tl.row = tl.phase * p.m_total + m;
-  return tl;
+  t.y0 = ty * p.TH;
+  t.x0 = (r - ty * p.tiles_x) * p.TW;
+  return t;
 }
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -83,28 +94,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ ConvKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = sA + (size_t)p.SA * p.a_slot_bytes;
-  float* red = reinterpret_cast<float*>(sB + (size_t)p.SB * p.b_slot_bytes);
+  // group slots: [SG][ CG activation patches | CG streamed weight slots ], then the resident weight set (if any)
+  const int slot_b = p.b_resident ? 0 : p.b_slot_bytes;
+  const int group_bytes = p.CG * (p.a_slot_bytes + slot_b);
+  uint8_t* sG = smem;
+  uint8_t* sBres = sG + (size_t)p.SG * group_bytes;
+  float* red = reinterpret_cast<float*>(sBres + (p.b_resident ? (size_t)p.SB * p.b_slot_bytes : 0));
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + kRedFloats);
-  uint64_t* a_full = bars;
-  uint64_t* a_empty = a_full + p.SA;
-  uint64_t* b_full = a_empty + p.SA;
-  uint64_t* b_empty = b_full + p.SB;
-  uint64_t* tmem_full = b_empty + p.SB;     // [2]
+  uint64_t* g_full = bars;
+  uint64_t* g_empty = g_full + p.SG;
+  uint64_t* bres_full = g_empty + p.SG;
+  uint64_t* bres_empty = bres_full + 1;
+  uint64_t* tmem_full = bres_empty + 1;     // [2]
   uint64_t* tmem_empty = tmem_full + 2;     // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t acc_cols = p.BN < 32 ? 32 : p.BN;     // columns per accumulator stage
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2 * acc_cols) tmem_cols <<= 1;
+  while (tmem_cols < 2 * p.MG * acc_cols) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int i = 0; i < p.SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < p.SB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < p.SG; ++i) { mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 1); }
+    mbar_init(bres_full, 1); mbar_init(bres_empty, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     fence_barrier_init();
   }
@@ -124,87 +138,93 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0) {
     if (elect_one_sync()) {
       // ---------------------------------------------------------- TMA producer (single elected lane)
-      int sa = 0, sb = 0;
-      uint32_t pa = 0, pb = 0, gen = 0;
+      // The K loop of a tile is a sequence of steps (tap group g, K block cb); CG consecutive steps share one
+      // full/empty barrier pair ("group slot"), so a barrier round trip and a tcgen05.commit are paid once per CG
+      // steps (measured: ~500 cycles of issue-side overhead per commit group, during which the tensor pipe idles).
+      int gs = 0;
+      uint32_t gpar = 0, gen = 0;
       int prev_key = -1;
-      for (int t = t_first; t < p.total_tiles; t += t_step) {
-        const Tile tl = decode_tile(p, t);
-        const ConvPhase ph = p.phases[tl.phase];
-        const bool load_b = !p.b_resident || tl.key != prev_key;
-        if (p.b_resident && tl.key != prev_key && prev_key >= 0) gen ^= 1;
-        prev_key = tl.key;
-        for (int g = ph.group_begin; g < ph.group_end; ++g) {
-          const ConvGroup grp = p.groups[g];
-          for (int cb = 0; cb < p.cblocks; ++cb) {
-            mbar_wait(&a_empty[sa], pa ^ 1);
-            mbar_expect_tx(&a_full[sa], a_tx);
-            tma_load_5d(sA + (size_t)sa * p.a_slot_bytes, &tmA, &a_full[sa], cb * p.kc, tl.x0 + grp.dx, tl.y0 + grp.dy,
-                        grp.plane, tl.n_img);
-            if (++sa == p.SA) { sa = 0; pa ^= 1; }
-            if (!load_b) continue;
-            int slot;
-            uint32_t par;
-            if (p.b_resident) { slot = (g - ph.group_begin) * p.cblocks + cb; par = gen ^ 1; }
-            else { slot = sb; par = pb ^ 1; }
-            mbar_wait(&b_empty[slot], par);
-            mbar_expect_tx(&b_full[slot], b_tx * p.R);             // one barrier for the R taps of this patch
-            for (int r = 0; r < p.R; ++r)
-              tma_load_2d(sB + (size_t)slot * p.b_slot_bytes + (size_t)r * b_tx, &tmB, &b_full[slot],
-                          (grp.tap0 + r) * p.Cp + cb * p.kc, tl.n0);
-            if (!p.b_resident && ++sb == p.SB) { sb = 0; pb ^= 1; }
-          }
+      for (int u = t_first; u < p.total_units; u += t_step) {
+        const Unit un = decode_unit(p, u);
+        const int pit = (u - t_first) / t_step;
+        TRACE(0, pit, 0);
+        const ConvPhase ph = p.phases[un.phase];
+        const TileXY tx = tile_xy(p, un.m_first);
+        const int nsteps = (ph.group_end - ph.group_begin) * p.cblocks;
+        if (p.b_resident && un.key != prev_key) {
+          if (prev_key >= 0) gen ^= 1;
+          mbar_wait(bres_empty, gen ^ 1);                      // all MMAs that read the previous weight set retired
+          mbar_expect_tx(bres_full, (uint32_t)nsteps * p.R * b_tx);
+          int sidx = 0;
+          for (int g = ph.group_begin; g < ph.group_end; ++g)
+            for (int cb = 0; cb < p.cblocks; ++cb, ++sidx)
+              for (int r = 0; r < p.R; ++r)
+                tma_load_2d(sBres + (size_t)sidx * p.b_slot_bytes + (size_t)r * b_tx, &tmB, bres_full,
+                            (p.groups[g].tap0 + r) * p.Cp + cb * p.kc, un.n0);
         }
-        if (p.b_resident && load_b) {
-          // phases with fewer taps leave slots unused: cycle their barriers so every slot advances once per key
-          for (int slot = (ph.group_end - ph.group_begin) * p.cblocks; slot < p.SB; ++slot) {
-            mbar_wait(&b_empty[slot], gen ^ 1);
-            mbar_arrive(&b_full[slot]);
+        prev_key = un.key;
+        int g = ph.group_begin, cb = 0;
+        for (int s0 = 0; s0 < nsteps; s0 += p.CG) {
+          const int n = min(p.CG, nsteps - s0);
+          uint8_t* base = sG + (size_t)gs * group_bytes;
+          mbar_wait(&g_empty[gs], gpar ^ 1);
+          mbar_expect_tx(&g_full[gs], (uint32_t)n * (a_tx + (p.b_resident ? 0 : p.R * b_tx)));
+          for (int i = 0; i < n; ++i) {
+            const ConvGroup grp = p.groups[g];
+            tma_load_5d(base + (size_t)i * p.a_slot_bytes, &tmA, &g_full[gs], cb * p.kc, tx.x0 + grp.dx, tx.y0 + grp.dy,
+                        grp.plane, tx.n_img);
+            if (!p.b_resident) {
+              uint8_t* bb = base + (size_t)p.CG * p.a_slot_bytes + (size_t)i * p.b_slot_bytes;
+              for (int r = 0; r < p.R; ++r)
+                tma_load_2d(bb + (size_t)r * b_tx, &tmB, &g_full[gs], (grp.tap0 + r) * p.Cp + cb * p.kc, un.n0);
+            }
+            if (++cb == p.cblocks) { cb = 0; ++g; }
           }
+          if (++gs == p.SG) { gs = 0; gpar ^= 1; }
         }
+        TRACE(0, pit, 2);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues)
     const uint32_t idesc = make_idesc_bf16(128, p.BN);
-    int sa = 0, sb = 0, it = 0;
-    uint32_t pa = 0, pb = 0, gen = 0;
+    int gs = 0, it = 0;
+    uint32_t gpar = 0, gen = 0;
     int prev_key = -1;
-    for (int t = t_first; t < p.total_tiles; t += t_step, ++it) {
-      const Tile tl = decode_tile(p, t);
-      const ConvPhase ph = p.phases[tl.phase];
-      const bool first_of_key = tl.key != prev_key;
+    const uint64_t a_step = (uint64_t)(p.row_bytes >> 4), b_step = (uint64_t)(b_tx >> 4);
+    for (int u = t_first; u < p.total_units; u += t_step, ++it) {
+      const Unit un = decode_unit(p, u);
+      const ConvPhase ph = p.phases[un.phase];
+      const bool first_of_key = un.key != prev_key;
       if (p.b_resident && first_of_key && prev_key >= 0) gen ^= 1;
-      prev_key = tl.key;
-      const int t_next = t + t_step;
-      const bool last_of_key = (t_next >= p.total_tiles) || (t_next / p.m_total != tl.key);
+      prev_key = un.key;
+      const int u_next = u + t_step;
+      const bool last_of_key = (u_next >= p.total_units) || (u_next / p.mg_total != un.key);
+      const int nsteps = (ph.group_end - ph.group_begin) * p.cblocks;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      TRACE(1, it, 0);
       mbar_wait(&tmem_empty[as], aphase ^ 1);        // the epilogue has drained this accumulator stage
+      if (p.b_resident && first_of_key) mbar_wait(bres_full, gen);
       tcgen05_fence_after();
+      TRACE(1, it, 1);
       const uint32_t tmem_d = tmem_base + as * acc_cols;
       uint32_t acc = 0;
-      for (int g = ph.group_begin; g < ph.group_end; ++g) {
-        for (int cb = 0; cb < p.cblocks; ++cb) {
-          mbar_wait(&a_full[sa], pa);
-          tcgen05_fence_after();
-          const uint32_t a_base = smem_u32(sA + (size_t)sa * p.a_slot_bytes);
-          int slot;
-          if (p.b_resident) {
-            slot = (g - ph.group_begin) * p.cblocks + cb;
-            if (first_of_key) mbar_wait(&b_full[slot], gen);
-          } else {
-            slot = sb;
-            mbar_wait(&b_full[slot], pb);
-          }
-          tcgen05_fence_after();
-          const uint32_t b_base = smem_u32(sB + (size_t)slot * p.b_slot_bytes);
-          if (elect_one_sync()) {
-            // descriptors differ only in the 14-bit (address >> 4) field: build once per slot, then add
-            const uint64_t adesc0 = make_kmajor_desc(a_base, p.sbo_bytes, p.layout_type);
-            const uint64_t bdesc0 = make_kmajor_desc(b_base, p.sbo_bytes, p.layout_type);
-            const uint64_t a_step = (uint64_t)(p.row_bytes >> 4), b_step = (uint64_t)(b_tx >> 4);
-            uint64_t ad = adesc0, bd = bdesc0;
-            uint32_t first = acc;
+      for (int s0 = 0; s0 < nsteps; s0 += p.CG) {
+        const int n = min(p.CG, nsteps - s0);
+        mbar_wait(&g_full[gs], gpar);
+        tcgen05_fence_after();
+        if (s0 == 0) TRACE(1, it, 2);
+        if (elect_one_sync()) {
+          const uint32_t base = smem_u32(sG + (size_t)gs * group_bytes);
+          uint32_t first = acc;
+          for (int i = 0; i < n; ++i) {
+            const uint32_t a_base = base + i * p.a_slot_bytes;
+            const uint32_t b_base = p.b_resident ? smem_u32(sBres) + (s0 + i) * p.b_slot_bytes
+                                                 : base + p.CG * p.a_slot_bytes + i * p.b_slot_bytes;
+            // descriptors differ only in the 14-bit (address >> 4) field: build once per step, then add
+            uint64_t ad = make_kmajor_desc(a_base, p.sbo_bytes, p.layout_type);
+            uint64_t bd = make_kmajor_desc(b_base, p.sbo_bytes, p.layout_type);
             // K = 16 bf16 = 32 bytes per MMA; kc/16 MMAs per smem row (fixed trip counts keep the issue loop tight)
             if (p.kmma == 4) {
               for (int r = 0; r < p.R; ++r, ad += a_step, bd += b_step) {
@@ -226,25 +246,18 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 first = 1u;
               }
             }
-            if (!p.b_resident || last_of_key) umma_commit(&b_empty[slot]);     // weight slot free when these retire
           }
-          __syncwarp();
-          acc = 1;
-          if (!p.b_resident && ++sb == p.SB) { sb = 0; pb ^= 1; }
-          if (elect_one_sync()) umma_commit(&a_empty[sa]);                     // activation patch free
-          __syncwarp();
-          if (++sa == p.SA) { sa = 0; pa ^= 1; }
+          umma_commit(&g_empty[gs]);                   // the whole group slot is free when these MMAs retire
+          if (s0 + n >= nsteps) {
+            if (p.b_resident && last_of_key) umma_commit(bres_empty);
+            umma_commit(&tmem_full[as]);               // accumulator complete
+          }
         }
+        __syncwarp();
+        acc = 1;
+        if (++gs == p.SG) { gs = 0; gpar ^= 1; }
       }
-      if (p.b_resident) {
-        for (int slot = (ph.group_end - ph.group_begin) * p.cblocks; slot < p.SB; ++slot) {
-          if (first_of_key) mbar_wait(&b_full[slot], gen);
-          if (last_of_key && elect_one_sync()) umma_commit(&b_empty[slot]);
-          __syncwarp();
-        }
-      }
-      if (elect_one_sync()) umma_commit(&tmem_full[as]);                       // accumulator complete
-      __syncwarp();
+      TRACE(1, it, 3);
     }
   } else {
     // ------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
@@ -255,29 +268,36 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // row per (phase, image, CTA) instead of one per tile keeps the finalize pass tiny
     float s_acc = 0.f, q_acc = 0.f;
     int acc_key = -1, acc_img = -1, acc_n0 = 0, acc_phase = 0;
-    for (int t = t_first; t < p.total_tiles; t += t_step, ++it) {
-      const Tile tl = decode_tile(p, t);
-      const ConvPhase ph = p.phases[tl.phase];
+    int red_it = 0;
+    for (int u = t_first; u < p.total_units; u += t_step, ++it) {
+      const Unit un = decode_unit(p, u);
+      const ConvPhase ph = p.phases[un.phase];
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
+      if (q == 0) TRACE(2, it, 0);
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
-
+      if (q == 0) TRACE(2, it, 1);
+     for (int jt = 0; jt < un.count; ++jt, ++red_it) {
+      const TileXY txy = tile_xy(p, un.m_first + jt);
+      const bool last_tile = (jt == un.count - 1);
       const int row = q * 32 + lane;
       const int ry = row / p.TW, rx = row - ry * p.TW;
-      const int gy = tl.y0 + ry, gx = tl.x0 + rx;
+      const int gy = txy.y0 + ry, gx = txy.x0 + rx;
       const bool valid = (gy < p.grid_h) && (gx < p.grid_w);
       const int oy = gy * p.oy_mul + ph.oy_add, ox = gx * p.ox_mul + ph.ox_add;
-      const uint32_t taddr = tmem_base + as * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
-      const int n0 = tl.n0, n_img = tl.n_img;
+      const uint32_t taddr = tmem_base + (as * p.MG + jt) * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
+      const int n0 = un.n0, n_img = txy.n_img;
 
       if (p.epi == EPI_HEAD_F32) {
         uint32_t r[16];
         tmem_ld_32x32b_x16(taddr, r);
         tmem_ld_wait();
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        if (last_tile) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[as]);
+        }
         if (valid) {
           const size_t pix = (size_t)oy * p.out_W + ox;
 #pragma unroll
@@ -291,8 +311,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       } else {
-        float* redp = red + (it & 1) * (4 * 2 * 128);
-        const bool do_stats = (p.epi == EPI_RAW_STATS) && (p.stats != nullptr);
+        float* redp = red + (red_it & 1) * (4 * 2 * 128);
+        const bool do_stats = (p.epi == EPI_RAW_STATS) && (p.stats != nullptr) && !(p.dbg & 1);
         bf16* dst = nullptr;
         if (valid) {
           if (p.epi == EPI_RAW_STATS)
@@ -305,7 +325,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c * 32, r);
           tmem_ld_wait();
-          if (c == nchunks - 1) {                 // accumulator fully read: hand the TMEM stage back to the MMA warp
+          if (last_tile && c == nchunks - 1) {    // accumulators fully read: hand the TMEM stage back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty[as]);
@@ -321,7 +341,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[j] = (col0 + j < p.Cout) ? apply_act(v[j] + b, p.act, p.lrelu_slope) : 0.f;
             }
           }
-          if (valid) {
+          if (valid && !(p.dbg & 2)) {
 #pragma unroll
             for (int qv = 0; qv < 4; ++qv) {
               if (col0 + qv * 8 < p.out_C) {
@@ -347,14 +367,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (do_stats) {
           named_bar_sync(1, kEpiThreads);        // the four epilogue warps only
           if (etid < p.BN) {
-            if (tl.key != acc_key || n_img != acc_img) {
+            if (un.key != acc_key || n_img != acc_img) {
               if (acc_key >= 0 && acc_n0 + etid < p.stats_C) {
                 const size_t rowi = ((size_t)acc_phase * p.N + acc_img) * gridDim.x + blockIdx.x;
                 p.stats[(rowi * 2 + 0) * p.stats_C + acc_n0 + etid] = s_acc;
                 p.stats[(rowi * 2 + 1) * p.stats_C + acc_n0 + etid] = q_acc;
               }
               s_acc = q_acc = 0.f;
-              acc_key = tl.key; acc_img = n_img; acc_n0 = n0; acc_phase = tl.phase;
+              acc_key = un.key; acc_img = n_img; acc_n0 = n0; acc_phase = un.phase;
             }
 #pragma unroll
             for (int w = 0; w < 4; ++w) {
@@ -364,6 +384,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+     }   // tiles of the unit
+      if (q == 0) TRACE(2, it, 2);
     }
     if (acc_key >= 0 && etid < p.BN && acc_n0 + etid < p.stats_C) {
       const size_t rowi = ((size_t)acc_phase * p.N + acc_img) * gridDim.x + blockIdx.x;
@@ -375,6 +397,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  if ((p.dbg & 4) && blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long t0 = g_trace[0][0][0];
+    for (int it = 0; it < 24; ++it)
+      printf("trace it=%2d prod: start %6lld issued %6lld | mma: start %6lld tmem_empty %6lld first_a %6lld [p1 top %6lld waited %6lld fenced %6lld descs %6lld] done %6lld | epi: start %6lld full %6lld done %6lld\n", it,
+             g_trace[0][it][0] - t0, g_trace[0][it][2] - t0, g_trace[1][it][0] - t0, g_trace[1][it][1] - t0, g_trace[1][it][2] - t0,
+             g_trace[1][it][4] - t0, g_trace[1][it][5] - t0, g_trace[1][it][6] - t0, g_trace[1][it][7] - t0,
+             g_trace[1][it][3] - t0, g_trace[2][it][0] - t0, g_trace[2][it][1] - t0, g_trace[2][it][2] - t0);
+  }
 }
 
 int device_sm_count() {
@@ -390,8 +420,9 @@ int device_sm_count() {
 
 cudaError_t launch_conv_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p,
                              cudaStream_t stream) {
-  const size_t smem = (size_t)p.SA * p.a_slot_bytes + (size_t)p.SB * p.b_slot_bytes + 1024 /*align*/ +
-                      kRedFloats * sizeof(float) + (2 * (p.SA + p.SB) + 4 + 2) * sizeof(uint64_t);
+  const size_t smem = (size_t)p.SG * p.CG * (p.a_slot_bytes + (p.b_resident ? 0 : p.b_slot_bytes)) +
+                      (p.b_resident ? (size_t)p.SB * p.b_slot_bytes : 0) + 1024 /*align*/ + kRedFloats * sizeof(float) +
+                      (2 * p.SG + 2 + 4 + 2) * sizeof(uint64_t);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -16,59 +16,89 @@ __device__ __forceinline__ int reflect_i(int i, int n) {
   return i;
 }
 
-// block (32, 8): tile of 32 padded-x positions x 64 channels at one (n, yp).
-__global__ void import_nchw_kernel(ImportParams p) {
-  __shared__ float tile[64][33];
+// block (32, 8): tile of 128 padded-x positions x CT channels at one (n, yp); CT = 64, or 16 for narrow tensors.
+// Loads are coalesced along x (4 independent 128-byte rows per channel per warp), stores along channels.
+template <int CT>
+__global__ void __launch_bounds__(256) import_nchw_kernel(ImportParams p) {
+  __shared__ float tile[CT][129];
   const float* src = reinterpret_cast<const float*>(p.io[p.slot]);
   const ActDesc& o = p.out;
   const int Wpad = o.W + o.pad_l + o.pad_r, Hpad = o.H + o.pad_t + o.pad_b;
-  const int xt = blockIdx.x * 32;
+  const int xt = blockIdx.x * 128;
   const int yp = blockIdx.y % Hpad, n = blockIdx.y / Hpad;
-  const int cblk = blockIdx.z * 64;
+  const int cblk = blockIdx.z * CT;
   int y = yp - o.pad_t;
   const bool yhalo = (y < 0 || y >= o.H);
   if (p.pad_mode == PAD_REFLECT) y = reflect_i(y, o.H);
-  const int xp = xt + threadIdx.x;
-  int x = xp - o.pad_l;
-  const bool xhalo = (x < 0 || x >= o.W);
-  if (p.pad_mode == PAD_REFLECT) x = reflect_i(x, o.W);
-  const bool zero_px = (xp >= Wpad) || ((yhalo || xhalo) && p.pad_mode != PAD_REFLECT);
-  for (int cc = threadIdx.y; cc < 64; cc += 8) {
+  int xs[4];
+  bool zero_px[4];
+#pragma unroll
+  for (int sx = 0; sx < 4; ++sx) {
+    const int xp = xt + sx * 32 + threadIdx.x;
+    int x = xp - o.pad_l;
+    const bool xhalo = (x < 0 || x >= o.W);
+    if (p.pad_mode == PAD_REFLECT) x = reflect_i(x, o.W);
+    xs[sx] = x;
+    zero_px[sx] = (xp >= Wpad) || ((yhalo || xhalo) && p.pad_mode != PAD_REFLECT);
+  }
+  for (int cc = threadIdx.y; cc < CT; cc += 8) {
     const int c = cblk + cc;
-    float v = 0.f;
-    if (!zero_px && c < o.Cvalid)
-      v = src[(((size_t)n * p.C_src + p.c_off + c) * o.H + y) * o.W + x];
-    tile[cc][threadIdx.x] = v;
+    const bool cv = c < o.Cvalid;
+    const float* row = src + (((size_t)n * p.C_src + p.c_off + (cv ? c : 0)) * o.H + y) * o.W;
+    float v[4];
+#pragma unroll
+    for (int sx = 0; sx < 4; ++sx) v[sx] = (cv && !zero_px[sx]) ? __ldg(row + xs[sx]) : 0.f;
+#pragma unroll
+    for (int sx = 0; sx < 4; ++sx) tile[cc][sx * 32 + threadIdx.x] = v[sx];
   }
   __syncthreads();
-  // write: thread (tx, ty) -> channel pair 2*tx, pixels ty, ty+8, ...
-  for (int px = threadIdx.y; px < 32; px += 8) {
-    const int xo = xt + px;
-    if (xo >= Wpad) continue;
-    if (cblk + 2 * (int)threadIdx.x >= o.C) continue;      // C may be 16 or 32
-    const uint32_t pk = pack_bf16x2(tile[2 * threadIdx.x][px], tile[2 * threadIdx.x + 1][px]);
-    *reinterpret_cast<uint32_t*>(o.base + o.offset(n, yp - o.pad_t, xo - o.pad_l) + cblk + 2 * threadIdx.x) = pk;
+  // write: lane -> channel pair (CT = 64) or (pixel parity, channel pair) (CT = 16)
+  if (CT == 64) {
+    for (int px = threadIdx.y; px < 128; px += 8) {
+      const int xo = xt + px;
+      if (xo >= Wpad) break;
+      if (cblk + 2 * (int)threadIdx.x >= o.C) continue;
+      const uint32_t pk = pack_bf16x2(tile[2 * threadIdx.x][px], tile[2 * threadIdx.x + 1][px]);
+      *reinterpret_cast<uint32_t*>(o.base + o.offset(n, yp - o.pad_t, xo - o.pad_l) + cblk + 2 * threadIdx.x) = pk;
+    }
+  } else {
+    const int cp = threadIdx.x & 7, sub = threadIdx.x >> 3;         // 8 channel pairs x 4 pixels per warp row
+    for (int px = threadIdx.y * 4 + sub; px < 128; px += 32) {
+      const int xo = xt + px;
+      if (xo >= Wpad || cblk + 2 * cp >= o.C) continue;
+      const uint32_t pk = pack_bf16x2(tile[2 * cp][px], tile[2 * cp + 1][px]);
+      *reinterpret_cast<uint32_t*>(o.base + o.offset(n, yp - o.pad_t, xo - o.pad_l) + cblk + 2 * cp) = pk;
+    }
   }
 }
 
-// block (32, 8): tile of 32 x positions x 32 channels at one (n, y).
-__global__ void export_nchw_kernel(ExportParams p) {
-  __shared__ float tile[32][33];
+// block (32, 8): tile of 128 x positions x 32 channels at one (n, y).
+__global__ void __launch_bounds__(256) export_nchw_kernel(ExportParams p) {
+  __shared__ float tile[32][129];
   float* dst = reinterpret_cast<float*>(p.io[p.slot]);
   const ActDesc& a = p.in;
-  const int xt = blockIdx.x * 32;
+  const int xt = blockIdx.x * 128;
   const int y = blockIdx.y % a.H, n = blockIdx.y / a.H;
   const int cblk = blockIdx.z * 32;
-  for (int px = threadIdx.y; px < 32; px += 8) {
-    const int x = xt + px, c = cblk + threadIdx.x;
-    float v = 0.f;
-    if (x < a.W && c < a.Cvalid) v = __bfloat162float(a.base[a.offset(n, y, x) + c]);
-    tile[threadIdx.x][px] = v;
+  // read: lane -> channel pair (16 pairs) x 2 pixels
+  const int cp = threadIdx.x & 15, sub = threadIdx.x >> 4;
+  for (int px = threadIdx.y * 2 + sub; px < 128; px += 16) {
+    const int x = xt + px, c = cblk + 2 * cp;
+    float2 v = make_float2(0.f, 0.f);
+    if (x < a.W && c < a.C) v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a.base + a.offset(n, y, x) + c));
+    tile[2 * cp][px] = v.x;
+    tile[2 * cp + 1][px] = v.y;
   }
   __syncthreads();
   for (int cc = threadIdx.y; cc < 32; cc += 8) {
-    const int c = cblk + cc, x = xt + threadIdx.x;
-    if (c < a.Cvalid && x < a.W) dst[(((size_t)n * a.Cvalid + c) * a.H + y) * a.W + x] = tile[cc][threadIdx.x];
+    const int c = cblk + cc;
+    if (c >= a.Cvalid) continue;
+    float* row = dst + (((size_t)n * a.Cvalid + c) * a.H + y) * a.W;
+#pragma unroll
+    for (int sx = 0; sx < 4; ++sx) {
+      const int x = xt + sx * 32 + threadIdx.x;
+      if (x < a.W) row[x] = tile[cc][sx * 32 + threadIdx.x];
+    }
   }
 }
 
@@ -98,14 +128,20 @@ __global__ void pack_weights_kernel(PackParams p) {
 cudaError_t launch_import_nchw(const ImportParams& p, cudaStream_t stream) {
   const ActDesc& o = p.out;
   const int Wpad = o.W + o.pad_l + o.pad_r, Hpad = o.H + o.pad_t + o.pad_b;
-  dim3 grid((Wpad + 31) / 32, Hpad * o.N, (o.C + 63) / 64), block(32, 8);
-  import_nchw_kernel<<<grid, block, 0, stream>>>(p);
+  dim3 block(32, 8);
+  if (o.C <= 16) {
+    dim3 grid((Wpad + 127) / 128, Hpad * o.N, 1);
+    import_nchw_kernel<16><<<grid, block, 0, stream>>>(p);
+  } else {
+    dim3 grid((Wpad + 127) / 128, Hpad * o.N, (o.C + 63) / 64);
+    import_nchw_kernel<64><<<grid, block, 0, stream>>>(p);
+  }
   return cudaGetLastError();
 }
 
 cudaError_t launch_export_nchw(const ExportParams& p, cudaStream_t stream) {
   const ActDesc& a = p.in;
-  dim3 grid((a.W + 31) / 32, a.H * a.N, (a.Cvalid + 31) / 32), block(32, 8);
+  dim3 grid((a.W + 127) / 128, a.H * a.N, (a.Cvalid + 31) / 32), block(32, 8);
   export_nchw_kernel<<<grid, block, 0, stream>>>(p);
   return cudaGetLastError();
 }

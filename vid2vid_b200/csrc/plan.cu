@@ -354,23 +354,38 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   const int nB = max_phase_groups * kp.cblocks;                 // weight slots of one (phase, N tile)
   const char* er = getenv("V2V_B_RESIDENT");
   const bool allow_res = !(er && er[0] == '0');
+  const int sms = device_sm_count();
   // resident weights pay off when a CTA walks several M tiles with the same weights
-  const bool many_m = kp.m_total > 148;
-  if (allow_res && many_m && (long long)nB * kp.b_slot_bytes <= 150 * 1024 &&
-      budget - nB * kp.b_slot_bytes >= 2 * kp.a_slot_bytes) {
-    kp.b_resident = 1;
-    kp.SB = nB;
-    kp.SA = std::max(2, std::min(24, (budget - nB * kp.b_slot_bytes) / kp.a_slot_bytes));   // small patches: keep many in flight
-  } else if (g.R == 1) {
-    int s = budget / (kp.a_slot_bytes + kp.b_slot_bytes);
-    s = std::max(2, std::min(12, s));
-    kp.SA = kp.SB = s;
-  } else {
-    int s = budget / (kp.a_slot_bytes + kp.b_slot_bytes);      // one weight slot (R taps) per activation patch
-    s = std::max(2, std::min(12, s));
-    kp.SA = kp.SB = s;
+  const bool many_m = kp.m_total > sms;
+  kp.MG = 1;
+  kp.b_resident = (allow_res && many_m && (long long)nB * kp.b_slot_bytes <= 150 * 1024 &&
+                   budget - nB * kp.b_slot_bytes >= 2 * kp.a_slot_bytes) ? 1 : 0;
+  kp.SB = kp.b_resident ? nB : 0;
+  // Commit groups.  Measured on B200: every tcgen05.commit / barrier round trip costs the issuing warp ~500 cycles
+  // during which the tensor pipe idles (its queue is shallow), so CG consecutive K-loop steps share one barrier pair;
+  // a step issues R * kmma MMAs of max(40, BN/2) cycles each (smem operand fetch floors small-N MMAs at ~40 cycles).
+  {
+    const int slot = kp.a_slot_bytes + (kp.b_resident ? 0 : kp.b_slot_bytes);
+    const int avail = budget - (kp.b_resident ? nB * kp.b_slot_bytes : 0);
+    const int nslots = std::max(2, avail / slot);
+    const int steps = max_phase_groups * kp.cblocks;
+    const int est = g.R * kp.kmma * std::max(40, kp.BN / 2);
+    int cg;
+    if (steps * est <= 6000 && 2 * steps <= nslots) cg = steps;           // one group per tile, double buffered
+    else {
+      cg = std::max(1, std::min({(1500 + est - 1) / est, steps, nslots / 2}));
+      if (nslots / cg < 3 && cg > 1) cg = std::max(1, nslots / 3);
+    }
+    const char* ec = getenv("V2V_CG");
+    if (ec) cg = std::max(1, std::min(atoi(ec), nslots / 2));
+    kp.CG = cg;
+    kp.SG = std::max(2, std::min(8, nslots / cg));
+    kp.SA = kp.SG * kp.CG;     // (informational)
   }
-  kp.grid = std::min(kp.total_tiles, device_sm_count());
+  { const char* dg = getenv("V2V_DBG"); kp.dbg = dg ? atoi(dg) : 0; }
+  kp.mg_total = (kp.m_total + kp.MG - 1) / kp.MG;
+  kp.total_units = kp.mg_total * kp.n_tiles * g.n_phases;
+  kp.grid = std::min(kp.total_units, device_sm_count());
   kp.num_phases = g.n_phases;
   memcpy(kp.phases, g.phases, sizeof(kp.phases));
   memcpy(kp.groups, g.groups, sizeof(kp.groups));

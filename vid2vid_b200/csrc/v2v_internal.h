@@ -75,6 +75,8 @@ struct ConvKernelParams {
   int a_slot_bytes, b_slot_bytes, SA, SB;
   int b_resident;                    // 1: SB == B tiles of one (phase, n-tile): loaded once per key, kept in smem
   int n_tiles, m_total, total_tiles; // N tiles, M tiles (N * tiles_x * tiles_y), all tiles incl. phases
+  int CG, SG;                        // K-loop steps per barrier / commit group, group slots in the ring
+  int MG, mg_total, total_units;     // M tiles accumulated side by side per weight pass (work unit), units per key, all units
   int num_phases;
   ConvPhase phases[V2V_MAX_PHASES];
   ConvGroup groups[V2V_MAX_TAPS];
@@ -88,6 +90,7 @@ struct ConvKernelParams {
   int stats_C;
   const float* bias;                 // may be null
   const float* bias2; int Cout1;     // fused heads: channels >= Cout1 take bias2[j - Cout1]
+  int dbg;                           // timing experiments only (V2V_DBG): bit0 skip stats, bit1 skip output stores
   int grid;                          // CTAs launched (persistent); also the stats partial rows per (phase, image)
   // EPI_HEAD_F32: per output channel destination = io[head_slot] + head_off (+ n * head_bstride),
   // activation and scale.  Caller pointers are read from the device IO table at run time.
