@@ -141,6 +141,11 @@ int v2v_g_conv(v2v_plan* plan, int value_in, const v2v_conv_desc* conv, int* raw
 /* value = act(norm(raw)) + add0 + add1   (add ids may be -1).  Conv bias is folded into running_mean only. */
 int v2v_g_norm_act(v2v_plan* plan, int raw_in, const v2v_norm_desc* norm, int act, float slope, int add0, int add1,
                    int* value_out);
+/* Same, on output channels [c_off, c_off + C) of the raw tensor (c_off % 8 == 0): lets convolutions that share their
+ * input and geometry run as one conv with stacked weights (v2v_conv_desc.weight2) and still feed separate norm layers
+ * (model_down_seg.1 / indv_down.1, models/networks.py:132,153).  The slice starting at Cout - Cout2 uses bias2. */
+int v2v_g_norm_act_slice(v2v_plan* plan, int raw_in, int c_off, int C, const v2v_norm_desc* norm, int act, float slope,
+                         int add0, int add1, int* value_out);
 /* value = act(conv(value_in) + bias)   (layers without normalisation) */
 int v2v_g_conv_act(v2v_plan* plan, int value_in, const v2v_conv_desc* conv, int act, float slope, int* value_out);
 /* Small-Cout head (Cout <= 16): per channel bias + activation + scale -> fp32 NCHW planes of caller tensors. */

@@ -111,3 +111,27 @@ def test_generator_simt_vs_umma_same_plan():
         print('%-12s umma-vs-simt max|d|=%.4f mean|d|=%.5f' % (key, d.max().item(), d.mean().item()))
         lim = 0.03 * b.pow(2).mean().sqrt().item() if key == 'flow' else (2e-2 if key == 'img_final' else 1e-2)
         assert d.mean().item() < lim, key
+
+
+def test_multiscale_discriminator_vs_reference_fixture():
+    """MultiscaleDiscriminator: all 5 layer outputs of all 3 towers, batch 2, BatchNorm train mode."""
+    c = C.CASES['D_small']
+    gold = load('D_small')
+    net = det_fill_(C.build_module(c), seed=c['seed']).cuda()
+    g = torch.Generator().manual_seed(c['seed'] + 1)
+    x = torch.randn(c['batch'], c['input_nc'], c['h'], c['w'], generator=g).cuda()
+    with torch.no_grad():
+        res = net(x)
+        res2 = net(x)
+    bad = []
+    for i, tower in enumerate(res):
+        for j, t in enumerate(tower):
+            assert torch.equal(t, res2[i][j])
+            gk = gold['t%d_l%d' % (i, j)]
+            d = np.abs(t.cpu().numpy() - gk)
+            rms = np.sqrt((gk ** 2).mean())
+            print('D tower %d layer %d: max|d|=%.4f mean|d|=%.5f ref rms=%.3f' % (i, j, d.max(), d.mean(), rms))
+            # bf16 operands, <= 5 layers deep: mean error within 2 %% of the layer's rms
+            if d.mean() > 0.02 * max(rms, 0.05):
+                bad.append((i, j, d.mean(), rms))
+    assert not bad, bad

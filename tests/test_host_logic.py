@@ -152,6 +152,20 @@ def test_plan_describe_layouts():
     assert d['conv_macs'] == 1057493090304
     # every value consumed by a stride-2 conv is parity split; reflect-3 layouts feed the 7x7 convs
     convs = d['convs']
-    assert sum(1 for c in convs if c['k'] == [7, 7]) == 3 + 3          # stems + heads (flow and weight heads fused)
+    assert sum(1 for c in convs if c['k'] == [7, 7]) == 2 + 3          # stems (seg+fg fused, img) + heads (flow+weight fused)
     assert all(c['TH'] * c['TW'] == 128 for c in convs)
     assert any(c['R'] == 7 for c in convs) and any(c['phases'] == 4 for c in convs)
+
+
+def test_conv_macs_discriminators():
+    """image D (39 ch) 42.54 GMAC and temporal D (13 ch) 37.93 GMAC per forward at 1024x512, num_D 3."""
+    from vid2vid_b200.plan import Plan
+    for nc, want in ((39, 42.54), (13, 37.93)):
+        d = NW.define_D(nc, 64, 3, 'batch', 3, True, [])
+        tot, h, w = 0.0, 512, 1024
+        for i in range(3):
+            p = Plan(0)
+            d._describe(p, 2 - i, 1, h, w)
+            tot += p.conv_macs
+            h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        assert abs(tot / 1e9 - want) < 0.01, (nc, tot)

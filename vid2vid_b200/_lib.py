@@ -40,7 +40,7 @@ SYMBOLS = [
     'v2v_version', 'v2v_last_error',
     'v2v_correlation_out_shape', 'v2v_correlation_forward', 'v2v_resample2d_forward', 'v2v_channelnorm_forward',
     'v2v_resample_forward', 'v2v_onehot_edges', 'v2v_avgpool3s2', 'v2v_fg_mask',
-    'v2v_plan_create', 'v2v_plan_destroy', 'v2v_g_input', 'v2v_g_conv', 'v2v_g_norm_act', 'v2v_g_conv_act',
+    'v2v_plan_create', 'v2v_plan_destroy', 'v2v_g_input', 'v2v_g_conv', 'v2v_g_norm_act', 'v2v_g_norm_act_slice', 'v2v_g_conv_act',
     'v2v_g_head', 'v2v_g_export', 'v2v_g_composite', 'v2v_plan_finalize', 'v2v_plan_repack', 'v2v_plan_run',
     'v2v_plan_profile', 'v2v_plan_num_kernels', 'v2v_plan_conv_macs', 'v2v_plan_workspace_bytes', 'v2v_plan_describe',
     'v2v_conv_tap_table',
@@ -66,6 +66,8 @@ def lib():
     l.v2v_g_conv.argtypes = [C.c_void_p, C.c_int, C.POINTER(ConvDesc), C.POINTER(C.c_int)]
     l.v2v_g_norm_act.argtypes = [C.c_void_p, C.c_int, C.POINTER(NormDesc), C.c_int, C.c_float, C.c_int, C.c_int,
                                  C.POINTER(C.c_int)]
+    l.v2v_g_norm_act_slice.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(NormDesc), C.c_int, C.c_float, C.c_int,
+                                       C.c_int, C.POINTER(C.c_int)]
     l.v2v_g_conv_act.argtypes = [C.c_void_p, C.c_int, C.POINTER(ConvDesc), C.c_int, C.c_float, C.POINTER(C.c_int)]
     l.v2v_g_head.argtypes = [C.c_void_p, C.c_int, C.POINTER(ConvDesc), C.POINTER(HeadChannel)]
     l.v2v_g_export.argtypes = [C.c_void_p, C.c_int, C.c_int]

@@ -28,7 +28,7 @@ namespace v2v {
 
 static constexpr int kThreads = 192;
 static constexpr int kEpiThreads = 128;
-static constexpr int kRedFloats = 2 * 4 * 2 * 128;   // [parity][warp][sum|sumsq][col]
+static constexpr int kRedFloats = 2 * 4 * 2 * 128 + 4 * 32 * 33;   // [parity][warp][sum|sumsq][col] + per-warp 32x33 transpose tiles
 
 // V2V_DBG bit2: CTA 0 records clock64() at role events of its first 24 work units and prints them at exit
 __device__ long long g_trace[3][24][8];
@@ -325,6 +325,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c * 32, r);
           tmem_ld_wait();
+          if (q == 0 && c == 0) TRACE(2, it, 3);
           if (last_tile && c == nchunks - 1) {    // accumulators fully read: hand the TMEM stage back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
@@ -354,18 +355,31 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
+          if (q == 0 && c == nchunks - 1) TRACE(2, it, 4);
           if (do_stats) {
-            float sq[32];
+            // column sums over this warp's 32 rows through a padded shared-memory transpose: 32 STS + 32 LDS per
+            // thread, conflict free, instead of two 31-step shuffle butterflies (the epilogue is the critical path of
+            // the small-K layers)
+            float* tt = red + 2 * 4 * 2 * 128 + q * (32 * 33);
+            __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-            const float s = warp_transpose_reduce(v, lane);
-            const float qq = warp_transpose_reduce(sq, lane);
+            for (int j = 0; j < 32; ++j) tt[lane * 33 + j] = v[j];
+            __syncwarp();
+            float s = 0.f, qq = 0.f;
+#pragma unroll
+            for (int r2 = 0; r2 < 32; ++r2) {
+              const float x = tt[r2 * 33 + lane];
+              s += x;
+              qq = fmaf(x, x, qq);
+            }
             redp[(q * 2 + 0) * 128 + c * 32 + lane] = s;
             redp[(q * 2 + 1) * 128 + c * 32 + lane] = qq;
           }
         }
+        if (q == 0) TRACE(2, it, 5);
         if (do_stats) {
           named_bar_sync(1, kEpiThreads);        // the four epilogue warps only
+          if (q == 0) TRACE(2, it, 6);
           if (etid < p.BN) {
             if (un.key != acc_key || n_img != acc_img) {
               if (acc_key >= 0 && acc_n0 + etid < p.stats_C) {
@@ -400,10 +414,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if ((p.dbg & 4) && blockIdx.x == 0 && threadIdx.x == 0) {
     const long long t0 = g_trace[0][0][0];
     for (int it = 0; it < 24; ++it)
-      printf("trace it=%2d prod: start %6lld issued %6lld | mma: start %6lld tmem_empty %6lld first_a %6lld [p1 top %6lld waited %6lld fenced %6lld descs %6lld] done %6lld | epi: start %6lld full %6lld done %6lld\n", it,
+      printf("trace it=%2d prod: start %6lld issued %6lld | mma: start %6lld tmem_empty %6lld first_a %6lld [p1 top %6lld waited %6lld fenced %6lld descs %6lld] done %6lld | epi: start %6lld full %6lld ld0 %6lld stored %6lld stats %6lld bar %6lld done %6lld\n", it,
              g_trace[0][it][0] - t0, g_trace[0][it][2] - t0, g_trace[1][it][0] - t0, g_trace[1][it][1] - t0, g_trace[1][it][2] - t0,
              g_trace[1][it][4] - t0, g_trace[1][it][5] - t0, g_trace[1][it][6] - t0, g_trace[1][it][7] - t0,
-             g_trace[1][it][3] - t0, g_trace[2][it][0] - t0, g_trace[2][it][1] - t0, g_trace[2][it][2] - t0);
+             g_trace[1][it][3] - t0, g_trace[2][it][0] - t0, g_trace[2][it][1] - t0, g_trace[2][it][3] - t0, g_trace[2][it][4] - t0,
+             g_trace[2][it][5] - t0, g_trace[2][it][6] - t0, g_trace[2][it][2] - t0);
   }
 }
 

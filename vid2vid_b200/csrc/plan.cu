@@ -154,6 +154,7 @@ struct Raw {
   float* stats = nullptr; int stats_rows = 0;
   float* scale = nullptr; float* shift = nullptr;
   int tiles_per_img = 0, num_phases = 1;
+  std::vector<int> running_done;   // channel offsets whose running stats already have an updating launch
 };
 
 enum GKind { G_INPUT, G_CONV, G_NORM_ACT, G_CONV_ACT, G_HEAD, G_EXPORT, G_COMPOSITE };
@@ -168,6 +169,7 @@ struct GOp {
   v2v_norm_desc norm{};
   int act = 0; float slope = 0.f;
   int add[2] = {-1, -1};
+  int n_off = 0, cC = 0;     // G_NORM_ACT: channel slice [n_off, n_off + cC) of the raw
   v2v_head_channel head[V2V_MAX_HEAD];
   CompositeParams comp{};
   // lowered
@@ -341,8 +343,8 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   kp.layout_type = kp.kc == 64 ? 2 : (kp.kc == 32 ? 4 : 6);
   kp.R = g.R;
   kp.a_slot_bytes = round_up((g.TW + g.R - 1) * g.TH * kp.row_bytes, 1024);
-  // shared-memory budget: 227 KB - stats scratch (8 KB) - alignment slack - barriers
-  const int budget = 212 * 1024;
+  // shared-memory budget: 227 KB - epilogue scratch (24.5 KB) - alignment slack - barriers
+  const int budget = 196 * 1024;
   // a weight slot holds the R taps served by one activation patch; keep >= 2 slots + 3 patches in the budget
   while (g.R > 1 && kp.BN > 32 && 2 * g.R * kp.BN * kp.row_bytes + 3 * kp.a_slot_bytes > budget) kp.BN /= 2;
   kp.b_slot_bytes = round_up(g.R * kp.BN * kp.row_bytes, 1024);
@@ -500,24 +502,32 @@ int v2v_g_conv(v2v_plan* p, int value_in, const v2v_conv_desc* c, int* raw_out) 
   return 0;
 }
 
-int v2v_g_norm_act(v2v_plan* p, int raw_in, const v2v_norm_desc* norm, int act, float slope, int add0, int add1,
-                   int* value_out) {
+int v2v_g_norm_act_slice(v2v_plan* p, int raw_in, int c_off, int C, const v2v_norm_desc* norm, int act, float slope,
+                         int add0, int add1, int* value_out) {
   V2V_REQUIRE(p && !p->lowered && norm && value_out, V2V_ERR_STATE, "plan already lowered or null");
   V2V_REQUIRE(raw_in >= 0 && raw_in < (int)p->raws.size(), V2V_ERR_INVALID, "bad raw id");
   const Raw& r = p->raws[raw_in];
+  V2V_REQUIRE(c_off >= 0 && C > 0 && c_off + C <= r.C && (c_off % 8) == 0, V2V_ERR_INVALID,
+              "bad channel slice [%d, %d) of %d", c_off, c_off + C, r.C);
   GOp op; op.kind = G_NORM_ACT; op.raw = raw_in; op.norm = *norm; op.act = act; op.slope = slope;
-  op.add[0] = add0; op.add[1] = add1;
+  op.add[0] = add0; op.add[1] = add1; op.n_off = c_off; op.cC = C;
   for (int k = 0; k < 2; ++k)
     if (op.add[k] >= 0) {
       V2V_REQUIRE(op.add[k] < (int)p->values.size(), V2V_ERR_INVALID, "bad addend id");
       const Value& a = p->values[op.add[k]];
-      V2V_REQUIRE(a.N == r.N && a.H == r.H && a.W == r.W && a.C == r.C, V2V_ERR_INVALID,
-                  "addend shape (%d,%d,%d,%d) != raw shape (%d,%d,%d,%d)", a.N, a.C, a.H, a.W, r.N, r.C, r.H, r.W);
+      V2V_REQUIRE(a.N == r.N && a.H == r.H && a.W == r.W && a.C == C, V2V_ERR_INVALID,
+                  "addend shape (%d,%d,%d,%d) != raw shape (%d,%d,%d,%d)", a.N, a.C, a.H, a.W, r.N, C, r.H, r.W);
     }
-  op.value_out = new_value(p, r.N, r.H, r.W, r.C);
+  op.value_out = new_value(p, r.N, r.H, r.W, C);
   p->gops.push_back(op);
   *value_out = op.value_out;
   return 0;
+}
+
+int v2v_g_norm_act(v2v_plan* p, int raw_in, const v2v_norm_desc* norm, int act, float slope, int add0, int add1,
+                   int* value_out) {
+  V2V_REQUIRE(p && raw_in >= 0 && raw_in < (int)p->raws.size(), V2V_ERR_INVALID, "bad raw id");
+  return v2v_g_norm_act_slice(p, raw_in, 0, p->raws[raw_in].C, norm, act, slope, add0, add1, value_out);
 }
 
 int v2v_g_conv_act(v2v_plan* p, int value_in, const v2v_conv_desc* c, int act, float slope, int* value_out) {
@@ -678,16 +688,25 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
       case G_NORM_ACT: {
         Raw& r = P->raws[op.raw];
         const GOp& cop = P->gops[r.conv_op];
+        bool fuse_fin = false;
+        FinalizeParams fin_params{};
         if (op.norm.kind != V2V_NORM_NONE) {
           XOp f; f.kind = X_FINALIZE;
           FinalizeParams& fp = f.fin;
-          fp.stats = r.stats; fp.Cs = r.C; fp.C = r.C; fp.N = r.N; fp.tiles_per_img = r.tiles_per_img; fp.num_phases = r.num_phases;
+          fp.stats = r.stats; fp.Cs = r.C; fp.C = op.cC; fp.c_off = op.n_off; fp.scale_stride = r.C;
+          fp.N = r.N; fp.tiles_per_img = r.tiles_per_img; fp.num_phases = r.num_phases;
           fp.count = (double)r.H * r.W; fp.instance = (op.norm.kind == V2V_NORM_INSTANCE);
-          fp.gamma = op.norm.gamma; fp.beta = op.norm.beta; fp.conv_bias = cop.conv.bias;
+          const int cout1 = cop.conv.Cout - cop.conv.Cout2;
+          V2V_REQUIRE(op.n_off == 0 || (cop.conv.Cout2 > 0 && op.n_off == cout1), V2V_ERR_UNSUPPORTED,
+                      "a raw slice must start at channel 0 or at the second weight set");
+          fp.gamma = op.norm.gamma; fp.beta = op.norm.beta; fp.conv_bias = op.n_off == 0 ? cop.conv.bias : cop.conv.bias2;
           fp.running_mean = op.norm.running_mean; fp.running_var = op.norm.running_var;
           fp.num_batches_tracked = reinterpret_cast<long long*>(op.norm.num_batches_tracked);
           fp.momentum = op.norm.momentum; fp.eps = op.norm.eps; fp.scale = r.scale; fp.shift = r.shift;
-          P->xops.push_back(f);
+          // fusing the finalize into the apply prologue measured slower than the separate launch: opt-in only
+          { const char* ef = getenv("V2V_FUSE_FINALIZE"); fuse_fin = (ef && ef[0] == '1') && r.N <= 8; }
+          fin_params = fp;
+          if (!fuse_fin) P->xops.push_back(f);
         } else {
           V2V_REQUIRE(cop.conv.bias == nullptr, V2V_ERR_UNSUPPORTED, "norm-less conv with bias must use v2v_g_conv_act");
         }
@@ -696,11 +715,18 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
           XOp a; a.kind = X_APPLY;
           ApplyParams& ap = a.app;
           ap.raw = r.desc;
-          ap.scale = op.norm.kind != V2V_NORM_NONE ? r.scale : nullptr; ap.shift = r.shift;
+          ap.raw.base = r.desc.base + op.n_off; ap.raw.Cvalid = op.cC;       // channel slice, full row stride
+          ap.scale = op.norm.kind != V2V_NORM_NONE ? r.scale + op.n_off : nullptr; ap.shift = r.shift + op.n_off;
+          ap.scale_stride = r.C;
           ap.act = op.act; ap.slope = op.slope;
           ap.n_add = 0;
           for (int k = 0; k < 2; ++k) if (op.add[k] >= 0) ap.add[ap.n_add++] = P->acts[P->values[op.add[k]].bufs[0]];
           ap.out = P->acts[vo.bufs[m]]; ap.pad_mode = P->act_pad_mode[vo.bufs[m]];
+          ap.fused = fuse_fin ? 1 : 0; ap.fin = fin_params;
+          ap.update_running = 0;
+          if (fuse_fin && std::find(r.running_done.begin(), r.running_done.end(), op.n_off) == r.running_done.end()) {
+            ap.update_running = 1; r.running_done.push_back(op.n_off);
+          }
           P->xops.push_back(a);
         }
         break;

@@ -125,19 +125,24 @@ struct FinalizeParams {
   float* running_var;
   long long* num_batches_tracked;
   float momentum, eps;
-  float* scale;            // [N][C]
-  float* shift;            // [N][C]
+  float* scale;            // [N][scale_stride], written at column c_off + c
+  float* shift;
+  int c_off, scale_stride; // channel slice of the raw tensor this norm layer covers
 };
 
 struct ApplyParams {
   RawDesc raw;
-  const float* scale;      // [N][raw.Cvalid]  (null -> identity)
+  const float* scale;      // [N][scale_stride], already offset to the slice  (null -> identity)
   const float* shift;
+  int scale_stride;
   int act; float slope;
   int n_add;
   ActDesc add[2];          // interior is read (any padding / parity)
   ActDesc out;
   int pad_mode;            // PadMode of out's halo
+  int fused;               // 1: compute scale/shift in the prologue from `fin` (no separate finalize launch)
+  int update_running;      // 1: this launch also applies the train-mode running-stat side effect
+  FinalizeParams fin;
 };
 
 // fp32 NCHW (caller tensor, read through the IO table) -> halo-padded NHWC bf16

@@ -210,6 +210,27 @@ def emit_head_pair(plan, mods_a, dst_a, mods_b, dst_b, v):
     plan.head(v, conv_desc(ca, pmode, pad, m2=cb), chans)
 
 
+def emit_unit_pair(plan, mods_a, mods_b, v):
+    """First units of two branches that read the same value with the same geometry (the 7x7 stems model_down_seg.1 and
+    indv_down.1, networks.py:132,153) as ONE convolution with stacked weights; each half keeps its own norm layer.
+    The small-N 7x7 stems are MMA-issue bound (a 128 x N x 16 MMA costs ~40 cycles for any N <= 32), so sharing the
+    instructions halves their cost.  Returns (value_a, value_b)."""
+    (ua,), (ub,) = _units(mods_a), _units(mods_b)
+    _, ca, pmode, pad, na, act_a, slope_a = ua
+    _, cb, pmode_b, pad_b, nb, act_b, slope_b = ub
+    assert na is not None and nb is not None and (pmode, pad) == (pmode_b, pad_b)
+    raw = plan.conv(v, conv_desc(ca, pmode, pad, m2=cb))
+    va = plan.norm_act(raw, norm_desc(na), act_a, slope_a, c_off=0, Cn=ca.out_channels)
+    vb = plan.norm_act(raw, norm_desc(nb), act_b, slope_b, c_off=ca.out_channels, Cn=cb.out_channels)
+    return va, vb
+
+
+def _can_pair(mods_a, mods_b):
+    ca, cb = mods_a[1], mods_b[1]
+    return (isinstance(ca, nn.Conv2d) and isinstance(cb, nn.Conv2d) and ca.in_channels == cb.in_channels and
+            ca.kernel_size == cb.kernel_size and ca.stride == cb.stride and ca.out_channels % 8 == 0)
+
+
 class _Planned(nn.Module):
     """Caches one plan per input-shape key; re-packs weights when parameters were modified in place
     and rebuilds when their storage moved (.cuda(), .to())."""
@@ -316,11 +337,17 @@ class CompositeGenerator(_Planned):
             self.model_final_w = nn.Sequential(*_head(ngf, 1, nn.Sigmoid()))
 
     flow_multiplier = 20.0
+    fuse_stems = True      # run model_down_seg.1 and indv_down.1 (same input, same 7x7 geometry) as one convolution
 
     def _describe(self, plan, N, H, W, use_raw_only=False):
         v_in = plan.input(S_IN, N, self.input_nc, 0, self.input_nc, H, W)
         v_prev = plan.input(S_PREV, N, self.prev_output_nc, 0, self.prev_output_nc, H, W)
-        seg = emit_seq(plan, self.model_down_seg, v_in)
+        fg0 = None
+        if self.use_fg_model and self.fuse_stems and _can_pair(self.model_down_seg, self.indv_down):
+            seg0, fg0 = emit_unit_pair(plan, list(self.model_down_seg)[:4], list(self.indv_down)[:4], v_in)
+            seg = emit_seq(plan, list(self.model_down_seg)[4:], seg0)
+        else:
+            seg = emit_seq(plan, self.model_down_seg, v_in)
         down = emit_seq(plan, self.model_down_img, v_prev, final_adds=(seg,))              # networks.py:204
         img_feat = emit_seq(plan, self.model_up_img, emit_seq(plan, self.model_res_img, down))   # :205
         plan.export(img_feat, S_IMGF)
@@ -331,7 +358,8 @@ class CompositeGenerator(_Planned):
             emit_head_pair(plan, self.model_final_flow, (S_FLOW, 2, self.flow_multiplier),               # :212
                            self.model_final_w, (S_W, 1, 1.0), flow_feat)                                # :213
         if self.use_fg_model:
-            fg_feat = emit_seq(plan, self.indv_up, emit_seq(plan, self.indv_res, emit_seq(plan, self.indv_down, v_in)))
+            fgd = emit_seq(plan, list(self.indv_down)[4:], fg0) if fg0 is not None else emit_seq(plan, self.indv_down, v_in)
+            fg_feat = emit_seq(plan, self.indv_up, emit_seq(plan, self.indv_res, fgd))
             plan.export(fg_feat, S_FGF)                                                    # :225
             emit_head(plan, self.indv_final, fg_feat, (S_FG, self.output_nc, 1.0))         # :226
         self._emit_composite(plan, N, H, W, use_raw_only)
@@ -404,7 +432,12 @@ class CompositeLocalGenerator(CompositeGenerator):
         v_in = plan.input(S_IN, N, self.input_nc, 0, self.input_nc, H, W)
         v_prev = plan.input(S_PREV, N, self.prev_output_nc, 0, self.prev_output_nc, H, W)
         ci = plan.input(S_CI, N, c2, 0, c2, h2, w2)
-        seg = emit_seq(plan, self.model_down_seg, v_in)
+        fg0 = None
+        if self.use_fg_model and self.fuse_stems and _can_pair(self.model_down_seg, self.indv_down):
+            seg0, fg0 = emit_unit_pair(plan, list(self.model_down_seg)[:4], list(self.indv_down)[:4], v_in)
+            seg = emit_seq(plan, list(self.model_down_seg)[4:], seg0)
+        else:
+            seg = emit_seq(plan, self.model_down_seg, v_in)
         fin = emit_seq(plan, self.model_down_img, v_prev, defer_last=True)      # down_img = seg + img (:298)
         img_feat = emit_seq(plan, self.model_up_img, fin((seg, ci)))             # :299
         plan.export(img_feat, S_IMGF)
@@ -418,7 +451,11 @@ class CompositeLocalGenerator(CompositeGenerator):
         if self.use_fg_model:
             cg_c = self.indv_down[4].out_channels
             cg = plan.input(S_CG, N, cg_c, 0, cg_c, h2, w2)
-            fg_feat = emit_seq(plan, self.indv_up, emit_seq(plan, self.indv_down, v_in, final_adds=(cg,)))   # :319
+            if fg0 is not None:
+                fgd = emit_seq(plan, list(self.indv_down)[4:], fg0, final_adds=(cg,))
+            else:
+                fgd = emit_seq(plan, self.indv_down, v_in, final_adds=(cg,))
+            fg_feat = emit_seq(plan, self.indv_up, fgd)                                                       # :319
             plan.export(fg_feat, S_FGF)
             emit_head(plan, self.indv_final, fg_feat, (S_FG, self.output_nc, 1.0))
         self._emit_composite(plan, N, H, W, use_raw_only)
@@ -545,13 +582,16 @@ class NLayerDiscriminator(nn.Module):
             self.model = nn.Sequential(*[m for s in seq for m in s])
 
 
-class MultiscaleDiscriminator(nn.Module):
-    """Parameter container with the keys of models/networks.py:634-675.  The tcgen05 forward of the
-    discriminator towers is scheduled after the generator path (DESIGN.md scope table)."""
+class MultiscaleDiscriminator(_Planned):
+    """models/networks.py:634-675: num_D PatchGAN towers (NLayerDiscriminator, :679-725) on an avg-pool pyramid of the
+    input; with getIntermFeat every layer output of every tower is returned (feature-matching loss,
+    models/vid2vid_model_D.py:35-36).  Each tower is one plan: 4x4 s2 conv + bias + LeakyReLU epilogue, (n_layers - 1) x
+    [4x4 s2 conv, norm, LeakyReLU], 4x4 s1 conv + norm + LeakyReLU, and the 1-channel 4x4 s1 head."""
 
     def __init__(self, input_nc, ndf=64, n_layers=3, norm_layer=nn.BatchNorm2d, num_D=3, getIntermFeat=False):
         super().__init__()
         self.num_D, self.n_layers, self.getIntermFeat = num_D, n_layers, getIntermFeat
+        self.input_nc = input_nc
         for i in range(num_D):
             netD = NLayerDiscriminator(input_nc, min(64, ndf * (2 ** (num_D - 1 - i))), n_layers, norm_layer,
                                        getIntermFeat)
@@ -562,9 +602,62 @@ class MultiscaleDiscriminator(nn.Module):
                 setattr(self, 'layer' + str(i), netD.model)
         self.downsample = nn.AvgPool2d(3, stride=2, padding=[1, 1], count_include_pad=False)
 
+    def _tower_layers(self, d):
+        """List of per-layer module lists of tower d."""
+        if self.getIntermFeat:
+            return [list(getattr(self, 'scale%d_layer%d' % (d, j))) for j in range(self.n_layers + 2)]
+        mods, layers, cur = list(getattr(self, 'layer' + str(d))), [], []
+        for m in mods:
+            if isinstance(m, nn.Conv2d) and cur:
+                layers.append(cur)
+                cur = []
+            cur.append(m)
+        layers.append(cur)
+        return layers
+
+    def _describe(self, plan, d, N, H, W):
+        layers = self._tower_layers(d)
+        v = plan.input(0, N, self.input_nc, 0, self.input_nc, H, W)
+        shapes = []
+        for j, mods in enumerate(layers):
+            last = j == len(layers) - 1
+            conv = mods[0]
+            oh = (H + 2 * conv.padding[0] - conv.kernel_size[0]) // conv.stride[0] + 1
+            ow = (W + 2 * conv.padding[1] - conv.kernel_size[1]) // conv.stride[1] + 1
+            if last:
+                plan.head(v, conv_desc(conv), [(1 + j, 0, 1, L.ACT_NONE, 1.0)])      # 1-channel patch logits, fp32
+            else:
+                v = emit_seq(plan, mods, v)
+                if self.getIntermFeat:
+                    plan.export(v, 1 + j)
+            shapes.append((conv.out_channels, oh, ow))
+            H, W = oh, ow
+        return shapes
+
+    def _tower_forward(self, d, x):
+        N, _, H, W = x.shape
+        key = ('D', d, N, H, W)
+        shapes_box = {}
+
+        def build(p):
+            shapes_box['s'] = self._describe(p, d, N, H, W)
+        plan = self._get_plan(key, x.device, build)
+        shapes = self._plans()[key].setdefault('shapes', shapes_box.get('s'))
+        outs = [torch.empty((N, c, h, w), device=x.device, dtype=torch.float32) for (c, h, w) in shapes]
+        io = [x] + [o if (self.getIntermFeat or j == len(outs) - 1) else None for j, o in enumerate(outs)]
+        plan.run(io, self.use_cuda_graph)
+        return outs if self.getIntermFeat else [outs[-1]]
+
     def forward(self, input):
-        raise NotImplementedError('MultiscaleDiscriminator.forward on sm_100a is not built yet (round 2); '
-                                  'there is deliberately no PyTorch fallback')
+        from . import ops
+        self._require_cuda(input)
+        result = []
+        x = input.contiguous()
+        for i in range(self.num_D):
+            result.append(self._tower_forward(self.num_D - 1 - i, x))
+            if i != self.num_D - 1:
+                x = ops.avgpool3s2(x)
+        return result
 
 
 def build_netG(opt, s):

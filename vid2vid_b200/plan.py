@@ -89,11 +89,15 @@ class Plan:
         L.check(L.lib().v2v_g_conv(self._h, vin, C.byref(desc), C.byref(r)))
         return r.value
 
-    def norm_act(self, raw, ndesc, act=L.ACT_NONE, slope=0.0, adds=()):
+    def norm_act(self, raw, ndesc, act=L.ACT_NONE, slope=0.0, adds=(), c_off=0, Cn=None):
         v = C.c_int()
         adds = list(adds) + [-1, -1]
         self._keep.append(ndesc)
-        L.check(L.lib().v2v_g_norm_act(self._h, raw, C.byref(ndesc), act, slope, adds[0], adds[1], C.byref(v)))
+        if Cn is None:
+            L.check(L.lib().v2v_g_norm_act(self._h, raw, C.byref(ndesc), act, slope, adds[0], adds[1], C.byref(v)))
+        else:
+            L.check(L.lib().v2v_g_norm_act_slice(self._h, raw, c_off, Cn, C.byref(ndesc), act, slope, adds[0], adds[1],
+                                                 C.byref(v)))
         return v.value
 
     def conv_act(self, vin, desc, act=L.ACT_NONE, slope=0.0):
