@@ -55,36 +55,53 @@ def frame_macs(wl):
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md): NVML every 20 ms, nvidia-smi fallback."""
+
+    REASONS = {'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40, 'sw_power_cap': 0x4}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.sm, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
-        q = 'clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
-            'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
         while not self.stop_flag:
             try:
-                o = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
-                                   capture_output=True, text=True, timeout=5).stdout.strip()
-                if o:
-                    self.samples.append([x.strip() for x in o.split(',')])
+                if self.nvml is not None:
+                    self.sm.append(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+                    try:
+                        mask = self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        mask = self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for n, bit in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(n)
+                    time.sleep(0.02)
+                else:
+                    q = 'clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+                        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+                    o = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q, '--format=csv,noheader,nounits'],
+                                       capture_output=True, text=True, timeout=5).stdout.strip().split(',')
+                    self.sm.append(int(float(o[0])))
+                    self.max_mhz = int(float(o[1]))
+                    for n, v in zip(['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'], o[2:]):
+                        if v.strip().lower().startswith('active'):
+                            self.reasons.add(n)
             except Exception:
-                pass
-            time.sleep(0.1)
+                time.sleep(0.05)
 
     def summary(self):
-        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace('.', '').isdigit())
-        reasons = set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
-        for s in self.samples:
-            for i, n in enumerate(names):
-                if len(s) > 3 + i and s[3 + i].lower().startswith('active'):
-                    reasons.add(n)
-        mx = [int(float(s[1])) for s in self.samples if len(s) > 1 and s[1].replace('.', '').isdigit()]
-        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx[0] if mx else None, 'reasons': sorted(reasons),
-                'samples': len(self.samples)}
+        sm = sorted(self.sm)
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+                'samples': len(sm)}
 
 
 def peaks():
@@ -209,51 +226,67 @@ def run_ours(args, rank, world, local_rank):
                      'frame_flops_over_frame_time_tflops': 2 * fmacs / (frame_ms * 1e-3) / 1e12},
     }
     if world == 1 and not args.no_cpu_baseline:
-        out['cpu_baseline'] = cpu_frames_per_s(args.workload, steps=1, warm=0)
+        out['cpu_baseline'] = cpu_frames_per_s(args.workload, steps=1, warm=0, budget_s=25.0)
     print(json.dumps(out))
 
 
 # ----------------------------------------------------------------------------------------------- CPU port
-def cpu_frames_per_s(workload, steps, warm):
-    """Oracle port on the host cores: steady-state frames of the same workload (prev-frame state zero-filled;
-    the cost of a frame does not depend on its content)."""
+def cpu_frames_per_s(workload, steps, warm, budget_s=150.0):
+    """Oracle port on the host cores.  A step is one steady-state frame of the workload restricted to a horizontal band
+    of the image (full width, height H*f, f in {1/8, 1/4, 1/2, 1}): every layer does the same work per pixel, so
+    frames/s = f / seconds-per-band.  f is the largest fraction for which steps + warm bands fit in `budget_s`
+    (calibrated on one 1/8 band); previous-frame state is zero-filled (the cost does not depend on the content)."""
     import torch
     from oracle import generator_oracle as GO
     from vid2vid_b200 import networks as NW
     from vid2vid_b200.utils import synth_label_sequence
     wl = WORKLOADS[workload]
-    cores = os.cpu_count()
+    # PyTorch's CPU convolutions stop scaling (and then regress) well before 128 threads on the GPU hosts
+    cores = min(os.cpu_count(), int(os.environ.get('V2V_CPU_THREADS', '32')))
     torch.set_num_threads(cores)
     opt = make_opt_for(workload)
     opt.gpu_ids = []
     torch.manual_seed(0)
     sds = [NW.build_netG(opt, s).state_dict() for s in range(wl['n_scales'])]
-    orc = GO.ModelGOracle(opt, sds)
-    orc.fake_B_prev = [torch.zeros(2, 3, wl['H'] // 2 ** s, wl['W'] // 2 ** s) for s in range(wl['n_scales'])]
-    seq = synth_label_sequence(steps + warm + 3, wl['H'], wl['W'], label_nc=35, block=64, seed=0)
-    t = 0
-    with torch.no_grad():
-        for _ in range(warm):
-            orc.inference(seq[:, t:t + 3], seq[:, t:t + 3]); t += 1
+
+    def run(frac, n, seed):
+        H = max(32, int(wl['H'] * frac) // 32 * 32)
+        orc = GO.ModelGOracle(opt, sds)
+        orc.fake_B_prev = [torch.zeros(2, 3, H // 2 ** s, wl['W'] // 2 ** s) for s in range(wl['n_scales'])]
+        seq = synth_label_sequence(n + 2, H, wl['W'], label_nc=35, block=32, seed=seed)
         t0 = time.time()
-        for _ in range(steps):
-            orc.inference(seq[:, t:t + 3], seq[:, t:t + 3]); t += 1
-        dt = time.time() - t0
+        with torch.no_grad():
+            for t in range(n):
+                orc.inference(seq[:, t:t + 3], seq[:, t:t + 3])
+        return (time.time() - t0) / n, H
+
+    run(1.0 / 16, 1, 0)                              # warm the thread pool / allocator
+    t8, _ = run(1.0 / 8, 1, 1)                       # calibration
+    frac = 1.0 / 16
+    for f in (1.0, 0.5, 0.25, 0.125):
+        if t8 * 8 * f * (steps + warm) <= budget_s:
+            frac = f
+            break
+    if warm:
+        run(frac, warm, 2)
+    dt, H = run(frac, steps, 3)
     model = ''
     try:
         model = [l.split(':')[1].strip() for l in open('/proc/cpuinfo') if l.startswith('model name')][0]
     except Exception:
         pass
-    return {'value': steps / dt, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-            'sample': '%d steady-state frame(s) of %s, torch %s CPU fp32, %d threads, %s' % (steps, wl['desc'], torch.__version__, cores, model),
-            'seconds': dt}
+    eff = H / wl['H']
+    return {'value': eff / dt, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
+            'sample': '%d step(s), each one steady-state frame of a %dx%d band (%.3f of the %s frame), torch %s CPU fp32, %d threads, %s'
+                      % (steps, wl['W'], H, eff, wl['desc'], torch.__version__, cores, model),
+            'seconds_per_step': dt}
 
 
 def run_reference(args, rank, world):
     if rank != 0:
         return
     K, Wm = args.steps, args.warmup
-    r = cpu_frames_per_s(args.workload, steps=K, warm=min(Wm, 1))
+    r = cpu_frames_per_s(args.workload, steps=K, warm=min(Wm, 1), budget_s=180.0)
     wl = WORKLOADS[args.workload]
     out = {'impl': 'reference',
            'metric': 'frames/sec at 2048x1024 inference' if args.workload == 'cfg4' else 'frames/sec inference (%s)' % args.workload,
@@ -269,8 +302,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=8)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg4', choices=list(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', dest='no_cpu_baseline', action='store_true')
