@@ -186,41 +186,43 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (warp-uniform loop, elected lane issues)
-    const uint32_t idesc = make_idesc_bf16(128, p.BN);
-    int gs = 0, it = 0;
-    uint32_t gpar = 0, gen = 0;
-    int prev_key = -1;
-    const uint64_t a_step = (uint64_t)(p.row_bytes >> 4), b_step = (uint64_t)(b_tx >> 4);
-    for (int u = t_first; u < p.total_units; u += t_step, ++it) {
-      const Unit un = decode_unit(p, u);
-      const ConvPhase ph = p.phases[un.phase];
-      const bool first_of_key = un.key != prev_key;
-      if (p.b_resident && first_of_key && prev_key >= 0) gen ^= 1;
-      prev_key = un.key;
-      const int u_next = u + t_step;
-      const bool last_of_key = (u_next >= p.total_units) || (u_next / p.mg_total != un.key);
-      const int nsteps = (ph.group_end - ph.group_begin) * p.cblocks;
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      TRACE(1, it, 0);
-      mbar_wait(&tmem_empty[as], aphase ^ 1);        // the epilogue has drained this accumulator stage
-      if (p.b_resident && first_of_key) mbar_wait(bres_full, gen);
-      tcgen05_fence_after();
-      TRACE(1, it, 1);
-      const uint32_t tmem_d = tmem_base + as * acc_cols;
-      uint32_t acc = 0;
-      for (int s0 = 0; s0 < nsteps; s0 += p.CG) {
-        const int n = min(p.CG, nsteps - s0);
-        mbar_wait(&g_full[gs], gpar);
+    // ------------------------------------------------------------ MMA issuer: one elected lane runs the whole loop
+    // (entered through elect.sync, so ptxas keeps UTCHMMA / UTCBAR on the uniform datapath; no per-group re-election
+    // or __syncwarp on the issue path)
+    if (elect_one_sync()) {
+      const uint32_t idesc = make_idesc_bf16(128, p.BN);
+      int gs = 0, it = 0;
+      uint32_t gpar = 0, gen = 0;
+      int prev_key = -1;
+      const uint64_t a_step = (uint64_t)(p.row_bytes >> 4), b_step = (uint64_t)(b_tx >> 4);
+      const uint32_t sBres_u32 = smem_u32(sBres);
+      for (int u = t_first; u < p.total_units; u += t_step, ++it) {
+        const Unit un = decode_unit(p, u);
+        const ConvPhase ph = p.phases[un.phase];
+        const bool first_of_key = un.key != prev_key;
+        if (p.b_resident && first_of_key && prev_key >= 0) gen ^= 1;
+        prev_key = un.key;
+        const int u_next = u + t_step;
+        const bool last_of_key = (u_next >= p.total_units) || (u_next / p.mg_total != un.key);
+        const int nsteps = (ph.group_end - ph.group_begin) * p.cblocks;
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        TRACE(1, it, 0);
+        mbar_wait(&tmem_empty[as], aphase ^ 1);        // the epilogue has drained this accumulator stage
+        if (p.b_resident && first_of_key) mbar_wait(bres_full, gen);
         tcgen05_fence_after();
-        if (s0 == 0) TRACE(1, it, 2);
-        if (elect_one_sync()) {
+        TRACE(1, it, 1);
+        const uint32_t tmem_d = tmem_base + as * acc_cols;
+        uint32_t first = 0;
+        for (int s0 = 0; s0 < nsteps; s0 += p.CG) {
+          const int n = min(p.CG, nsteps - s0);
+          mbar_wait(&g_full[gs], gpar);
+          tcgen05_fence_after();
+          if (s0 == 0) TRACE(1, it, 2);
           const uint32_t base = smem_u32(sG + (size_t)gs * group_bytes);
-          uint32_t first = acc;
           for (int i = 0; i < n; ++i) {
             const uint32_t a_base = base + i * p.a_slot_bytes;
-            const uint32_t b_base = p.b_resident ? smem_u32(sBres) + (s0 + i) * p.b_slot_bytes
+            const uint32_t b_base = p.b_resident ? sBres_u32 + (s0 + i) * p.b_slot_bytes
                                                  : base + p.CG * p.a_slot_bytes + i * p.b_slot_bytes;
             // descriptors differ only in the 14-bit (address >> 4) field: build once per step, then add
             uint64_t ad = make_kmajor_desc(a_base, p.sbo_bytes, p.layout_type);
@@ -252,12 +254,10 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (p.b_resident && last_of_key) umma_commit(bres_empty);
             umma_commit(&tmem_full[as]);               // accumulator complete
           }
+          if (++gs == p.SG) { gs = 0; gpar ^= 1; }
         }
-        __syncwarp();
-        acc = 1;
-        if (++gs == p.SG) { gs = 0; gpar ^= 1; }
+        TRACE(1, it, 3);
       }
-      TRACE(1, it, 3);
     }
   } else {
     // ------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)

@@ -12,67 +12,66 @@
 
 namespace v2v {
 
-__global__ void stats_finalize_kernel(FinalizeParams p) {
-  const int c = blockIdx.x;
-  __shared__ double sh[2][128];
-  double bs = 0.0, bq = 0.0;       // batch totals (thread 0 only)
-  double rm_acc = 0.0, rv_acc = 0.0;
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// One warp per channel (4 channels per block): lanes stride the per-CTA partial rows, fp64 shuffle reduction.
+__global__ void __launch_bounds__(128) stats_finalize_kernel(FinalizeParams p) {
+  const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (c >= p.C) return;
+  const int rows_img = p.num_phases * p.tiles_per_img;
+  double bs = 0.0, bq = 0.0, rm_acc = 0.0, rv_acc = 0.0;
   for (int n = 0; n < p.N; ++n) {
     double s = 0.0, q = 0.0;
-    const int rows_img = p.num_phases * p.tiles_per_img;
-    for (int i = threadIdx.x; i < rows_img; i += blockDim.x) {
+    for (int i = lane; i < rows_img; i += 32) {
       const int ph = i / p.tiles_per_img, t = i - ph * p.tiles_per_img;
       const size_t row = (size_t)ph * p.N * p.tiles_per_img + (size_t)n * p.tiles_per_img + t;
       s += (double)p.stats[(row * 2 + 0) * p.Cs + p.c_off + c];
       q += (double)p.stats[(row * 2 + 1) * p.Cs + p.c_off + c];
     }
-    sh[0][threadIdx.x] = s; sh[1][threadIdx.x] = q;
-    __syncthreads();
-    for (int k = blockDim.x / 2; k > 0; k >>= 1) {
-      if (threadIdx.x < k) { sh[0][threadIdx.x] += sh[0][threadIdx.x + k]; sh[1][threadIdx.x] += sh[1][threadIdx.x + k]; }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-      s = sh[0][0]; q = sh[1][0];
-      if (p.instance) {
-        const double mean = s / p.count;
-        double var = q / p.count - mean * mean;
-        if (var < 0) var = 0;
+    s = warp_sum_d(s); q = warp_sum_d(q);
+    if (p.instance) {
+      const double mean = s / p.count;
+      double var = q / p.count - mean * mean;
+      if (var < 0) var = 0;
+      if (lane == 0) {
         const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
         const float sc = g * (float)(1.0 / sqrt(var + (double)p.eps));
         p.scale[(size_t)n * p.scale_stride + p.c_off + c] = sc;
         p.shift[(size_t)n * p.scale_stride + p.c_off + c] = b - (float)mean * sc;
-        rm_acc += mean;
-        rv_acc += var * (p.count / (p.count > 1 ? p.count - 1 : 1));
-      } else {
-        bs += s; bq += q;
       }
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    double mean_run, var_run;
-    if (p.instance) {
-      mean_run = rm_acc / p.N; var_run = rv_acc / p.N;
+      rm_acc += mean;
+      rv_acc += var * (p.count / (p.count > 1 ? p.count - 1 : 1));
     } else {
-      const double cnt = p.count * p.N;
-      const double mean = bs / cnt;
-      double var = bq / cnt - mean * mean;
-      if (var < 0) var = 0;
-      const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
-      const float sc = g * (float)(1.0 / sqrt(var + (double)p.eps));
-      for (int n = 0; n < p.N; ++n) {
-        p.scale[(size_t)n * p.scale_stride + p.c_off + c] = sc;
-        p.shift[(size_t)n * p.scale_stride + p.c_off + c] = b - (float)mean * sc;
-      }
-      mean_run = mean; var_run = var * (cnt / (cnt > 1 ? cnt - 1 : 1));
+      bs += s; bq += q;
     }
-    if (p.running_mean) {   // train-mode side effect of nn.BatchNorm2d / InstanceNorm2d(track_running_stats)
-      const float bias = p.conv_bias ? p.conv_bias[c] : 0.f;
-      p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * ((float)mean_run + bias);
-      p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)var_run;
-      if (c == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
+  }
+  if (lane != 0) return;
+  double mean_run, var_run;
+  if (p.instance) {
+    mean_run = rm_acc / p.N; var_run = rv_acc / p.N;
+  } else {
+    const double cnt = p.count * p.N;
+    const double mean = bs / cnt;
+    double var = bq / cnt - mean * mean;
+    if (var < 0) var = 0;
+    const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
+    const float sc = g * (float)(1.0 / sqrt(var + (double)p.eps));
+    for (int n = 0; n < p.N; ++n) {
+      p.scale[(size_t)n * p.scale_stride + p.c_off + c] = sc;
+      p.shift[(size_t)n * p.scale_stride + p.c_off + c] = b - (float)mean * sc;
     }
+    mean_run = mean; var_run = var * (cnt / (cnt > 1 ? cnt - 1 : 1));
+  }
+  if (p.running_mean) {   // train-mode side effect of nn.BatchNorm2d / InstanceNorm2d(track_running_stats)
+    const float bias = p.conv_bias ? p.conv_bias[c] : 0.f;
+    p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * ((float)mean_run + bias);
+    p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)var_run;
+    if (c == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
   }
 }
 
@@ -83,12 +82,15 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {   // nn.ReflectionPad
 }
 
 // Grid-stride over (padded pixel, 8-channel vector) items (2-D-grid and multi-item-per-thread variants measured slower).
-__device__ __forceinline__ void apply_item(const ApplyParams& p, int vecs, int Wpad, int Hpad, long long idx) {
-  const int v = (int)(idx % vecs);
-  long long t = idx / vecs;
-  const int xp = (int)(t % Wpad); t /= Wpad;
-  const int yp = (int)(t % Hpad);
-  const int n = (int)(t / Hpad);
+// 32-bit index arithmetic throughout: with 64-bit div/mod this kernel was instruction bound (~4 x 100-instruction
+// divisions per 16-byte item), not bandwidth bound.
+__device__ __forceinline__ void apply_item(const ApplyParams& p, int vecs, int Wpad, int Hpad, unsigned idx) {
+  const unsigned t0 = idx / (unsigned)vecs;
+  const int v = (int)(idx - t0 * (unsigned)vecs);
+  const unsigned t1 = t0 / (unsigned)Wpad;
+  const int xp = (int)(t0 - t1 * (unsigned)Wpad);
+  const int n = (int)(t1 / (unsigned)Hpad);
+  const int yp = (int)(t1 - (unsigned)n * (unsigned)Hpad);
   int y = yp - p.out.pad_t, x = xp - p.out.pad_l;
   const bool halo = (y < 0 || y >= p.out.H || x < 0 || x >= p.out.W);
   uint4 o = make_uint4(0, 0, 0, 0);
@@ -137,9 +139,9 @@ __device__ __forceinline__ void apply_item(const ApplyParams& p, int vecs, int W
 __global__ void __launch_bounds__(256) norm_apply_kernel(ApplyParams p) {
   const int vecs = p.out.C / 8;
   const int Hpad = p.out.H + p.out.pad_t + p.out.pad_b, Wpad = p.out.W + p.out.pad_l + p.out.pad_r;
-  const long long total = (long long)p.out.N * Hpad * Wpad * vecs;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += stride) apply_item(p, vecs, Wpad, Hpad, idx);
+  const unsigned total = (unsigned)p.out.N * Hpad * Wpad * vecs;        // < 2^31 checked by the launcher
+  const unsigned stride = gridDim.x * blockDim.x;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += stride) apply_item(p, vecs, Wpad, Hpad, idx);
 }
 
 // Fused variant: block (x, g) owns channel group g (64 channels = 128 bytes per pixel, coalesced) and a grid-stride share
@@ -262,13 +264,14 @@ static inline int grid_for(long long total, int block) {
 }
 
 cudaError_t launch_stats_finalize(const FinalizeParams& p, cudaStream_t stream) {
-  stats_finalize_kernel<<<p.C, 128, 0, stream>>>(p);
+  stats_finalize_kernel<<<(p.C + 3) / 4, 128, 0, stream>>>(p);
   return cudaGetLastError();
 }
 
 cudaError_t launch_norm_apply(const ApplyParams& p, cudaStream_t stream) {
   const long long total = (long long)p.out.N * (p.out.H + p.out.pad_t + p.out.pad_b) *
                           (p.out.W + p.out.pad_l + p.out.pad_r) * (p.out.C / 8);
+  if (total >= (1LL << 31)) return cudaErrorInvalidValue;
   if (p.fused) {
     const int groups = (p.out.C + 63) / 64;
     int gx = grid_for(total / groups + 1, 256);

@@ -13,13 +13,12 @@ namespace v2v {
 // out (F, label_nc + use_inst, H, W) ; labels / inst (F, H, W) float ids ; F = b * t frames
 __global__ void onehot_edges_kernel(const float* __restrict__ labels, const float* __restrict__ inst,
                                     float* __restrict__ out, int F, int label_nc, int use_inst, int H, int W) {
-  const size_t HW = (size_t)H * W, total = (size_t)F * HW;
+  const size_t HW = (size_t)H * W;
   const int Cout = label_nc + (use_inst ? 1 : 0);
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int f = (int)(idx / HW);
-    const size_t pix = idx - (size_t)f * HW;
-    const int y = (int)(pix / W), x = (int)(pix - (size_t)y * W);
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;   // grid = (x blocks, row, frame)
+  if (x < W) {
+    const size_t pix = (size_t)y * W + x;
+    const size_t idx = (size_t)f * HW + pix;
     const int lab = (int)labels[idx];
     float* o = out + (size_t)f * Cout * HW + pix;
     for (int c = 0; c < label_nc; ++c) o[(size_t)c * HW] = (c == lab) ? 1.f : 0.f;
@@ -36,16 +35,14 @@ __global__ void onehot_edges_kernel(const float* __restrict__ labels, const floa
   }
 }
 
-// in (P, H, W) -> out (P, H/2, W/2) planes
-__global__ void avgpool3s2_kernel(const float* __restrict__ in, float* __restrict__ out, int P, int H, int W) {
-  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
-  const size_t total = (size_t)P * Ho * Wo;
-  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int xo = (int)(idx % Wo);
-    const int yo = (int)((idx / Wo) % Ho);
-    const size_t pl = idx / ((size_t)Wo * Ho);
-    const float* ip = in + pl * (size_t)H * W;
+// in (P, H, W) -> out (P, H/2, W/2) planes; grid = (x blocks, output row, plane): no per-element divisions
+__global__ void __launch_bounds__(256) avgpool3s2_kernel(const float* __restrict__ in, float* __restrict__ out, int P, int H, int W,
+                                                         int Ho, int Wo) {
+  const int xo = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xo >= Wo) return;
+  const int yo = blockIdx.y;
+  for (int pl = blockIdx.z; pl < P; pl += gridDim.z) {
+    const float* ip = in + (size_t)pl * H * W;
     float s = 0.f;
     int cnt = 0;
 #pragma unroll
@@ -56,11 +53,11 @@ __global__ void avgpool3s2_kernel(const float* __restrict__ in, float* __restric
       for (int dx = -1; dx <= 1; ++dx) {
         const int x = 2 * xo + dx;
         if (x < 0 || x >= W) continue;
-        s += ip[(size_t)y * W + x];
+        s += __ldg(ip + (size_t)y * W + x);
         ++cnt;
       }
     }
-    out[idx] = s / (float)cnt;
+    out[((size_t)pl * Ho + yo) * Wo + xo] = s / (float)cnt;
   }
 }
 
@@ -87,12 +84,14 @@ static inline int grid1d(size_t total) {
 
 cudaError_t launch_onehot_edges(const float* labels, const float* inst, float* out, int F, int label_nc, int use_inst,
                                 int H, int W, cudaStream_t s) {
-  onehot_edges_kernel<<<grid1d((size_t)F * H * W), 256, 0, s>>>(labels, inst, out, F, label_nc, use_inst, H, W);
+  dim3 grid((W + 255) / 256, H, F);
+  onehot_edges_kernel<<<grid, 256, 0, s>>>(labels, inst, out, F, label_nc, use_inst, H, W);
   return cudaGetLastError();
 }
 cudaError_t launch_avgpool3s2(const float* in, float* out, int P, int H, int W, cudaStream_t s) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
-  avgpool3s2_kernel<<<grid1d((size_t)P * Ho * Wo), 256, 0, s>>>(in, out, P, H, W);
+  dim3 grid((Wo + 255) / 256, Ho, P < 64 ? P : 64);
+  avgpool3s2_kernel<<<grid, 256, 0, s>>>(in, out, P, H, W, Ho, Wo);
   return cudaGetLastError();
 }
 cudaError_t launch_fg_mask(const float* real_A, float* mask, int B, int T, int C, int H, int W, int t,
