@@ -35,8 +35,9 @@ for f in sorted(os.listdir(src)):
         tot = sum(r['ms'] for r in rows)
         agg = {}
         for r in rows:
+            opname = r.get('op', r.get('kind'))
             if 'Cin' not in r:
-                key = ('scale%d' % r['scale'], r['kind'] if isinstance(r['kind'], str) else 'conv')
+                key = ('scale%d' % r['scale'], opname if isinstance(opname, str) else 'conv')
             else:
                 key = ('scale%d' % r['scale'], 'head' if r['Cout'] <= 3 else 'conv', r['Cin'], r['Cout'], '%dx%d' % tuple(r['k']),
                        's%d' % r['stride'], 'T' if r['transposed'] else '-', '%dx%d' % tuple(r['grid']), 'R%d' % r['R'],
