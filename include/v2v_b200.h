@@ -176,7 +176,8 @@ int64_t v2v_plan_workspace_bytes(const v2v_plan* plan);
 int64_t v2v_plan_describe(const v2v_plan* plan, char* buf, int64_t cap);
 
 /* Host-only: the tap-group table the kernel would use for a convolution (pure function; no GPU).
- * Each group g: plane[g], dy[g], dx[g], tap0[g]; R taps per group; phase p covers groups
+ * Each group g: plane[g], dy[g], dx[g], tap0[g]; R[0] taps per group, tap r reading the group's patch shifted by
+ * (r / R[1]) rows and (r % R[1]) columns (R must hold 2 entries); phase p covers groups
  * [phase_begin[p], phase_begin[p+1]); per-phase output offsets oy_add/ox_add; buffer padding pads[4] =
  * {top, left, bottom, right}; parity; grid_h/grid_w; out_h/out_w.  Arrays must hold 64 / 5 / 4 entries. */
 int v2v_conv_tap_table(const v2v_conv_desc* conv, int H, int W, int allow_reuse, int* n_groups, int* R, int* plane,

@@ -92,6 +92,14 @@ CASES = [
     ('kc16_s2_then_kc32_deconv', lambda: NW._down(16, 32, BN) + NW._up(32, 16, BN), (1, 16, 32, 64)),
     ('kc16_resblock_small', lambda: [NW.ResnetBlock(16, 'reflect', BN)], (1, 16, 16, 32)),
     ('kc32_s2_mt', lambda: NW._down(32, 64, BN), (1, 32, 160, 512)),
+    # 2-D patch mode (16x8 tiles, one patch for all taps): ragged edges, batch straddle, halved N tile with resident
+    # weights, 64-byte rows with streamed weights, 49 taps from one patch
+    ('p2d_ragged_c64', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(64, 64, 3), BN(64), nn.ReLU(True)], (1, 64, 30, 52)),
+    ('p2d_batch2_c32_zero_pad', lambda: [nn.Conv2d(32, 64, 3, padding=1), BN(64), nn.ReLU(True)], (2, 32, 48, 72)),
+    ('p2d_bn64_resident_c128', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(128, 128, 3), BN(128), nn.ReLU(True)], (1, 128, 192, 512)),
+    ('p2d_stream_kc32_c256', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(256, 256, 3), BN(256), nn.ReLU(True)], (1, 256, 32, 64)),
+    ('p2d_c7_cin16_mt', lambda: NW._stem(16, 64, BN), (1, 16, 96, 256)),
+    ('p2d_resblock_instance_batch2', lambda: [NW.ResnetBlock(64, 'reflect', IN)], (2, 64, 32, 40)),
 ]
 
 

@@ -31,12 +31,13 @@ def test_abi_exports_every_declared_symbol():
 
 def _tap_table(desc, H, W, reuse):
     ia = lambda n: (C.c_int * n)()
-    ng, R, nph, par, mul = C.c_int(), C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    ng, nph, par, mul = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    R = ia(2)
     plane, dy, dx, tap0 = ia(64), ia(64), ia(64), ia(64)
     pb, oya, oxa, pads, ghw, ohw = ia(5), ia(4), ia(4), ia(4), ia(2), ia(2)
-    L.check(L.lib().v2v_conv_tap_table(C.byref(desc), H, W, int(reuse), C.byref(ng), C.byref(R), plane, dy, dx, tap0,
+    L.check(L.lib().v2v_conv_tap_table(C.byref(desc), H, W, int(reuse), C.byref(ng), R, plane, dy, dx, tap0,
                                        C.byref(nph), pb, oya, oxa, pads, C.byref(par), ghw, ohw, C.byref(mul)))
-    return dict(groups=[(plane[i], dy[i], dx[i], tap0[i]) for i in range(ng.value)], R=R.value,
+    return dict(groups=[(plane[i], dy[i], dx[i], tap0[i]) for i in range(ng.value)], R=R[0], RW=R[1],
                 phases=[(pb[i], pb[i + 1], oya[i], oxa[i]) for i in range(nph.value)], pads=list(pads), parity=par.value,
                 grid=tuple(ghw), out=tuple(ohw), mul=mul.value)
 
@@ -64,7 +65,8 @@ def _emulate(x, w, t, kh, kw, transposed, reflect):
         for (plane, dy, dx, tap0) in t['groups'][b:e]:
             for r in range(t['R']):
                 ky, kx = divmod(tap0 + r, kw)
-                a = planes[plane, :, dy:dy + gh, dx + r:dx + r + gw]
+                ry, rx = divmod(r, t['RW'])          # tap r reads the patch shifted by ry rows, rx columns
+                a = planes[plane, :, dy + ry:dy + ry + gh, dx + rx:dx + rx + gw]
                 wk = w[:, :, ky, kx].T if transposed else w[:, :, ky, kx]      # (Cout, Cin)
                 acc += np.einsum('oc,chw->ohw', wk, a)
         out[:, oya::t['mul'], oxa::t['mul']] = acc
@@ -76,6 +78,9 @@ def _emulate(x, w, t, kh, kw, transposed, reflect):
     (3, 1, 1, True, False, 0, 5, 130, True),     # row tiles: taps served from one patch (R = 3)
     (7, 1, 3, True, False, 0, 9, 140, True),     # R = 7
     (7, 1, 3, True, False, 0, 9, 140, False),
+    (3, 1, 1, True, False, 0, 32, 24, True),     # 16x8 tiles, one 18x10 patch serves all nine taps
+    (7, 1, 3, True, False, 0, 16, 16, True),     # 22x14 patch, 49 taps
+    (3, 1, 1, False, False, 0, 30, 17, True),    # 2-D patch with ragged edges
     (3, 2, 1, False, False, 0, 8, 12, True),
     (3, 2, 1, False, False, 0, 7, 9, True),      # odd extents
     (4, 2, 2, False, False, 0, 8, 10, True),     # discriminator
@@ -103,7 +108,8 @@ def test_tap_table_matches_torch_conv(kh, stride, pad, reflect, transposed, op, 
         ref = F.conv2d(xin, w, stride=stride, padding=0 if reflect else pad)
     assert tuple(ref.shape[2:]) == t['out']
     if reuse and not transposed and stride == 1 and W > 64 and kh > 1:
-        assert t['R'] == kh
+        assert t['R'] in (kh, kh * kh)                  # row tiles with horizontal reuse, or one 2-D patch for all taps
+        assert t['RW'] == kh
     out = _emulate(x[0].numpy(), w.numpy(), t, kh, kh, transposed, reflect)
     np.testing.assert_allclose(out, ref[0].numpy(), rtol=1e-10, atol=1e-10)
 

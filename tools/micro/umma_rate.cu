@@ -6,7 +6,8 @@
 #include "ptx.cuh"
 using namespace v2v;
 
-__global__ void __launch_bounds__(128, 1) k(int N, int iters, int commit_every, int kstep_bytes, long long* out) {
+// layout: 2 = SWIZZLE_128B (4 MMAs per 128-byte row), 4 = SWIZZLE_64B (2 per 64-byte row), 6 = SWIZZLE_32B (1 per row)
+__global__ void __launch_bounds__(128, 1) k(int N, int iters, int commit_every, int kstep_bytes, int layout, long long* out) {
   extern __shared__ uint8_t raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar[2];
@@ -28,9 +29,14 @@ __global__ void __launch_bounds__(128, 1) k(int N, int iters, int commit_every, 
     uint32_t ph = 0;
     for (int it = 0; it < iters; ++it) {
       if (elect_one_sync()) {
-        const uint64_t ad = make_kmajor_desc(a + (it & 1) * 16384, 1024, 2), bd = make_kmajor_desc(b + (it & 1) * 32768 / 2, 1024, 2);
+        const int rowb = layout == 2 ? 128 : (layout == 4 ? 64 : 32), per_row = rowb / 32;
+        const uint64_t ad = make_kmajor_desc(a + (it & 1) * 16384, 8 * rowb, layout), bd = make_kmajor_desc(b + (it & 1) * 32768 / 2, 8 * rowb, layout);
+        // 4 MMAs per iteration: per_row K sub-steps inside a row, then the next 128-row operand block
 #pragma unroll
-        for (int kq = 0; kq < 4; ++kq) umma_bf16(tm, ad + kq * (kstep_bytes >> 4), bd + kq * (kstep_bytes >> 4), idesc, 1u);
+        for (int kq = 0; kq < 4; ++kq) {
+          const uint64_t off = (uint64_t)(((kq % per_row) * kstep_bytes + (kq / per_row) * 128 * rowb) >> 4);
+          umma_bf16(tm, ad + off, bd + off, idesc, 1u);
+        }
         if (commit_every && (it % commit_every) == commit_every - 1) umma_commit(&bar[1]);
       }
       __syncwarp();
@@ -50,17 +56,18 @@ int main() {
   long long* d; cudaMalloc(&d, 8);
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
   const int iters = 2000;
-  for (int ce : {0, 1}) for (int ks : {32, 0}) for (int N : {16, 32, 64, 128, 256}) {
+  for (int layout : {2, 4, 6}) for (int ce : {0, 1}) for (int ks : {32, 0}) for (int N : {16, 32, 64, 128, 256}) {
+    if (layout != 2 && (ce == 1 || ks == 0)) continue;
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-    k<<<148, 128, 100 * 1024>>>(N, 10, ce, ks, d);     // warm
+    k<<<148, 128, 100 * 1024>>>(N, 10, ce, ks, layout, d);     // warm
     cudaEventRecord(e0);
-    k<<<148, 128, 100 * 1024>>>(N, iters, ce, ks, d);
+    k<<<148, 128, 100 * 1024>>>(N, iters, ce, ks, layout, d);
     cudaEventRecord(e1);
     cudaError_t e = cudaDeviceSynchronize();
     long long cyc; cudaMemcpy(&cyc, d, 8, cudaMemcpyDeviceToHost);
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     const double mmas = 4.0 * iters;
-    printf("N=%3d commit_every=%d kstep=%2dB: %7.1f cycles/MMA  (%6.1f ns/MMA by events)  -> %.0f TFLOP/s chip  %s\n", N, ce, ks, cyc / mmas,
+    printf("layout=%d N=%3d commit_every=%d kstep=%2dB: %7.1f cycles/MMA  (%6.1f ns/MMA by events)  -> %.0f TFLOP/s chip  %s\n", layout, N, ce, ks, cyc / mmas,
            ms * 1e6 / mmas, 148 * mmas * 2.0 * 128 * N * 16 / (ms * 1e-3) / 1e12, cudaGetErrorString(e));
   }
   return 0;

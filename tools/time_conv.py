@@ -12,6 +12,8 @@ SHAPES = {
     'c128_256x512': (lambda: [nn.ReflectionPad2d(1), nn.Conv2d(128, 128, 3), BN(128), nn.ReLU(True)], (1, 128, 256, 512)),
     'c64_512x1024': (lambda: [nn.ReflectionPad2d(1), nn.Conv2d(64, 64, 3), BN(64), nn.ReLU(True)], (1, 64, 512, 1024)),
     'stem108_32': (lambda: NW._stem(108, 32, BN), (1, 108, 1024, 2048)),
+    'head32_2048': (lambda: [nn.ReflectionPad2d(3), nn.Conv2d(32, 3, 7), nn.Tanh()], (1, 32, 1024, 2048)),
+    'up64_32': (lambda: [nn.ConvTranspose2d(64, 32, 3, stride=2, padding=1, output_padding=1), BN(32), nn.ReLU(True)], (1, 64, 512, 1024)),
     'c32_512x1024': (lambda: [nn.ReflectionPad2d(1), nn.Conv2d(32, 32, 3), BN(32), nn.ReLU(True)], (1, 32, 512, 1024)),
 }
 names = sys.argv[1:] or list(SHAPES)
@@ -28,5 +30,5 @@ for n in names:
             ms = [p[1] for p in prof if p[0] == 1]
             macs = [p[2] for p in prof if p[0] == 1]
             best = ms if best is None else [min(a, b) for a, b in zip(best, ms)]
-    print('%-14s dbg=%s mg=%s res=%s conv_ms=%s TF=%s' % (n, os.environ.get('V2V_DBG', '0'), os.environ.get('V2V_MG', '-'), os.environ.get('V2V_B_RESIDENT', '1'),
+    print('%-14s dbg=%s eg=%s res=%s conv_ms=%s TF=%s' % (n, os.environ.get('V2V_DBG', '0'), os.environ.get('V2V_EG', '-'), os.environ.get('V2V_B_RESIDENT', '1'),
           ['%.4f' % m for m in best], ['%.1f' % (2 * a / (m * 1e-3) / 1e12) for a, m in zip(macs, best)]), flush=True)

@@ -34,7 +34,7 @@ __global__ void conv_simt_kernel(ActDesc in, const bf16* __restrict__ w, int Kto
     for (int g = ph.group_begin; g < ph.group_end; ++g) {
       const ConvGroup grp = p.groups[g];
       for (int r = 0; r < p.R; ++r) {
-        const int yy = gy + grp.dy, xx = gx + grp.dx + r;
+        const int yy = gy + grp.dy + r / p.RW, xx = gx + grp.dx + r % p.RW;
         if (yy < 0 || yy >= in.Hp || xx < 0 || xx >= in.Wp) continue;   // TMA zero fill
         const bf16* a = in.base + ((((size_t)n * in.P + grp.plane) * in.Hp + yy) * in.Wp + xx) * in.C;
         const bf16* b = w + (size_t)co * Ktotal + (size_t)(grp.tap0 + r) * p.Cp;

@@ -16,7 +16,9 @@
 // One CTA per SM walks tiles t = blockIdx.x, += gridDim.x (M fastest, so co-running CTAs share weights in L2).
 //   warp 0        TMA producer (one elected lane)
 //   warp 1        tcgen05.mma issuer (whole warp loops, one elected lane issues) + TMEM owner
-//   warps 2..5    epilogue: tcgen05.ld the accumulator (2 TMEM stages, so tile i drains while tile i+1 accumulates)
+//   warps 2..     epilogue groups of 4 warps: tcgen05.ld the accumulator.  EG = 1: one group drains both TMEM stages;
+//                 EG = 2/3: group h owns stage h, so EG tiles drain concurrently while the next one accumulates (the
+//                 epilogue, with one warp per SM sub-partition, is latency bound and the critical path of small-K layers)
 //     EPI_RAW_STATS : bf16 NHWC raw output + per-tile per-channel (sum, sumsq) partials for the following
 //                     Batch/InstanceNorm (deterministic: no atomics)
 //     EPI_HEAD_F32  : bias + tanh/sigmoid/scale -> fp32 NCHW planes (the 7x7 image/flow/weight heads)
@@ -26,9 +28,11 @@
 
 namespace v2v {
 
-static constexpr int kThreads = 192;
+static constexpr int kMaxGroups = 2;                      // epilogue groups of 4 warps (one TMEM lane quarter each)
+static constexpr int kMaxThreads = 64 + 128 * kMaxGroups;
 static constexpr int kEpiThreads = 128;
-static constexpr int kRedFloats = 2 * 4 * 2 * 128 + 4 * 32 * 33;   // [parity][warp][sum|sumsq][col] + per-warp 32x33 transpose tiles
+// per epilogue group: [warp][sum|sumsq][128 columns] running column sums; per epilogue warp: a 32 x 17 transpose tile
+static constexpr int kRedFloatsPerGroup = 4 * 2 * 128 + 4 * 32 * 17;
 
 // V2V_DBG bit2: CTA 0 records clock64() at role events of its first 24 work units and prints them at exit
 __device__ long long g_trace[3][24][8];
@@ -89,7 +93,96 @@ __device__ __forceinline__ TileXY tile_xy(const ConvKernelParams& p, int m) {
   return t;
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+
+struct MmaCtx {
+  uint8_t* sG; uint8_t* sBres;
+  uint64_t *g_full, *g_empty, *bres_full, *bres_empty, *tmem_full, *tmem_empty;
+  uint32_t tmem_base, acc_cols;
+  int group_bytes, b_tx, NS, t_first, t_step;
+};
+
+// The tcgen05.mma issue loop.  kWarpWide = false: called by ONE elected lane, which runs the whole loop (no re-election
+// or warp synchronisation on the issue path; descriptors live in vector registers and are moved to uniform registers
+// per MMA).  kWarpWide = true: all 32 lanes walk the loop in lock step, so ptxas can keep the descriptor arithmetic on
+// the uniform datapath, and elect.sync guards each group of MMAs / each commit.
+template <bool kWarpWide>
+__device__ __forceinline__ void mma_role(const ConvKernelParams& p, const MmaCtx& cx) {
+  const uint32_t idesc = make_idesc_bf16(128, p.BN);
+  int gs = 0, it = 0, as = 0;
+  uint32_t gpar = 0, gen = 0, aphase = 0;
+  int prev_key = -1;
+  const uint32_t a_step = (uint32_t)(p.row_bytes >> 4), b_step = (uint32_t)(cx.b_tx >> 4);
+  const uint32_t a_wrap = (uint32_t)(((p.PW - p.RW) * p.row_bytes) >> 4);     // to the next patch row
+  const uint32_t sBres_u32 = smem_u32(cx.sBres);
+  // descriptors differ only in the 14-bit (address >> 4) field of the low word
+  const uint32_t a_hi = (uint32_t)(make_kmajor_desc(0, p.sbo_a_bytes, p.layout_type) >> 32);
+  const uint32_t b_hi = (uint32_t)(make_kmajor_desc(0, p.sbo_bytes, p.layout_type) >> 32);
+  const uint32_t a_lo0 = (uint32_t)make_kmajor_desc(0, p.sbo_a_bytes, p.layout_type);
+  const uint32_t b_lo0 = (uint32_t)make_kmajor_desc(0, p.sbo_bytes, p.layout_type);
+  for (int u = cx.t_first; u < p.total_units; u += cx.t_step, ++it) {
+    const Unit un = decode_unit(p, u);
+    const ConvPhase ph = p.phases[un.phase];
+    const bool first_of_key = un.key != prev_key;
+    if (p.b_resident && first_of_key && prev_key >= 0) gen ^= 1;
+    prev_key = un.key;
+    const int u_next = u + cx.t_step;
+    const bool last_of_key = (u_next >= p.total_units) || (u_next / p.mg_total != un.key);
+    const int nsteps = (ph.group_end - ph.group_begin) * p.cblocks;
+    TRACE(1, it, 0);
+    mbar_wait(&cx.tmem_empty[as], aphase ^ 1);        // the epilogue has drained this accumulator stage
+    if (p.b_resident && first_of_key) mbar_wait(cx.bres_full, gen);
+    tcgen05_fence_after();
+    TRACE(1, it, 1);
+    const uint32_t tmem_d = cx.tmem_base + as * cx.acc_cols;
+    uint32_t first = 0;
+    for (int s0 = 0; s0 < nsteps; s0 += p.CG) {
+      const int n = min(p.CG, nsteps - s0);
+      mbar_wait(&cx.g_full[gs], gpar);
+      tcgen05_fence_after();
+      if (s0 == 0) TRACE(1, it, 2);
+      const uint32_t base = smem_u32(cx.sG + (size_t)gs * cx.group_bytes);
+      for (int i = 0; i < n; ++i) {
+        const uint32_t a_base = base + i * p.a_slot_bytes;
+        const uint32_t b_base = p.b_resident ? sBres_u32 + (s0 + i) * p.b_slot_bytes
+                                             : base + p.CG * p.a_slot_bytes + i * p.b_slot_bytes;
+        uint32_t al = a_lo0 + ((a_base & 0x3FFFF) >> 4), bl = b_lo0 + ((b_base & 0x3FFFF) >> 4);
+        // tap r reads the patch shifted by (r / RW) patch rows and (r % RW) pixels; K = 16 bf16 = 32 bytes per MMA,
+        // kc/16 MMAs per smem row (fixed trip counts keep the issue loop tight)
+        for (int r0 = 0; r0 < p.R; r0 += p.RW, al += a_wrap) {
+          for (int r = 0; r < p.RW; ++r, al += a_step, bl += b_step) {
+            if (kWarpWide ? elect_one_sync() : true) {
+              const uint64_t ad = ((uint64_t)a_hi << 32) | al, bd = ((uint64_t)b_hi << 32) | bl;
+              if (p.kmma == 4) {
+                umma_bf16(tmem_d, ad, bd, idesc, first);
+                umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
+                umma_bf16(tmem_d, ad + 4, bd + 4, idesc, 1u);
+                umma_bf16(tmem_d, ad + 6, bd + 6, idesc, 1u);
+              } else if (p.kmma == 2) {
+                umma_bf16(tmem_d, ad, bd, idesc, first);
+                umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
+              } else {
+                umma_bf16(tmem_d, ad, bd, idesc, first);
+              }
+            }
+            first = 1u;
+          }
+        }
+      }
+      if (kWarpWide ? elect_one_sync() : true) {
+        umma_commit(&cx.g_empty[gs]);                   // the whole group slot is free when these MMAs retire
+        if (s0 + n >= nsteps) {
+          if (p.b_resident && last_of_key) umma_commit(cx.bres_empty);
+          umma_commit(&cx.tmem_full[as]);               // accumulator complete
+        }
+      }
+      if (++gs == p.SG) { gs = 0; gpar ^= 1; }
+    }
+    TRACE(1, it, 3);
+    if (++as == cx.NS) { as = 0; aphase ^= 1; }
+  }
+}
+
+__global__ void __launch_bounds__(kMaxThreads, 1)
 conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ ConvKernelParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -100,26 +193,27 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sG = smem;
   uint8_t* sBres = sG + (size_t)p.SG * group_bytes;
   float* red = reinterpret_cast<float*>(sBres + (p.b_resident ? (size_t)p.SB * p.b_slot_bytes : 0));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red + kRedFloats);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red + p.EG * kRedFloatsPerGroup);
   uint64_t* g_full = bars;
   uint64_t* g_empty = g_full + p.SG;
   uint64_t* bres_full = g_empty + p.SG;
   uint64_t* bres_empty = bres_full + 1;
-  uint64_t* tmem_full = bres_empty + 1;     // [2]
-  uint64_t* tmem_empty = tmem_full + 2;     // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* tmem_full = bres_empty + 1;     // [kMaxGroups]
+  uint64_t* tmem_empty = tmem_full + kMaxGroups;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kMaxGroups);
+  const int NS = p.EG > 1 ? p.EG : 2;       // accumulator stages in TMEM
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t acc_cols = p.BN < 32 ? 32 : p.BN;     // columns per accumulator stage
   uint32_t tmem_cols = 32;
-  while (tmem_cols < 2 * p.MG * acc_cols) tmem_cols <<= 1;
+  while (tmem_cols < NS * p.MG * acc_cols) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < p.SG; ++i) { mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 1); }
     mbar_init(bres_full, 1); mbar_init(bres_empty, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -131,7 +225,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int a_tx = (p.TW + p.R - 1) * p.TH * p.row_bytes;
+  const int a_tx = p.PW * p.PH * p.row_bytes;
   const int b_tx = p.BN * p.row_bytes;
   const int t_first = blockIdx.x, t_step = gridDim.x;
 
@@ -186,133 +280,97 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer: one elected lane runs the whole loop
-    // (entered through elect.sync, so ptxas keeps UTCHMMA / UTCBAR on the uniform datapath; no per-group re-election
-    // or __syncwarp on the issue path)
-    if (elect_one_sync()) {
-      const uint32_t idesc = make_idesc_bf16(128, p.BN);
-      int gs = 0, it = 0;
-      uint32_t gpar = 0, gen = 0;
-      int prev_key = -1;
-      const uint64_t a_step = (uint64_t)(p.row_bytes >> 4), b_step = (uint64_t)(b_tx >> 4);
-      const uint32_t sBres_u32 = smem_u32(sBres);
-      for (int u = t_first; u < p.total_units; u += t_step, ++it) {
-        const Unit un = decode_unit(p, u);
-        const ConvPhase ph = p.phases[un.phase];
-        const bool first_of_key = un.key != prev_key;
-        if (p.b_resident && first_of_key && prev_key >= 0) gen ^= 1;
-        prev_key = un.key;
-        const int u_next = u + t_step;
-        const bool last_of_key = (u_next >= p.total_units) || (u_next / p.mg_total != un.key);
-        const int nsteps = (ph.group_end - ph.group_begin) * p.cblocks;
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        TRACE(1, it, 0);
-        mbar_wait(&tmem_empty[as], aphase ^ 1);        // the epilogue has drained this accumulator stage
-        if (p.b_resident && first_of_key) mbar_wait(bres_full, gen);
-        tcgen05_fence_after();
-        TRACE(1, it, 1);
-        const uint32_t tmem_d = tmem_base + as * acc_cols;
-        uint32_t first = 0;
-        for (int s0 = 0; s0 < nsteps; s0 += p.CG) {
-          const int n = min(p.CG, nsteps - s0);
-          mbar_wait(&g_full[gs], gpar);
-          tcgen05_fence_after();
-          if (s0 == 0) TRACE(1, it, 2);
-          const uint32_t base = smem_u32(sG + (size_t)gs * group_bytes);
-          for (int i = 0; i < n; ++i) {
-            const uint32_t a_base = base + i * p.a_slot_bytes;
-            const uint32_t b_base = p.b_resident ? sBres_u32 + (s0 + i) * p.b_slot_bytes
-                                                 : base + p.CG * p.a_slot_bytes + i * p.b_slot_bytes;
-            // descriptors differ only in the 14-bit (address >> 4) field: build once per step, then add
-            uint64_t ad = make_kmajor_desc(a_base, p.sbo_bytes, p.layout_type);
-            uint64_t bd = make_kmajor_desc(b_base, p.sbo_bytes, p.layout_type);
-            // K = 16 bf16 = 32 bytes per MMA; kc/16 MMAs per smem row (fixed trip counts keep the issue loop tight)
-            if (p.kmma == 4) {
-              for (int r = 0; r < p.R; ++r, ad += a_step, bd += b_step) {
-                umma_bf16(tmem_d, ad, bd, idesc, first);
-                umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
-                umma_bf16(tmem_d, ad + 4, bd + 4, idesc, 1u);
-                umma_bf16(tmem_d, ad + 6, bd + 6, idesc, 1u);
-                first = 1u;
-              }
-            } else if (p.kmma == 2) {
-              for (int r = 0; r < p.R; ++r, ad += a_step, bd += b_step) {
-                umma_bf16(tmem_d, ad, bd, idesc, first);
-                umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
-                first = 1u;
-              }
-            } else {
-              for (int r = 0; r < p.R; ++r, ad += a_step, bd += b_step) {
-                umma_bf16(tmem_d, ad, bd, idesc, first);
-                first = 1u;
-              }
-            }
-          }
-          umma_commit(&g_empty[gs]);                   // the whole group slot is free when these MMAs retire
-          if (s0 + n >= nsteps) {
-            if (p.b_resident && last_of_key) umma_commit(bres_empty);
-            umma_commit(&tmem_full[as]);               // accumulator complete
-          }
-          if (++gs == p.SG) { gs = 0; gpar ^= 1; }
-        }
-        TRACE(1, it, 3);
-      }
+    // ------------------------------------------------------------ MMA issuer
+    MmaCtx cx{sG, sBres, g_full, g_empty, bres_full, bres_empty, tmem_full, tmem_empty, tmem_base, acc_cols,
+              group_bytes, b_tx, NS, t_first, t_step};
+    if (p.dbg & 8) {
+      mma_role<true>(p, cx);                   // whole warp walks the loop (uniform datapath), elect.sync per MMA group
+    } else if (elect_one_sync()) {
+      mma_role<false>(p, cx);                  // one elected lane runs the whole loop
     }
   } else {
     // ------------------------------------------------------------ epilogue warps (TMEM lane quarter = warp % 4)
     const int q = warp & 3;
+    const int eg = (warp - 2) >> 2;                       // epilogue group
     const int etid = q * 32 + lane;
-    int it = 0;
-    // per-CTA running (sum, sumsq) of column n0 + etid; flushed when (phase, N tile, image) changes: one partial
-    // row per (phase, image, CTA) instead of one per tile keeps the finalize pass tiny
-    float s_acc = 0.f, q_acc = 0.f;
+    // running (sum, sumsq) of this warp's rows, per column of the current N tile, in shared memory; the group's four
+    // warps are combined and flushed to the (phase, image, CTA) partial row only when (phase, N tile, image) changes.
+    // Every partial row element receives at most one addend per group onto a zeroed row, and EG <= 2 when statistics
+    // are on, so the atomic adds are order independent (deterministic).
+    float* racc = red + eg * (4 * 2 * 128);
+    float* tt = red + p.EG * (4 * 2 * 128) + (eg * 4 + q) * (32 * 17);
+    const bool do_stats = (p.epi == EPI_RAW_STATS) && (p.stats != nullptr) && !(p.dbg & 1);
     int acc_key = -1, acc_img = -1, acc_n0 = 0, acc_phase = 0;
-    int red_it = 0;
-    for (int u = t_first; u < p.total_units; u += t_step, ++it) {
+    const int nchunks = p.BN / 32;
+    auto flush = [&]() {
+      named_bar_sync(1 + eg, kEpiThreads);                // all four warps have added their last tile
+      if (etid < p.BN && acc_n0 + etid < p.stats_C) {
+        float s = 0.f, qq = 0.f;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+          s += racc[(w * 2 + 0) * 128 + etid];
+          qq += racc[(w * 2 + 1) * 128 + etid];
+        }
+        const size_t rowi = ((size_t)acc_phase * p.N + acc_img) * gridDim.x + blockIdx.x;
+        atomicAdd(&p.stats[(rowi * 2 + 0) * p.stats_C + acc_n0 + etid], s);
+        atomicAdd(&p.stats[(rowi * 2 + 1) * p.stats_C + acc_n0 + etid], qq);
+      }
+      named_bar_sync(1 + eg, kEpiThreads);                // racc may be cleared again
+    };
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int u = t_first, it = 0; u < p.total_units; u += t_step, ++it) {
+      const int my_as = as;
+      const uint32_t my_phase = aphase;
+      if (++as == NS) { as = 0; aphase ^= 1; }
+      if (p.EG > 1 && my_as != eg) continue;              // stage h belongs to group h
       const Unit un = decode_unit(p, u);
       const ConvPhase ph = p.phases[un.phase];
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
       if (q == 0) TRACE(2, it, 0);
-      mbar_wait(&tmem_full[as], aphase);
+      mbar_wait(&tmem_full[my_as], my_phase);
       tcgen05_fence_after();
       if (q == 0) TRACE(2, it, 1);
-     for (int jt = 0; jt < un.count; ++jt, ++red_it) {
-      const TileXY txy = tile_xy(p, un.m_first + jt);
-      const bool last_tile = (jt == un.count - 1);
-      const int row = q * 32 + lane;
-      const int ry = row / p.TW, rx = row - ry * p.TW;
-      const int gy = txy.y0 + ry, gx = txy.x0 + rx;
-      const bool valid = (gy < p.grid_h) && (gx < p.grid_w);
-      const int oy = gy * p.oy_mul + ph.oy_add, ox = gx * p.ox_mul + ph.ox_add;
-      const uint32_t taddr = tmem_base + (as * p.MG + jt) * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
-      const int n0 = un.n0, n_img = txy.n_img;
+      for (int jt = 0; jt < un.count; ++jt) {
+        const TileXY txy = tile_xy(p, un.m_first + jt);
+        const bool last_tile = (jt == un.count - 1);
+        const int row = q * 32 + lane;
+        const int ry = row / p.TW, rx = row - ry * p.TW;
+        const int gy = txy.y0 + ry, gx = txy.x0 + rx;
+        const bool valid = (gy < p.grid_h) && (gx < p.grid_w);
+        const int oy = gy * p.oy_mul + ph.oy_add, ox = gx * p.ox_mul + ph.ox_add;
+        const uint32_t taddr = tmem_base + (my_as * p.MG + jt) * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
+        const int n0 = un.n0, n_img = txy.n_img;
 
-      if (p.epi == EPI_HEAD_F32) {
-        uint32_t r[16];
-        tmem_ld_32x32b_x16(taddr, r);
-        tmem_ld_wait();
-        if (last_tile) {
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[as]);
-        }
-        if (valid) {
-          const size_t pix = (size_t)oy * p.out_W + ox;
+        if (p.epi == EPI_HEAD_F32) {
+          uint32_t r[16];
+          tmem_ld_32x32b_x16(taddr, r);
+          tmem_ld_wait();
+          if (last_tile) {
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[my_as]);
+          }
+          if (valid) {
+            const size_t pix = (size_t)oy * p.out_W + ox;
 #pragma unroll
-          for (int j = 0; j < V2V_MAX_HEAD; ++j) {
-            if (j < p.Cout) {
-              float v = __uint_as_float(r[j]);
-              if (p.bias) v += (p.bias2 && j >= p.Cout1) ? __ldg(p.bias2 + j - p.Cout1) : __ldg(p.bias + j);
-              v = apply_act(v, p.head_act[j], p.lrelu_slope) * p.head_scale[j];
-              reinterpret_cast<float*>(p.io[p.head_slot[j]])[p.head_off[j] + (size_t)n_img * p.head_bstride[j] + pix] = v;
+            for (int j = 0; j < V2V_MAX_HEAD; ++j) {
+              if (j < p.Cout) {
+                float v = __uint_as_float(r[j]);
+                if (p.bias) v += (p.bias2 && j >= p.Cout1) ? __ldg(p.bias2 + j - p.Cout1) : __ldg(p.bias + j);
+                v = apply_act(v, p.head_act[j], p.lrelu_slope) * p.head_scale[j];
+                reinterpret_cast<float*>(p.io[p.head_slot[j]])[p.head_off[j] + (size_t)n_img * p.head_bstride[j] + pix] = v;
+              }
             }
           }
+          continue;
         }
-      } else {
-        float* redp = red + (red_it & 1) * (4 * 2 * 128);
-        const bool do_stats = (p.epi == EPI_RAW_STATS) && (p.stats != nullptr) && !(p.dbg & 1);
+
+        if (do_stats && (un.key != acc_key || n_img != acc_img)) {
+          if (acc_key >= 0) flush();
+          for (int c = lane; c < 2 * 128; c += 32) racc[q * 256 + c] = 0.f;
+          __syncwarp();
+          acc_key = un.key; acc_img = n_img; acc_n0 = n0; acc_phase = un.phase;
+        }
         bf16* dst = nullptr;
         if (valid) {
           if (p.epi == EPI_RAW_STATS)
@@ -320,7 +378,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           else
             dst = p.out_act.base + p.out_act.offset(n_img, oy, ox);
         }
-        const int nchunks = p.BN / 32;
         for (int c = 0; c < nchunks; ++c) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c * 32, r);
@@ -329,7 +386,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (last_tile && c == nchunks - 1) {    // accumulators fully read: hand the TMEM stage back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[as]);
+            if (lane == 0) mbar_arrive(&tmem_empty[my_as]);
           }
           float v[32];
           const int col0 = n0 + c * 32;
@@ -357,55 +414,38 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (q == 0 && c == nchunks - 1) TRACE(2, it, 4);
           if (do_stats) {
-            // column sums over this warp's 32 rows through a padded shared-memory transpose: 32 STS + 32 LDS per
-            // thread, conflict free, instead of two 31-step shuffle butterflies (the epilogue is the critical path of
-            // the small-K layers)
-            float* tt = red + 2 * 4 * 2 * 128 + q * (32 * 33);
-            __syncwarp();
+            // column sums over this warp's 32 rows through a padded shared-memory transpose, 16 columns per pass:
+            // lane = row stores 16 values (stride 17: conflict free); lane l then walks column l % 16 over rows
+            // 16 * (l / 16) .. +15 (banks 17 r + 16 (l / 16) + l % 16: conflict free) and one xor-16 shuffle joins
+            // the two half sums.  Lanes 0-15 keep the first pass, lanes 16-31 the second: lane l owns column l.
+            float s_keep = 0.f, q_keep = 0.f;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) tt[lane * 33 + j] = v[j];
-            __syncwarp();
-            float s = 0.f, qq = 0.f;
+            for (int h2 = 0; h2 < 2; ++h2) {
+              __syncwarp();
 #pragma unroll
-            for (int r2 = 0; r2 < 32; ++r2) {
-              const float x = tt[r2 * 33 + lane];
-              s += x;
-              qq = fmaf(x, x, qq);
+              for (int j = 0; j < 16; ++j) tt[lane * 17 + j] = v[h2 * 16 + j];
+              __syncwarp();
+              float s = 0.f, qq = 0.f;
+              const float* colp = tt + (lane >> 4) * (16 * 17) + (lane & 15);
+#pragma unroll
+              for (int r2 = 0; r2 < 16; ++r2) {
+                const float x = colp[r2 * 17];
+                s += x;
+                qq = fmaf(x, x, qq);
+              }
+              s += __shfl_xor_sync(0xffffffffu, s, 16);
+              qq += __shfl_xor_sync(0xffffffffu, qq, 16);
+              if ((lane >> 4) == h2) { s_keep = s; q_keep = qq; }
             }
-            redp[(q * 2 + 0) * 128 + c * 32 + lane] = s;
-            redp[(q * 2 + 1) * 128 + c * 32 + lane] = qq;
+            racc[(q * 2 + 0) * 128 + c * 32 + lane] += s_keep;
+            racc[(q * 2 + 1) * 128 + c * 32 + lane] += q_keep;
           }
         }
         if (q == 0) TRACE(2, it, 5);
-        if (do_stats) {
-          named_bar_sync(1, kEpiThreads);        // the four epilogue warps only
-          if (q == 0) TRACE(2, it, 6);
-          if (etid < p.BN) {
-            if (un.key != acc_key || n_img != acc_img) {
-              if (acc_key >= 0 && acc_n0 + etid < p.stats_C) {
-                const size_t rowi = ((size_t)acc_phase * p.N + acc_img) * gridDim.x + blockIdx.x;
-                p.stats[(rowi * 2 + 0) * p.stats_C + acc_n0 + etid] = s_acc;
-                p.stats[(rowi * 2 + 1) * p.stats_C + acc_n0 + etid] = q_acc;
-              }
-              s_acc = q_acc = 0.f;
-              acc_key = un.key; acc_img = n_img; acc_n0 = n0; acc_phase = un.phase;
-            }
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-              s_acc += redp[(w * 2 + 0) * 128 + etid];
-              q_acc += redp[(w * 2 + 1) * 128 + etid];
-            }
-          }
-        }
-      }
-     }   // tiles of the unit
+      }   // tiles of the unit
       if (q == 0) TRACE(2, it, 2);
     }
-    if (acc_key >= 0 && etid < p.BN && acc_n0 + etid < p.stats_C) {
-      const size_t rowi = ((size_t)acc_phase * p.N + acc_img) * gridDim.x + blockIdx.x;
-      p.stats[(rowi * 2 + 0) * p.stats_C + acc_n0 + etid] = s_acc;
-      p.stats[(rowi * 2 + 1) * p.stats_C + acc_n0 + etid] = q_acc;
-    }
+    if (do_stats && acc_key >= 0) flush();
   }
 
   tcgen05_fence_before();
@@ -436,15 +476,15 @@ int device_sm_count() {
 cudaError_t launch_conv_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p,
                              cudaStream_t stream) {
   const size_t smem = (size_t)p.SG * p.CG * (p.a_slot_bytes + (p.b_resident ? 0 : p.b_slot_bytes)) +
-                      (p.b_resident ? (size_t)p.SB * p.b_slot_bytes : 0) + 1024 /*align*/ + kRedFloats * sizeof(float) +
-                      (2 * p.SG + 2 + 4 + 2) * sizeof(uint64_t);
+                      (p.b_resident ? (size_t)p.SB * p.b_slot_bytes : 0) + 1024 /*align*/ + (size_t)p.EG * kRedFloatsPerGroup * sizeof(float) +
+                      (2 * p.SG + 2 + 2 * kMaxGroups + 2) * sizeof(uint64_t);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  conv_umma_kernel<<<p.grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  conv_umma_kernel<<<p.grid, 64 + 128 * p.EG, smem, stream>>>(tmA, tmB, p);
   return cudaGetLastError();
 }
 

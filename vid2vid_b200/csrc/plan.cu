@@ -59,12 +59,58 @@ struct ConvGeom {
   int out_h, out_w;       // conv output extent
   int mul;                // output coord = grid coord * mul + phase add
   int TH, TW, R;
+  int RW;                 // taps per patch row: tap r of a group reads the patch shifted by (r / RW) rows, (r % RW) columns
+  int patch2d_kc;         // > 0: 16x8 pixel tiles, ONE activation patch of (16+kh-1) x (8+kw-1) pixels serves all kh*kw taps;
+  int patch2d_bn;         //      K block / N tile / weight residency chosen together with the geometry (they decide the fit)
+  int patch2d_resident;
   int n_groups, n_phases;
   ConvGroup groups[V2V_MAX_TAPS];
   ConvPhase phases[V2V_MAX_PHASES];
 };
 
-static int conv_geometry(const v2v_conv_desc& c, int H, int W, bool allow_reuse, ConvGeom* g) {
+
+static inline int round_up_i(int a, int b) { return round_up(a, b); }
+static const int kSmemBudget = 196 * 1024;      // operand slots + resident weights (epilogue scratch and barriers excluded)
+static const int kResidentMax = 150 * 1024;
+
+// 2-D patch mode (stride-1 filters): a tile of 16 rows x 8 pixels makes every 8-row core-matrix group of the A operand
+// one tile row, so the operand of tap (ky, kx) is the SAME shared-memory patch of (16+kh-1) x (8+kw-1) pixels read with
+// start address advanced by (ky * PW + kx) rows and a group stride (SBO) of PW rows.  Each input pixel is then fetched
+// ~1.4x (3x3) instead of 3x (row tiles with horizontal reuse) or 9x (one box per tap).  Feasible when a step's weights
+// (all taps of one K block) fit next to the patch, double buffered, or the whole (phase, N tile) weight set stays resident.
+static bool choose_patch2d(const v2v_conv_desc& c, bool head, int N, int grid_h, int grid_w, int* kc_out, int* bn_out, int* res_out) {
+  const char* e = getenv("V2V_PATCH2D");
+  if (e && e[0] == '0') return false;
+  if (c.transposed || c.stride != 1 || c.kh * c.kw == 1 || grid_w < 8) return false;
+  const long long tiles = (long long)((grid_w + 7) / 8) * ((grid_h + 15) / 16);
+  if (tiles * 128 * 4 > (long long)grid_h * grid_w * 5) return false;          // > 25 % masked rows: keep row tiles
+  const int Cp = pad_channels(c.Cin), taps = c.kh * c.kw, PH = 16 + c.kh - 1, PW = 8 + c.kw - 1;
+  const int bn0 = head ? 16 : std::min(128, round_up_i(c.Cout, 32));
+  const long long m_total = tiles * N;
+  const int sms = device_sm_count();
+  const int kc_max = std::min(Cp, 64);
+  // (1) resident weights with the natural N tile, (2) with a halved N tile when a CTA walks >= 4 M tiles (streaming the
+  // weights again for every tile costs more L2 traffic than the second pass over the activations)
+  for (int pass = 0; pass < 2; ++pass) {
+    const int bn = pass == 0 ? bn0 : bn0 / 2;
+    if (pass == 1 && (bn0 < 128 || m_total < 4LL * sms)) break;
+    if (m_total <= sms) break;
+    const long long res_bytes = (long long)(Cp / kc_max) * round_up_i(taps * bn * kc_max * 2, 1024);
+    const int patch = round_up_i(PH * PW * kc_max * 2, 1024);
+    if (res_bytes <= kResidentMax && kSmemBudget - res_bytes >= 2 * patch) {
+      *kc_out = kc_max; *bn_out = bn; *res_out = 1;
+      return true;
+    }
+  }
+  for (int kc = kc_max; kc >= 16; kc >>= 1) {
+    if (Cp % kc) continue;
+    const int patch = round_up_i(PH * PW * kc * 2, 1024), bstep = round_up_i(taps * bn0 * kc * 2, 1024);
+    if (2 * (patch + bstep) <= kSmemBudget) { *kc_out = kc; *bn_out = bn0; *res_out = 0; return true; }
+  }
+  return false;
+}
+
+static int conv_geometry(const v2v_conv_desc& c, bool head, int N, int H, int W, bool allow_reuse, ConvGeom* g) {
   memset(g, 0, sizeof(*g));
   V2V_REQUIRE(c.kh >= 1 && c.kw >= 1 && c.kh * c.kw <= V2V_MAX_TAPS, V2V_ERR_UNSUPPORTED, "kernel %dx%d unsupported",
               c.kh, c.kw);
@@ -89,7 +135,13 @@ static int conv_geometry(const v2v_conv_desc& c, int H, int W, bool allow_reuse,
   g->TH = 128 / g->TW;
   g->R = 1;
   int ng = 0;
-  if (!c.transposed && c.stride == 1) {
+  if (allow_reuse && choose_patch2d(c, head, N, g->grid_h, g->grid_w, &g->patch2d_kc, &g->patch2d_bn, &g->patch2d_resident)) {
+    g->n_phases = 1;
+    g->TH = 16; g->TW = 8;
+    g->R = c.kh * c.kw; g->RW = c.kw;
+    g->groups[ng++] = ConvGroup{0, 0, 0, 0, 0, 0};
+    g->phases[0] = ConvPhase{0, ng, 0, 0};
+  } else if (!c.transposed && c.stride == 1) {
     g->n_phases = 1;
     if (allow_reuse && g->TH == 1 && c.kw > 1) {
       g->R = c.kw;
@@ -132,6 +184,7 @@ static int conv_geometry(const v2v_conv_desc& c, int H, int W, bool allow_reuse,
       }
   }
   g->n_groups = ng;
+  if (!g->patch2d_kc) g->RW = g->R;
   return 0;
 }
 
@@ -301,7 +354,7 @@ static int lower(v2v_plan* P) {
   for (auto& op : P->gops) {
     if (op.kind == G_CONV || op.kind == G_CONV_ACT || op.kind == G_HEAD) {
       Value& vin = P->values[op.value_in];
-      int rc = conv_geometry(op.conv, vin.H, vin.W, P->allow_reuse, &op.geom);
+      int rc = conv_geometry(op.conv, op.kind == G_HEAD, vin.N, vin.H, vin.W, P->allow_reuse, &op.geom);
       if (rc) return rc;
       op.req_index = add_req(vin, conv_req(op.conv, op.geom));
       const v2v_conv_desc& c = op.conv;
@@ -338,15 +391,30 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   kp.Cout = op.conv.Cout;
   kp.BN = op.kind == G_HEAD ? 16 : std::min(128, round_up(op.conv.Cout, 32));
   kp.Cp = pad_channels(op.conv.Cin);
-  kp.kc = std::min(kp.Cp, 64); kp.cblocks = kp.Cp / kp.kc;
-  kp.row_bytes = kp.kc * 2; kp.kmma = kp.kc / 16; kp.sbo_bytes = 8 * kp.row_bytes;
+  kp.kc = std::min(kp.Cp, 64);
+  const bool p2d = g.patch2d_kc > 0;
+  if (p2d) { kp.kc = g.patch2d_kc; if (op.kind != G_HEAD) kp.BN = g.patch2d_bn; }
+  kp.cblocks = kp.Cp / kp.kc;
+  kp.row_bytes = kp.kc * 2; kp.kmma = kp.kc / 16;
   kp.layout_type = kp.kc == 64 ? 2 : (kp.kc == 32 ? 4 : 6);
-  kp.R = g.R;
-  kp.a_slot_bytes = round_up((g.TW + g.R - 1) * g.TH * kp.row_bytes, 1024);
-  // shared-memory budget: 227 KB - epilogue scratch (24.5 KB) - alignment slack - barriers
-  const int budget = 196 * 1024;
+  kp.R = g.R; kp.RW = g.RW;
+  // patch extent in pixels; 8-row core-matrix groups of the A operand are SBO bytes apart: the canonical 8 rows for
+  // row tiles, one patch row (PW pixels) in 2-D patch mode
+  kp.PW = p2d ? g.TW + op.conv.kw - 1 : g.TW + g.R - 1;
+  kp.PH = p2d ? g.TH + op.conv.kh - 1 : g.TH;
+  kp.sbo_bytes = 8 * kp.row_bytes;
+  kp.sbo_a_bytes = p2d ? kp.PW * kp.row_bytes : 8 * kp.row_bytes;
+  kp.a_slot_bytes = round_up(kp.PW * kp.PH * kp.row_bytes, 1024);
+  // Epilogue groups: layers whose K loop is shorter than the epilogue of a tile (small Cin * taps) are epilogue bound
+  // with one group; statistics allow at most 2 groups (order-independent atomic adds need <= 2 addends per element).
+  {
+    const char* eg = getenv("V2V_EG");
+    kp.EG = eg ? std::max(1, std::min(2, atoi(eg))) : 2;
+  }
+  // shared-memory budget: 227 KB - epilogue scratch (12.5 KB per group) - alignment slack - barriers
+  const int budget = kSmemBudget;
   // a weight slot holds the R taps served by one activation patch; keep >= 2 slots + 3 patches in the budget
-  while (g.R > 1 && kp.BN > 32 && 2 * g.R * kp.BN * kp.row_bytes + 3 * kp.a_slot_bytes > budget) kp.BN /= 2;
+  while (!p2d && g.R > 1 && kp.BN > 32 && 2 * g.R * kp.BN * kp.row_bytes + 3 * kp.a_slot_bytes > budget) kp.BN /= 2;
   kp.b_slot_bytes = round_up(g.R * kp.BN * kp.row_bytes, 1024);
   kp.n_tiles = (kp.Cout + kp.BN - 1) / kp.BN;
   kp.m_total = kp.N * kp.tiles_x * kp.tiles_y;
@@ -360,8 +428,11 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   // resident weights pay off when a CTA walks several M tiles with the same weights
   const bool many_m = kp.m_total > sms;
   kp.MG = 1;
-  kp.b_resident = (allow_res && many_m && (long long)nB * kp.b_slot_bytes <= 150 * 1024 &&
+  kp.b_resident = (allow_res && many_m && (long long)nB * kp.b_slot_bytes <= kResidentMax &&
                    budget - nB * kp.b_slot_bytes >= 2 * kp.a_slot_bytes) ? 1 : 0;
+  if (p2d && !kp.b_resident && 2 * (kp.a_slot_bytes + kp.b_slot_bytes) > budget) {
+    set_error("internal: 2-D patch conv does not fit (a %d b %d)", kp.a_slot_bytes, kp.b_slot_bytes);
+  }
   kp.SB = kp.b_resident ? nB : 0;
   // Commit groups.  Measured on B200: every tcgen05.commit / barrier round trip costs the issuing warp ~500 cycles
   // during which the tensor pipe idles (its queue is shallow), so CG consecutive K-loop steps share one barrier pair;
@@ -413,6 +484,10 @@ static int pack_one(const GOp& op, cudaStream_t stream) {
 }
 
 static int run_xop(v2v_plan* P, const XOp& x, cudaStream_t s) {
+  // V2V_SKIP (timing experiments only, results are wrong): bit mask of XOp kinds left out of the frame, to measure what
+  // each kind costs inside the captured graph (CUDA events around single launches over-state tiny kernels)
+  static const int skip = [] { const char* e = getenv("V2V_SKIP"); return e ? atoi(e) : 0; }();
+  if (skip & (1 << (int)x.kind)) return 0;
   switch (x.kind) {
     case X_IMPORT: V2V_CUDA(launch_import_nchw(x.imp, s)); break;
     case X_EXPORT: V2V_CUDA(launch_export_nchw(x.exp, s)); break;
@@ -492,7 +567,7 @@ static int check_conv(v2v_plan* p, int value_in, const v2v_conv_desc* c) {
 int v2v_g_conv(v2v_plan* p, int value_in, const v2v_conv_desc* c, int* raw_out) {
   int rc = check_conv(p, value_in, c); if (rc) return rc;
   V2V_REQUIRE(raw_out, V2V_ERR_INVALID, "null raw_out");
-  ConvGeom g; rc = conv_geometry(*c, p->values[value_in].H, p->values[value_in].W, p->allow_reuse, &g); if (rc) return rc;
+  ConvGeom g; rc = conv_geometry(*c, false, p->values[value_in].N, p->values[value_in].H, p->values[value_in].W, p->allow_reuse, &g); if (rc) return rc;
   GOp op; op.kind = G_CONV; op.value_in = value_in; op.conv = *c;
   Raw r{}; r.N = p->values[value_in].N; r.H = g.out_h; r.W = g.out_w; r.C = c->Cout; r.conv_op = (int)p->gops.size();
   p->raws.push_back(r);
@@ -533,7 +608,7 @@ int v2v_g_norm_act(v2v_plan* p, int raw_in, const v2v_norm_desc* norm, int act, 
 int v2v_g_conv_act(v2v_plan* p, int value_in, const v2v_conv_desc* c, int act, float slope, int* value_out) {
   int rc = check_conv(p, value_in, c); if (rc) return rc;
   V2V_REQUIRE(value_out, V2V_ERR_INVALID, "null value_out");
-  ConvGeom g; rc = conv_geometry(*c, p->values[value_in].H, p->values[value_in].W, p->allow_reuse, &g); if (rc) return rc;
+  ConvGeom g; rc = conv_geometry(*c, false, p->values[value_in].N, p->values[value_in].H, p->values[value_in].W, p->allow_reuse, &g); if (rc) return rc;
   GOp op; op.kind = G_CONV_ACT; op.value_in = value_in; op.conv = *c; op.act = act; op.slope = slope;
   op.value_out = new_value(p, p->values[value_in].N, g.out_h, g.out_w, c->Cout);
   p->gops.push_back(op);
@@ -673,7 +748,7 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
           }
         }
         if (P->impl == V2V_IMPL_UMMA) {
-          rc = make_tmap_act(&op.tmA, ain, op.geom.TW + op.geom.R - 1, op.geom.TH, kp.kc); if (rc) return rc;
+          rc = make_tmap_act(&op.tmA, ain, kp.PW, kp.PH, kp.kc); if (rc) return rc;
           rc = make_tmap_w(&op.tmB, op.wpacked, op.Ktotal, op.conv.Cout, kp.BN, kp.kc); if (rc) return rc;
         }
         rc = pack_one(op, stream); if (rc) return rc;
@@ -863,9 +938,9 @@ int v2v_conv_tap_table(const v2v_conv_desc* conv, int H, int W, int allow_reuse,
                        int* pads, int* parity, int* grid_hw, int* out_hw, int* mul) {
   V2V_REQUIRE(conv, V2V_ERR_INVALID, "null conv");
   ConvGeom g;
-  int rc = conv_geometry(*conv, H, W, allow_reuse != 0, &g);
+  int rc = conv_geometry(*conv, false, 1, H, W, allow_reuse != 0, &g);
   if (rc) return rc;
-  *n_groups = g.n_groups; *R = g.R; *n_phases = g.n_phases; *parity = g.parity; *mul = g.mul;
+  *n_groups = g.n_groups; R[0] = g.R; R[1] = g.RW; *n_phases = g.n_phases; *parity = g.parity; *mul = g.mul;
   for (int i = 0; i < g.n_groups; ++i) { plane[i] = g.groups[i].plane; dy[i] = g.groups[i].dy; dx[i] = g.groups[i].dx; tap0[i] = g.groups[i].tap0; }
   for (int i = 0; i < g.n_phases; ++i) { phase_begin[i] = g.phases[i].group_begin; oy_add[i] = g.phases[i].oy_add; ox_add[i] = g.phases[i].ox_add; }
   phase_begin[g.n_phases] = g.n_groups;

@@ -71,7 +71,9 @@ struct ConvKernelParams {
   int Cp, cblocks;                   // padded input channels, K blocks per tap (Cp / kc)
   int kc, row_bytes, kmma;           // channels per K block (16/32/64), smem row bytes (2*kc), MMAs per row (kc/16)
   int layout_type, sbo_bytes;        // UMMA smem-descriptor swizzle code (6/4/2) and 8-row group stride (8*row_bytes)
-  int R;                             // taps served per A patch (1 = none)
+  int R, RW;                         // taps served per A patch (1 = none); taps per patch row (tap r: row r / RW, column r % RW)
+  int PW, PH;                        // patch extent in pixels (TMA box)
+  int sbo_a_bytes;                   // A operand 8-row group stride: 8*row_bytes (row tiles) or PW*row_bytes (2-D patch)
   int a_slot_bytes, b_slot_bytes, SA, SB;
   int b_resident;                    // 1: SB == B tiles of one (phase, n-tile): loaded once per key, kept in smem
   int n_tiles, m_total, total_tiles; // N tiles, M tiles (N * tiles_x * tiles_y), all tiles incl. phases
@@ -91,6 +93,7 @@ struct ConvKernelParams {
   const float* bias;                 // may be null
   const float* bias2; int Cout1;     // fused heads: channels >= Cout1 take bias2[j - Cout1]
   int dbg;                           // timing experiments only (V2V_DBG): bit0 skip stats, bit1 skip output stores
+  int EG;                            // epilogue groups (4 warps each); EG > 1: group h owns TMEM accumulator stage h
   int grid;                          // CTAs launched (persistent); also the stats partial rows per (phase, image)
   // EPI_HEAD_F32: per output channel destination = io[head_slot] + head_off (+ n * head_bstride),
   // activation and scale.  Caller pointers are read from the device IO table at run time.
