@@ -64,35 +64,39 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
   return v[0];
 }
 
-// A work unit = MG consecutive M tiles of one (phase, N tile): their accumulators sit side by side in TMEM and every
-// weight tile fetched from L2 is used MG times (the small-N 7x7 stems are otherwise weight-traffic bound).
-struct Unit {
-  int key, phase, n0, m_first, count;
+// Work units (one M tile of one (phase, N tile) "key"; M fastest) are walked by every role as u = first, first + step, ...
+// Integer division is ~150 cycles of dependent SASS on one thread, and the single MMA-issuing thread used to spend
+// ~1000 cycles per tile decoding u (measured with the V2V_DBG traces: a 1000-cycle bubble between tiles of 2100 cycles
+// of MMAs).  The iterator therefore keeps (key, N tile, phase, image, tile row, tile column) as a mixed-radix number and
+// advances it by the pre-split step with carries: divisions happen once per kernel.
+struct UnitIter {
+  int u, key, nt, phase, img, ty, txi;
+  int s_img, s_ty, s_tx, step;
+  __device__ __forceinline__ void init(const ConvKernelParams& p, int first, int step_) {
+    const int per_img = p.tiles_x * p.tiles_y;
+    u = first; step = step_;
+    key = first / p.m_total;
+    const int m = first - key * p.m_total;
+    phase = key / p.n_tiles; nt = key - phase * p.n_tiles;
+    img = m / per_img;
+    const int r = m - img * per_img;
+    ty = r / p.tiles_x; txi = r - ty * p.tiles_x;
+    s_tx = step_ % p.tiles_x;
+    const int q = step_ / p.tiles_x;
+    s_ty = q % p.tiles_y; s_img = q / p.tiles_y;
+  }
+  __device__ __forceinline__ bool valid(const ConvKernelParams& p) const { return u < p.total_units; }
+  __device__ __forceinline__ void next(const ConvKernelParams& p) {
+    u += step;
+    txi += s_tx; if (txi >= p.tiles_x) { txi -= p.tiles_x; ++ty; }
+    ty += s_ty;  if (ty >= p.tiles_y) { ty -= p.tiles_y; ++img; }
+    img += s_img;
+    while (img >= p.N) { img -= p.N; ++key; if (++nt == p.n_tiles) { nt = 0; ++phase; } }
+  }
+  __device__ __forceinline__ int n0(const ConvKernelParams& p) const { return nt * p.BN; }
+  __device__ __forceinline__ int x0(const ConvKernelParams& p) const { return txi * p.TW; }
+  __device__ __forceinline__ int y0(const ConvKernelParams& p) const { return ty * p.TH; }
 };
-struct TileXY { int n_img, y0, x0; };
-
-__device__ __forceinline__ Unit decode_unit(const ConvKernelParams& p, int u) {
-  Unit un;
-  un.key = u / p.mg_total;
-  const int mg = u - un.key * p.mg_total;
-  const int nt = un.key % p.n_tiles;
-  un.phase = un.key / p.n_tiles;
-  un.n0 = nt * p.BN;
-  un.m_first = mg * p.MG;
-  un.count = min(p.MG, p.m_total - un.m_first);
-  return un;
-}
-__device__ __forceinline__ TileXY tile_xy(const ConvKernelParams& p, int m) {
-  TileXY t;
-  const int per_img = p.tiles_x * p.tiles_y;
-  t.n_img = m / per_img;
-  const int r = m - t.n_img * per_img;
-  const int ty = r / p.tiles_x;
-  t.y0 = ty * p.TH;
-  t.x0 = (r - ty * p.tiles_x) * p.TW;
-  return t;
-}
-
 
 struct MmaCtx {
   uint8_t* sG; uint8_t* sBres;
@@ -119,14 +123,16 @@ __device__ __forceinline__ void mma_role(const ConvKernelParams& p, const MmaCtx
   const uint32_t b_hi = (uint32_t)(make_kmajor_desc(0, p.sbo_bytes, p.layout_type) >> 32);
   const uint32_t a_lo0 = (uint32_t)make_kmajor_desc(0, p.sbo_a_bytes, p.layout_type);
   const uint32_t b_lo0 = (uint32_t)make_kmajor_desc(0, p.sbo_bytes, p.layout_type);
-  for (int u = cx.t_first; u < p.total_units; u += cx.t_step, ++it) {
-    const Unit un = decode_unit(p, u);
+  UnitIter un;
+  un.init(p, cx.t_first, cx.t_step);
+  for (; un.valid(p); ++it) {
     const ConvPhase ph = p.phases[un.phase];
-    const bool first_of_key = un.key != prev_key;
+    const int key = un.key;
+    const bool first_of_key = key != prev_key;
     if (p.b_resident && first_of_key && prev_key >= 0) gen ^= 1;
-    prev_key = un.key;
-    const int u_next = u + cx.t_step;
-    const bool last_of_key = (u_next >= p.total_units) || (u_next / p.mg_total != un.key);
+    prev_key = key;
+    un.next(p);                                          // (everything below uses the values captured above)
+    const bool last_of_key = !un.valid(p) || un.key != key;
     const int nsteps = (ph.group_end - ph.group_begin) * p.cblocks;
     TRACE(1, it, 0);
     mbar_wait(&cx.tmem_empty[as], aphase ^ 1);        // the epilogue has drained this accumulator stage
@@ -238,12 +244,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int gs = 0;
       uint32_t gpar = 0, gen = 0;
       int prev_key = -1;
-      for (int u = t_first; u < p.total_units; u += t_step) {
-        const Unit un = decode_unit(p, u);
-        const int pit = (u - t_first) / t_step;
+      UnitIter un;
+      un.init(p, t_first, t_step);
+      for (int pit = 0; un.valid(p); un.next(p), ++pit) {
         TRACE(0, pit, 0);
         const ConvPhase ph = p.phases[un.phase];
-        const TileXY tx = tile_xy(p, un.m_first);
+        const int x0 = un.x0(p), y0 = un.y0(p), n0 = un.n0(p);
         const int nsteps = (ph.group_end - ph.group_begin) * p.cblocks;
         if (p.b_resident && un.key != prev_key) {
           if (prev_key >= 0) gen ^= 1;
@@ -254,7 +260,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int cb = 0; cb < p.cblocks; ++cb, ++sidx)
               for (int r = 0; r < p.R; ++r)
                 tma_load_2d(sBres + (size_t)sidx * p.b_slot_bytes + (size_t)r * b_tx, &tmB, bres_full,
-                            (p.groups[g].tap0 + r) * p.Cp + cb * p.kc, un.n0);
+                            (p.groups[g].tap0 + r) * p.Cp + cb * p.kc, n0);
         }
         prev_key = un.key;
         int g = ph.group_begin, cb = 0;
@@ -265,12 +271,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_expect_tx(&g_full[gs], (uint32_t)n * (a_tx + (p.b_resident ? 0 : p.R * b_tx)));
           for (int i = 0; i < n; ++i) {
             const ConvGroup grp = p.groups[g];
-            tma_load_5d(base + (size_t)i * p.a_slot_bytes, &tmA, &g_full[gs], cb * p.kc, tx.x0 + grp.dx, tx.y0 + grp.dy,
-                        grp.plane, tx.n_img);
+            tma_load_5d(base + (size_t)i * p.a_slot_bytes, &tmA, &g_full[gs], cb * p.kc, x0 + grp.dx, y0 + grp.dy,
+                        grp.plane, un.img);
             if (!p.b_resident) {
               uint8_t* bb = base + (size_t)p.CG * p.a_slot_bytes + (size_t)i * p.b_slot_bytes;
               for (int r = 0; r < p.R; ++r)
-                tma_load_2d(bb + (size_t)r * b_tx, &tmB, &g_full[gs], (grp.tap0 + r) * p.Cp + cb * p.kc, un.n0);
+                tma_load_2d(bb + (size_t)r * b_tx, &tmB, &g_full[gs], (grp.tap0 + r) * p.Cp + cb * p.kc, n0);
             }
             if (++cb == p.cblocks) { cb = 0; ++g; }
           }
@@ -317,29 +323,36 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       named_bar_sync(1 + eg, kEpiThreads);                // racc may be cleared again
     };
-    int as = 0;
-    uint32_t aphase = 0;
-    for (int u = t_first, it = 0; u < p.total_units; u += t_step, ++it) {
-      const int my_as = as;
-      const uint32_t my_phase = aphase;
-      if (++as == NS) { as = 0; aphase ^= 1; }
-      if (p.EG > 1 && my_as != eg) continue;              // stage h belongs to group h
-      const Unit un = decode_unit(p, u);
+    // group eg handles units it = eg, eg + EG, ...; with EG > 1 its accumulator stage is always eg
+    const int tw_shift = __ffs(p.TW) - 1;                 // TW is a power of two
+    const int row = q * 32 + lane;
+    const int ry = row >> tw_shift, rx = row & (p.TW - 1);
+    UnitIter un;
+    un.init(p, t_first + eg * t_step, t_step * p.EG);
+    for (int ju = 0; un.valid(p); un.next(p), ++ju) {
+      const int it = eg + ju * p.EG;
+      const int my_as = p.EG > 1 ? eg : (ju & 1);
+      const uint32_t my_phase = p.EG > 1 ? (ju & 1) : ((ju >> 1) & 1);
+      // everything that does not depend on the accumulator is computed before waiting for it
       const ConvPhase ph = p.phases[un.phase];
+      const int gy = un.y0(p) + ry, gx = un.x0(p) + rx;
+      const bool valid = (gy < p.grid_h) && (gx < p.grid_w);
+      const int oy = gy * p.oy_mul + ph.oy_add, ox = gx * p.ox_mul + ph.ox_add;
+      const uint32_t taddr = tmem_base + my_as * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
+      const int n0 = un.n0(p), n_img = un.img;
+      bf16* dst = nullptr;
+      if (valid && p.epi != EPI_HEAD_F32) {
+        if (p.epi == EPI_RAW_STATS)
+          dst = reinterpret_cast<bf16*>(p.out) + (((size_t)n_img * p.out_H + oy) * p.out_W + ox) * p.out_C;
+        else
+          dst = p.out_act.base + p.out_act.offset(n_img, oy, ox);
+      }
       if (q == 0) TRACE(2, it, 0);
       mbar_wait(&tmem_full[my_as], my_phase);
       tcgen05_fence_after();
       if (q == 0) TRACE(2, it, 1);
-      for (int jt = 0; jt < un.count; ++jt) {
-        const TileXY txy = tile_xy(p, un.m_first + jt);
-        const bool last_tile = (jt == un.count - 1);
-        const int row = q * 32 + lane;
-        const int ry = row / p.TW, rx = row - ry * p.TW;
-        const int gy = txy.y0 + ry, gx = txy.x0 + rx;
-        const bool valid = (gy < p.grid_h) && (gx < p.grid_w);
-        const int oy = gy * p.oy_mul + ph.oy_add, ox = gx * p.ox_mul + ph.ox_add;
-        const uint32_t taddr = tmem_base + (my_as * p.MG + jt) * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
-        const int n0 = un.n0, n_img = txy.n_img;
+      {
+        const bool last_tile = true;
 
         if (p.epi == EPI_HEAD_F32) {
           uint32_t r[16];
@@ -370,13 +383,6 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int c = lane; c < 2 * 128; c += 32) racc[q * 256 + c] = 0.f;
           __syncwarp();
           acc_key = un.key; acc_img = n_img; acc_n0 = n0; acc_phase = un.phase;
-        }
-        bf16* dst = nullptr;
-        if (valid) {
-          if (p.epi == EPI_RAW_STATS)
-            dst = reinterpret_cast<bf16*>(p.out) + (((size_t)n_img * p.out_H + oy) * p.out_W + ox) * p.out_C;
-          else
-            dst = p.out_act.base + p.out_act.offset(n_img, oy, ox);
         }
         for (int c = 0; c < nchunks; ++c) {
           uint32_t r[32];
@@ -442,7 +448,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (q == 0) TRACE(2, it, 5);
-      }   // tiles of the unit
+      }
       if (q == 0) TRACE(2, it, 2);
     }
     if (do_stats && acc_key >= 0) flush();

@@ -93,7 +93,9 @@ static bool choose_patch2d(const v2v_conv_desc& c, bool head, int N, int grid_h,
   // weights again for every tile costs more L2 traffic than the second pass over the activations)
   for (int pass = 0; pass < 2; ++pass) {
     const int bn = pass == 0 ? bn0 : bn0 / 2;
-    if (pass == 1 && (bn0 < 128 || m_total < 4LL * sms)) break;
+    // (measured on 128->128 @256x512: 58 us with the halved N tile vs 50 us streamed, so pass 2 is opt-in)
+    static const bool half_ok = [] { const char* e = getenv("V2V_P2D_HALF"); return e && e[0] == '1'; }();
+    if (pass == 1 && (!half_ok || bn0 < 128 || m_total < 4LL * sms)) break;
     if (m_total <= sms) break;
     const long long res_bytes = (long long)(Cp / kc_max) * round_up_i(taps * bn * kc_max * 2, 1024);
     const int patch = round_up_i(PH * PW * kc_max * 2, 1024);
