@@ -84,6 +84,10 @@ CASES = [
     ('mg2_stream_c128', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(128, 128, 3), BN(128), nn.ReLU(True)], (1, 128, 160, 512)),
     ('mg4_stem', lambda: NW._stem(108, 32, BN), (1, 108, 256, 640)),
     ('mg2_stem_batch2_straddle', lambda: NW._stem(108, 16, BN), (2, 108, 107, 384)),
+    ('mg4_stem_108_48', lambda: NW._stem(108, 48, BN), (1, 108, 160, 512)),
+    ('mg2_bn96_stem_108_96', lambda: NW._stem(108, 96, BN), (1, 108, 160, 512)),
+    ('mg_stem_batch2_instance', lambda: NW._stem(108, 32, IN), (2, 108, 80, 512)),
+    ('mg_stem_108_192_ntiles', lambda: NW._stem(108, 192, BN), (1, 108, 160, 512)),
     # 16- and 32-channel K blocks (32-byte / 64-byte swizzled rows), with and without tap reuse
     ('kc16_stem_R7', lambda: NW._stem(6, 32, BN), (1, 6, 12, 136)),
     ('kc16_stem_R7_mt', lambda: NW._stem(6, 32, BN), (1, 6, 80, 256)),

@@ -12,6 +12,9 @@ SHAPES = {
     'c128_256x512': (lambda: [nn.ReflectionPad2d(1), nn.Conv2d(128, 128, 3), BN(128), nn.ReLU(True)], (1, 128, 256, 512)),
     'c64_512x1024': (lambda: [nn.ReflectionPad2d(1), nn.Conv2d(64, 64, 3), BN(64), nn.ReLU(True)], (1, 64, 512, 1024)),
     'stem108_32': (lambda: NW._stem(108, 32, BN), (1, 108, 1024, 2048)),
+    'stem108_48': (lambda: NW._stem(108, 48, BN), (1, 108, 1024, 2048)),
+    'stem108_96': (lambda: NW._stem(108, 96, BN), (1, 108, 512, 1024)),
+    'stem108_192': (lambda: NW._stem(108, 192, BN), (1, 108, 256, 512)),
     'head32_2048': (lambda: [nn.ReflectionPad2d(3), nn.Conv2d(32, 3, 7), nn.Tanh()], (1, 32, 1024, 2048)),
     'up64_32': (lambda: [nn.ConvTranspose2d(64, 32, 3, stride=2, padding=1, output_padding=1), BN(32), nn.ReLU(True)], (1, 64, 512, 1024)),
     'c32_512x1024': (lambda: [nn.ReflectionPad2d(1), nn.Conv2d(32, 32, 3), BN(32), nn.ReLU(True)], (1, 32, 512, 1024)),

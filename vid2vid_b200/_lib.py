@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libv2v_b200.so')
+LIB_PATH = os.environ.get('V2V_LIB') or os.path.join(_HERE, 'libv2v_b200.so')   # V2V_LIB: A/B timing of two builds
 
 PAD_NONE, PAD_ZERO, PAD_REFLECT = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4

@@ -64,7 +64,7 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
   return v[0];
 }
 
-// Work units (one M tile of one (phase, N tile) "key"; M fastest) are walked by every role as u = first, first + step, ...
+// Work units (MG consecutive M tiles of one tile row, of one (phase, N tile) "key"; M fastest) are walked by every role as u = first, first + step, ...
 // Integer division is ~150 cycles of dependent SASS on one thread, and the single MMA-issuing thread used to spend
 // ~1000 cycles per tile decoding u (measured with the V2V_DBG traces: a 1000-cycle bubble between tiles of 2100 cycles
 // of MMAs).  The iterator therefore keeps (key, N tile, phase, image, tile row, tile column) as a mixed-radix number and
@@ -73,28 +73,30 @@ struct UnitIter {
   int u, key, nt, phase, img, ty, txi;
   int s_img, s_ty, s_tx, step;
   __device__ __forceinline__ void init(const ConvKernelParams& p, int first, int step_) {
-    const int per_img = p.tiles_x * p.tiles_y;
+    const int txu = p.tiles_x / p.MG;                   // units per tile row (MG consecutive x tiles share a weight pass)
+    const int per_img = txu * p.tiles_y;
     u = first; step = step_;
     key = first / p.m_total;
     const int m = first - key * p.m_total;
     phase = key / p.n_tiles; nt = key - phase * p.n_tiles;
     img = m / per_img;
     const int r = m - img * per_img;
-    ty = r / p.tiles_x; txi = r - ty * p.tiles_x;
-    s_tx = step_ % p.tiles_x;
-    const int q = step_ / p.tiles_x;
+    ty = r / txu; txi = r - ty * txu;
+    s_tx = step_ % txu;
+    const int q = step_ / txu;
     s_ty = q % p.tiles_y; s_img = q / p.tiles_y;
   }
   __device__ __forceinline__ bool valid(const ConvKernelParams& p) const { return u < p.total_units; }
   __device__ __forceinline__ void next(const ConvKernelParams& p) {
     u += step;
-    txi += s_tx; if (txi >= p.tiles_x) { txi -= p.tiles_x; ++ty; }
+    const int txu = p.tiles_x / p.MG;
+    txi += s_tx; if (txi >= txu) { txi -= txu; ++ty; }
     ty += s_ty;  if (ty >= p.tiles_y) { ty -= p.tiles_y; ++img; }
     img += s_img;
     while (img >= p.N) { img -= p.N; ++key; if (++nt == p.n_tiles) { nt = 0; ++phase; } }
   }
   __device__ __forceinline__ int n0(const ConvKernelParams& p) const { return nt * p.BN; }
-  __device__ __forceinline__ int x0(const ConvKernelParams& p) const { return txi * p.TW; }
+  __device__ __forceinline__ int x0(const ConvKernelParams& p) const { return txi * p.MG * p.TW; }   // first tile of the unit
   __device__ __forceinline__ int y0(const ConvKernelParams& p) const { return ty * p.TH; }
 };
 
@@ -139,8 +141,7 @@ __device__ __forceinline__ void mma_role(const ConvKernelParams& p, const MmaCtx
     if (p.b_resident && first_of_key) mbar_wait(cx.bres_full, gen);
     tcgen05_fence_after();
     TRACE(1, it, 1);
-    const uint32_t tmem_d = cx.tmem_base + as * cx.acc_cols;
-    uint32_t first = 0;
+    const uint32_t tmem_d0 = cx.tmem_base + as * p.MG * cx.acc_cols;
     for (int s0 = 0; s0 < nsteps; s0 += p.CG) {
       const int n = min(p.CG, nsteps - s0);
       mbar_wait(&cx.g_full[gs], gpar);
@@ -148,29 +149,35 @@ __device__ __forceinline__ void mma_role(const ConvKernelParams& p, const MmaCtx
       if (s0 == 0) TRACE(1, it, 2);
       const uint32_t base = smem_u32(cx.sG + (size_t)gs * cx.group_bytes);
       for (int i = 0; i < n; ++i) {
-        const uint32_t a_base = base + i * p.a_slot_bytes;
         const uint32_t b_base = p.b_resident ? sBres_u32 + (s0 + i) * p.b_slot_bytes
-                                             : base + p.CG * p.a_slot_bytes + i * p.b_slot_bytes;
-        uint32_t al = a_lo0 + ((a_base & 0x3FFFF) >> 4), bl = b_lo0 + ((b_base & 0x3FFFF) >> 4);
-        // tap r reads the patch shifted by (r / RW) patch rows and (r % RW) pixels; K = 16 bf16 = 32 bytes per MMA,
-        // kc/16 MMAs per smem row (fixed trip counts keep the issue loop tight)
-        for (int r0 = 0; r0 < p.R; r0 += p.RW, al += a_wrap) {
-          for (int r = 0; r < p.RW; ++r, al += a_step, bl += b_step) {
-            if (kWarpWide ? elect_one_sync() : true) {
-              const uint64_t ad = ((uint64_t)a_hi << 32) | al, bd = ((uint64_t)b_hi << 32) | bl;
-              if (p.kmma == 4) {
-                umma_bf16(tmem_d, ad, bd, idesc, first);
-                umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
-                umma_bf16(tmem_d, ad + 4, bd + 4, idesc, 1u);
-                umma_bf16(tmem_d, ad + 6, bd + 6, idesc, 1u);
-              } else if (p.kmma == 2) {
-                umma_bf16(tmem_d, ad, bd, idesc, first);
-                umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
-              } else {
-                umma_bf16(tmem_d, ad, bd, idesc, first);
+                                             : base + p.CG * p.MG * p.a_slot_bytes + i * p.b_slot_bytes;
+        const uint32_t bl0 = b_lo0 + ((b_base & 0x3FFFF) >> 4);
+        // MG accumulators side by side: every weight tile fetched from L2 is used for MG M tiles
+        for (int j = 0; j < p.MG; ++j) {
+          const uint32_t a_base = base + (i * p.MG + j) * p.a_slot_bytes;
+          const uint32_t tmem_d = tmem_d0 + j * cx.acc_cols;
+          uint32_t first = (s0 + i) > 0 ? 1u : 0u;
+          uint32_t al = a_lo0 + ((a_base & 0x3FFFF) >> 4), bl = bl0;
+          // tap r reads the patch shifted by (r / RW) patch rows and (r % RW) pixels; K = 16 bf16 = 32 bytes per MMA,
+          // kc/16 MMAs per smem row (fixed trip counts keep the issue loop tight)
+          for (int r0 = 0; r0 < p.R; r0 += p.RW, al += a_wrap) {
+            for (int r = 0; r < p.RW; ++r, al += a_step, bl += b_step) {
+              if (kWarpWide ? elect_one_sync() : true) {
+                const uint64_t ad = ((uint64_t)a_hi << 32) | al, bd = ((uint64_t)b_hi << 32) | bl;
+                if (p.kmma == 4) {
+                  umma_bf16(tmem_d, ad, bd, idesc, first);
+                  umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
+                  umma_bf16(tmem_d, ad + 4, bd + 4, idesc, 1u);
+                  umma_bf16(tmem_d, ad + 6, bd + 6, idesc, 1u);
+                } else if (p.kmma == 2) {
+                  umma_bf16(tmem_d, ad, bd, idesc, first);
+                  umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
+                } else {
+                  umma_bf16(tmem_d, ad, bd, idesc, first);
+                }
               }
+              first = 1u;
             }
-            first = 1u;
           }
         }
       }
@@ -195,7 +202,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // group slots: [SG][ CG activation patches | CG streamed weight slots ], then the resident weight set (if any)
   const int slot_b = p.b_resident ? 0 : p.b_slot_bytes;
-  const int group_bytes = p.CG * (p.a_slot_bytes + slot_b);
+  const int group_bytes = p.CG * (p.MG * p.a_slot_bytes + slot_b);
   uint8_t* sG = smem;
   uint8_t* sBres = sG + (size_t)p.SG * group_bytes;
   float* red = reinterpret_cast<float*>(sBres + (p.b_resident ? (size_t)p.SB * p.b_slot_bytes : 0));
@@ -268,13 +275,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int n = min(p.CG, nsteps - s0);
           uint8_t* base = sG + (size_t)gs * group_bytes;
           mbar_wait(&g_empty[gs], gpar ^ 1);
-          mbar_expect_tx(&g_full[gs], (uint32_t)n * (a_tx + (p.b_resident ? 0 : p.R * b_tx)));
+          mbar_expect_tx(&g_full[gs], (uint32_t)n * (p.MG * a_tx + (p.b_resident ? 0 : p.R * b_tx)));
           for (int i = 0; i < n; ++i) {
             const ConvGroup grp = p.groups[g];
-            tma_load_5d(base + (size_t)i * p.a_slot_bytes, &tmA, &g_full[gs], cb * p.kc, x0 + grp.dx, y0 + grp.dy,
-                        grp.plane, un.img);
+            for (int j = 0; j < p.MG; ++j)
+              tma_load_5d(base + (size_t)(i * p.MG + j) * p.a_slot_bytes, &tmA, &g_full[gs], cb * p.kc,
+                          x0 + j * p.TW + grp.dx, y0 + grp.dy, grp.plane, un.img);
             if (!p.b_resident) {
-              uint8_t* bb = base + (size_t)p.CG * p.a_slot_bytes + (size_t)i * p.b_slot_bytes;
+              uint8_t* bb = base + (size_t)p.CG * p.MG * p.a_slot_bytes + (size_t)i * p.b_slot_bytes;
               for (int r = 0; r < p.R; ++r)
                 tma_load_2d(bb + (size_t)r * b_tx, &tmB, &g_full[gs], (grp.tap0 + r) * p.Cp + cb * p.kc, n0);
             }
@@ -335,24 +343,26 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t my_phase = p.EG > 1 ? (ju & 1) : ((ju >> 1) & 1);
       // everything that does not depend on the accumulator is computed before waiting for it
       const ConvPhase ph = p.phases[un.phase];
-      const int gy = un.y0(p) + ry, gx = un.x0(p) + rx;
-      const bool valid = (gy < p.grid_h) && (gx < p.grid_w);
-      const int oy = gy * p.oy_mul + ph.oy_add, ox = gx * p.ox_mul + ph.ox_add;
-      const uint32_t taddr = tmem_base + my_as * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
+      const int gy = un.y0(p) + ry, gx0 = un.x0(p) + rx;
+      const int oy = gy * p.oy_mul + ph.oy_add;
       const int n0 = un.n0(p), n_img = un.img;
-      bf16* dst = nullptr;
-      if (valid && p.epi != EPI_HEAD_F32) {
-        if (p.epi == EPI_RAW_STATS)
-          dst = reinterpret_cast<bf16*>(p.out) + (((size_t)n_img * p.out_H + oy) * p.out_W + ox) * p.out_C;
-        else
-          dst = p.out_act.base + p.out_act.offset(n_img, oy, ox);
-      }
       if (q == 0) TRACE(2, it, 0);
       mbar_wait(&tmem_full[my_as], my_phase);
       tcgen05_fence_after();
       if (q == 0) TRACE(2, it, 1);
-      {
-        const bool last_tile = true;
+      for (int jt = 0; jt < p.MG; ++jt) {                   // the unit's MG tiles sit side by side along x
+        const bool last_tile = (jt == p.MG - 1);
+        const int gx = gx0 + jt * p.TW;
+        const bool valid = (gy < p.grid_h) && (gx < p.grid_w);
+        const int ox = gx * p.ox_mul + ph.ox_add;
+        const uint32_t taddr = tmem_base + (my_as * p.MG + jt) * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
+        bf16* dst = nullptr;
+        if (valid && p.epi != EPI_HEAD_F32) {
+          if (p.epi == EPI_RAW_STATS)
+            dst = reinterpret_cast<bf16*>(p.out) + (((size_t)n_img * p.out_H + oy) * p.out_W + ox) * p.out_C;
+          else
+            dst = p.out_act.base + p.out_act.offset(n_img, oy, ox);
+        }
 
         if (p.epi == EPI_HEAD_F32) {
           uint32_t r[16];

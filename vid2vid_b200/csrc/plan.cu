@@ -104,7 +104,13 @@ static bool choose_patch2d(const v2v_conv_desc& c, bool head, int N, int grid_h,
       return true;
     }
   }
-  for (int kc = kc_max; kc >= 16; kc >>= 1) {
+  // Streamed weights: only when a CTA sees few M tiles (the weights pass through once per unit either way, and the
+  // patch saves the activation re-reads: 1024->1024 @32x64 50 us vs 58.6 us with one box per tap).  With many M tiles
+  // per CTA the row-tile path with M blocking shares each weight tile between tiles instead (measured: 128->128 @256x512
+  // 54 us here vs 51 us row tiles even before M blocking), and K blocks below 32 channels turn the 49 taps of a 7x7
+  // filter into 1 KB TMA boxes (108->32 @1024x2048: 2.16 ms vs 1.49 ms).
+  if (m_total >= 4LL * sms) return false;
+  for (int kc = kc_max; kc >= 32; kc >>= 1) {
     if (Cp % kc) continue;
     const int patch = round_up_i(PH * PW * kc * 2, 1024), bstep = round_up_i(taps * bn0 * kc * 2, 1024);
     if (2 * (patch + bstep) <= kSmemBudget) { *kc_out = kc; *bn_out = bn0; *res_out = 0; return true; }
@@ -394,8 +400,45 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   kp.BN = op.kind == G_HEAD ? 16 : std::min(128, round_up(op.conv.Cout, 32));
   kp.Cp = pad_channels(op.conv.Cin);
   kp.kc = std::min(kp.Cp, 64);
+  kp.MG = 1;
   const bool p2d = g.patch2d_kc > 0;
   if (p2d) { kp.kc = g.patch2d_kc; if (op.kind != G_HEAD) kp.BN = g.patch2d_bn; }
+  const int m_tiles = kp.N * kp.tiles_x * kp.tiles_y;
+  // M blocking for row-tile filters whose weights must be streamed (the 7x7 stems over the 108-channel label input):
+  // per M tile such a layer pulls taps*Cp*BN*2 bytes of weights through L2 -> SM (802 KB for 108->48, 13 GB per launch at
+  // 2048x1024: the measured 1.6 ms IS that traffic at ~8 TB/s), i.e. 64 B per SM clock at the full MMA rate against the
+  // ~33 B/clk an SM can ingest.  MG consecutive x tiles accumulate side by side in TMEM and share every weight tile.
+  // Candidates (K block, N tile, MG) are ranked by max(MMA cycles, ingest cycles) per M tile.
+  bool mblock = false;
+  if (!p2d && !op.conv.transposed && op.conv.stride == 1 && g.R > 1 && g.n_phases == 1 && op.kind != G_HEAD &&
+      m_tiles >= 4 * device_sm_count()) {
+    const char* em = getenv("V2V_MG");
+    const int mg_cap = em ? atoi(em) : 4;
+    const int taps = op.conv.kh * op.conv.kw, ngroups = g.n_groups;
+    double best = 1e30;
+    const int bn0 = std::min(128, round_up(op.conv.Cout, 32));
+    for (int bn = 128; bn >= 32; bn -= 32) {
+      if (bn > bn0) continue;
+      const int ntiles = (op.conv.Cout + bn - 1) / bn;
+      const int acc = std::max(32, bn);
+      for (int kc = std::min(kp.Cp, 64); kc >= 16; kc >>= 1) {
+        if (kp.Cp % kc) continue;
+        const int a_slot = round_up((g.TW + g.R - 1) * g.TH * kc * 2, 1024), b_slot = round_up(g.R * bn * kc * 2, 1024);
+        const long long w_bytes = (long long)taps * kp.Cp * bn * 2;
+        for (int mg = 1; mg <= mg_cap; mg <<= 1) {
+          if (kp.tiles_x % mg || 2 * mg * acc > 512) continue;
+          const bool res = mg == 1 && w_bytes <= kResidentMax && kSmemBudget - w_bytes >= 2 * a_slot;
+          if (!res && 2 * (mg * a_slot + b_slot) > kSmemBudget) continue;
+          const double mma = (double)ntiles * taps * (kp.Cp / 16) * std::max(40, bn / 2);
+          const double a_bytes = (double)ngroups * (kp.Cp / kc) * (g.TW + g.R - 1) * g.TH * kc * 2;
+          const double ingest = ntiles * (a_bytes + (res ? 0.0 : (double)w_bytes / mg)) / 33.0;
+          const double commits = (double)ntiles * ngroups * (kp.Cp / kc) * 300.0 / mg;
+          const double cost = std::max(mma, ingest) + commits;
+          if (cost < best - 1.0) { best = cost; kp.kc = kc; kp.BN = bn; kp.MG = mg; mblock = true; }
+        }
+      }
+    }
+  }
   kp.cblocks = kp.Cp / kp.kc;
   kp.row_bytes = kp.kc * 2; kp.kmma = kp.kc / 16;
   kp.layout_type = kp.kc == 64 ? 2 : (kp.kc == 32 ? 4 : 6);
@@ -416,10 +459,10 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   // shared-memory budget: 227 KB - epilogue scratch (12.5 KB per group) - alignment slack - barriers
   const int budget = kSmemBudget;
   // a weight slot holds the R taps served by one activation patch; keep >= 2 slots + 3 patches in the budget
-  while (!p2d && g.R > 1 && kp.BN > 32 && 2 * g.R * kp.BN * kp.row_bytes + 3 * kp.a_slot_bytes > budget) kp.BN /= 2;
+  while (!p2d && !mblock && g.R > 1 && kp.BN > 32 && 2 * g.R * kp.BN * kp.row_bytes + 3 * kp.a_slot_bytes > budget) kp.BN /= 2;
   kp.b_slot_bytes = round_up(g.R * kp.BN * kp.row_bytes, 1024);
   kp.n_tiles = (kp.Cout + kp.BN - 1) / kp.BN;
-  kp.m_total = kp.N * kp.tiles_x * kp.tiles_y;
+  kp.m_total = kp.N * (kp.tiles_x / kp.MG) * kp.tiles_y;       // M units: MG consecutive x tiles each
   kp.total_tiles = kp.m_total * kp.n_tiles * g.n_phases;
   int max_phase_groups = 0;
   for (int i = 0; i < g.n_phases; ++i) max_phase_groups = std::max(max_phase_groups, g.phases[i].group_end - g.phases[i].group_begin);
@@ -429,9 +472,9 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   const int sms = device_sm_count();
   // resident weights pay off when a CTA walks several M tiles with the same weights
   const bool many_m = kp.m_total > sms;
-  kp.MG = 1;
   kp.b_resident = (allow_res && many_m && (long long)nB * kp.b_slot_bytes <= kResidentMax &&
                    budget - nB * kp.b_slot_bytes >= 2 * kp.a_slot_bytes) ? 1 : 0;
+  if (kp.MG > 1) kp.b_resident = 0;
   if (p2d && !kp.b_resident && 2 * (kp.a_slot_bytes + kp.b_slot_bytes) > budget) {
     set_error("internal: 2-D patch conv does not fit (a %d b %d)", kp.a_slot_bytes, kp.b_slot_bytes);
   }
@@ -440,11 +483,11 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   // during which the tensor pipe idles (its queue is shallow), so CG consecutive K-loop steps share one barrier pair;
   // a step issues R * kmma MMAs of max(40, BN/2) cycles each (smem operand fetch floors small-N MMAs at ~40 cycles).
   {
-    const int slot = kp.a_slot_bytes + (kp.b_resident ? 0 : kp.b_slot_bytes);
+    const int slot = kp.MG * kp.a_slot_bytes + (kp.b_resident ? 0 : kp.b_slot_bytes);
     const int avail = budget - (kp.b_resident ? nB * kp.b_slot_bytes : 0);
     const int nslots = std::max(2, avail / slot);
     const int steps = max_phase_groups * kp.cblocks;
-    const int est = g.R * kp.kmma * std::max(40, kp.BN / 2);
+    const int est = kp.MG * g.R * kp.kmma * std::max(40, kp.BN / 2);
     int cg;
     if (steps * est <= 6000 && 2 * steps <= nslots) cg = steps;           // one group per tile, double buffered
     else {
@@ -458,8 +501,8 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
     kp.SA = kp.SG * kp.CG;     // (informational)
   }
   { const char* dg = getenv("V2V_DBG"); kp.dbg = dg ? atoi(dg) : 0; }
-  kp.mg_total = (kp.m_total + kp.MG - 1) / kp.MG;
-  kp.total_units = kp.mg_total * kp.n_tiles * g.n_phases;
+  kp.mg_total = kp.m_total;
+  kp.total_units = kp.m_total * kp.n_tiles * g.n_phases;
   kp.grid = std::min(kp.total_units, device_sm_count());
   kp.num_phases = g.n_phases;
   memcpy(kp.phases, g.phases, sizeof(kp.phases));
@@ -917,11 +960,16 @@ int64_t v2v_plan_describe(const v2v_plan* P_, char* buf, int64_t cap) {
   for (const GOp& op : P->gops) {
     if (!(op.kind == G_CONV || op.kind == G_CONV_ACT || op.kind == G_HEAD)) continue;
     const ConvGeom& g = op.geom;
+    GOp tmp = op;                                  // kernel configuration (host-only logic; no device state needed)
+    fill_conv_params(const_cast<v2v_plan*>(P), tmp);
+    const ConvKernelParams& kp = tmp.kp;
     snprintf(t, sizeof(t),
              "%s{\"kind\":%d,\"Cin\":%d,\"Cout\":%d,\"k\":[%d,%d],\"stride\":%d,\"transposed\":%d,\"in\":%d,\"TH\":%d,\"TW\":%d,"
-             "\"R\":%d,\"groups\":%d,\"phases\":%d,\"grid\":[%d,%d],\"out\":[%d,%d]}",
+             "\"R\":%d,\"groups\":%d,\"phases\":%d,\"grid\":[%d,%d],\"out\":[%d,%d],"
+             "\"BN\":%d,\"kc\":%d,\"MG\":%d,\"CG\":%d,\"SG\":%d,\"resident\":%d,\"EG\":%d,\"units\":%d}",
              first ? "" : ",", (int)op.kind, op.conv.Cin, op.conv.Cout, op.conv.kh, op.conv.kw, op.conv.stride, op.conv.transposed,
-             op.value_in, g.TH, g.TW, g.R, g.n_groups, g.n_phases, g.grid_h, g.grid_w, g.out_h, g.out_w);
+             op.value_in, g.TH, g.TW, g.R, g.n_groups, g.n_phases, g.grid_h, g.grid_w, g.out_h, g.out_w,
+             kp.BN, kp.kc, kp.MG, kp.CG, kp.SG, kp.b_resident, kp.EG, kp.total_units);
     s += t;
     first = false;
   }
