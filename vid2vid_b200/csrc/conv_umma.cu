@@ -491,7 +491,7 @@ int device_sm_count() {
 
 cudaError_t launch_conv_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p,
                              cudaStream_t stream) {
-  const size_t smem = (size_t)p.SG * p.CG * (p.a_slot_bytes + (p.b_resident ? 0 : p.b_slot_bytes)) +
+  const size_t smem = (size_t)p.SG * p.CG * ((size_t)p.MG * p.a_slot_bytes + (p.b_resident ? 0 : p.b_slot_bytes)) +
                       (p.b_resident ? (size_t)p.SB * p.b_slot_bytes : 0) + 1024 /*align*/ + (size_t)p.EG * kRedFloatsPerGroup * sizeof(float) +
                       (2 * p.SG + 2 + 2 * kMaxGroups + 2) * sizeof(uint64_t);
   static size_t configured = 0;

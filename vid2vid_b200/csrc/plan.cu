@@ -406,37 +406,28 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   const int m_tiles = kp.N * kp.tiles_x * kp.tiles_y;
   // M blocking for row-tile filters whose weights must be streamed (the 7x7 stems over the 108-channel label input):
   // per M tile such a layer pulls taps*Cp*BN*2 bytes of weights through L2 -> SM (802 KB for 108->48, 13 GB per launch at
-  // 2048x1024: the measured 1.6 ms IS that traffic at ~8 TB/s), i.e. 64 B per SM clock at the full MMA rate against the
-  // ~33 B/clk an SM can ingest.  MG consecutive x tiles accumulate side by side in TMEM and share every weight tile.
-  // Candidates (K block, N tile, MG) are ranked by max(MMA cycles, ingest cycles) per M tile.
+  // 2048x1024), i.e. 64 B per SM clock at the full MMA rate against the ~42 B/clk an SM ingests.  MG = 2 consecutive x
+  // tiles accumulate side by side in TMEM and share every weight tile.  The (K block, N tile, MG) choice is measured,
+  // not modelled (gpurun sweep with V2V_FORCE, ms per launch):
+  //     108->48 @1024x2048 : (64,64,1) 1.73  (64,64,2) 1.51  (32,64,2) 2.19  (32,64,4) 1.98  (64,32,2) 2.65
+  //     108->96 @512x1024  : (64,64,1) 0.875 (64,64,2) 0.769 (32,96,2) 0.622 (64,96,1) 0.826 (32,128,2) 0.828
+  //     108->192 @256x512  : (64,64,2) 0.316 (32,96,2) 0.323 (64,96,1) 0.337 (32,128,2) 0.351
+  //     128->128 3x3 @256x512 : (64,128,1) 52.2 us (64,128,2) 52.3 (32,128,2) 66.8 (64,64,2) 64.5   -> 3x3 stays as it was
+  // 64-byte rows (32-channel K blocks) cost ingest rate (requests, not bytes, are the limit) unless they buy an exact
+  // N tile (Cout = 96), and 4 tiles per unit (all 512 TMEM columns) were always slower than 2.
   bool mblock = false;
-  if (!p2d && !op.conv.transposed && op.conv.stride == 1 && g.R > 1 && g.n_phases == 1 && op.kind != G_HEAD &&
-      m_tiles >= 4 * device_sm_count()) {
+  if (!p2d && !op.conv.transposed && op.conv.stride == 1 && g.R >= 5 && g.n_phases == 1 && op.kind != G_HEAD &&
+      m_tiles >= 4 * device_sm_count() &&
+      (long long)op.conv.kh * op.conv.kw * kp.Cp * std::min(64, kp.BN) * 2 > kResidentMax) {   // cannot stay resident
+    int c_kc = std::min(kp.Cp, 64), c_bn = std::min(64, round_up(op.conv.Cout, 32)), c_mg = 2;
+    if (round_up(op.conv.Cout, 32) == 96 && kp.Cp % 32 == 0) { c_kc = 32; c_bn = 96; }
+    if (const char* ef = getenv("V2V_FORCE")) sscanf(ef, "%d,%d,%d", &c_kc, &c_bn, &c_mg);      // timing experiments
     const char* em = getenv("V2V_MG");
-    const int mg_cap = em ? atoi(em) : 4;
-    const int taps = op.conv.kh * op.conv.kw, ngroups = g.n_groups;
-    double best = 1e30;
-    const int bn0 = std::min(128, round_up(op.conv.Cout, 32));
-    for (int bn = 128; bn >= 32; bn -= 32) {
-      if (bn > bn0) continue;
-      const int ntiles = (op.conv.Cout + bn - 1) / bn;
-      const int acc = std::max(32, bn);
-      for (int kc = std::min(kp.Cp, 64); kc >= 16; kc >>= 1) {
-        if (kp.Cp % kc) continue;
-        const int a_slot = round_up((g.TW + g.R - 1) * g.TH * kc * 2, 1024), b_slot = round_up(g.R * bn * kc * 2, 1024);
-        const long long w_bytes = (long long)taps * kp.Cp * bn * 2;
-        for (int mg = 1; mg <= mg_cap; mg <<= 1) {
-          if (kp.tiles_x % mg || 2 * mg * acc > 512) continue;
-          const bool res = mg == 1 && w_bytes <= kResidentMax && kSmemBudget - w_bytes >= 2 * a_slot;
-          if (!res && 2 * (mg * a_slot + b_slot) > kSmemBudget) continue;
-          const double mma = (double)ntiles * taps * (kp.Cp / 16) * std::max(40, bn / 2);
-          const double a_bytes = (double)ngroups * (kp.Cp / kc) * (g.TW + g.R - 1) * g.TH * kc * 2;
-          const double ingest = ntiles * (a_bytes + (res ? 0.0 : (double)w_bytes / mg)) / 33.0;
-          const double commits = (double)ntiles * ngroups * (kp.Cp / kc) * 300.0 / mg;
-          const double cost = std::max(mma, ingest) + commits;
-          if (cost < best - 1.0) { best = cost; kp.kc = kc; kp.BN = bn; kp.MG = mg; mblock = true; }
-        }
-      }
+    if (em && atoi(em) == 0) c_mg = 0;                                                           // V2V_MG=0: off
+    const int a_slot = round_up((g.TW + g.R - 1) * g.TH * c_kc * 2, 1024), b_slot = round_up(g.R * c_bn * c_kc * 2, 1024);
+    if (c_mg >= 1 && kp.Cp % c_kc == 0 && c_bn % 32 == 0 && c_bn <= 128 && kp.tiles_x % c_mg == 0 &&
+        2 * c_mg * std::max(32, c_bn) <= 512 && 2 * (c_mg * a_slot + b_slot) <= kSmemBudget) {
+      kp.kc = c_kc; kp.BN = c_bn; kp.MG = c_mg; mblock = true;
     }
   }
   kp.cblocks = kp.Cp / kp.kc;
