@@ -200,7 +200,7 @@ def run_ours(args, rank, world, local_rank):
         return
 
     # ---- roofline of the conv kernel (per-launch CUDA events over one more frame)
-    conv_ms, conv_macs, other_ms, top = 0.0, 0.0, 0.0, {}
+    conv_ms, conv_macs, other_ms, top, conv_launches = 0.0, 0.0, 0.0, {}, 0
     kind_ms = {}
     for s in range(wl['n_scales']):
         net = getattr(model, 'netG%d' % s)
@@ -210,12 +210,20 @@ def run_ours(args, rank, world, local_rank):
                 if kind == 1:
                     conv_ms += ms
                     conv_macs += macs
+                    conv_launches += 1
                 else:
                     other_ms += ms
     peak_tf, peak_gbs, peak_src = peaks()
     achieved_tf = 2.0 * conv_macs / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     fmacs = frame_macs(args.workload)
     frame_ms = ms_dev / K
+    # DRAM bytes per conv launch: not measurable here (needs ncu); taken from the committed ncu capture of this command
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'conv_dram_traffic.json')))[args.workload]
+        traffic, traffic_src = tj['dram_bytes_per_launch_avg'], tj['source']
+    except Exception:
+        pass
     out = {
         'metric': 'frames/sec at 2048x1024 inference' if args.workload == 'cfg4' else 'frames/sec inference (%s)' % args.workload,
         'value': world * K / (ms_dev * 1e-3), 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
@@ -228,7 +236,11 @@ def run_ours(args, rank, world, local_rank):
         'gpu_launches': launches,
         'clocks': sampler.summary(),
         'roofline': {'bound': 'tensor', 'kernel': 'conv_umma_kernel (all launches of one frame)', 'achieved': achieved_tf,
-                     'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf, 'peak_source': peak_src, 'traffic': None,
+                     'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf, 'peak_source': peak_src, 'traffic': traffic,
+                     'traffic_unit': 'bytes per launch (dram read + write, ncu, mean over the launches of a frame)',
+                     'traffic_source': traffic_src, 'launches_per_frame': conv_launches,
+                     'algorithmic_flops_per_launch_avg': 2.0 * conv_macs / max(conv_launches, 1),
+                     'avg_launch_us': 1e3 * conv_ms / max(conv_launches, 1),
                      'conv_kernel_ms_per_frame': conv_ms, 'other_kernels_ms_per_frame': other_ms,
                      'ms_by_kernel_kind': {str(k): round(v, 4) for k, v in sorted(kind_ms.items())},
                      'frame_flops_over_frame_time_tflops': 2 * fmacs / (frame_ms * 1e-3) / 1e12},

@@ -23,6 +23,7 @@
 //                     Batch/InstanceNorm (deterministic: no atomics)
 //     EPI_HEAD_F32  : bias + tanh/sigmoid/scale -> fp32 NCHW planes (the 7x7 image/flow/weight heads)
 //     EPI_ACT_BF16  : bias + (leaky)ReLU -> interior of the next layer's padded NHWC buffer
+#include <cstdlib>
 #include "ptx.cuh"
 #include "v2v_internal.h"
 
@@ -237,6 +238,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_prologue();          // everything above overlaps the previous kernel's tail; nothing above touches global memory
 
   const int a_tx = p.PW * p.PH * p.row_bytes;
   const int b_tx = p.BN * p.row_bytes;
@@ -478,6 +480,13 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
+bool pdl_enabled() {
+  // opt-in (V2V_PDL=1): measured on cfg4 it is correct but slower (16.4 vs 15.6 ms/frame; cfg2 5.0 vs 4.6): the early-launched
+  // blocks of the elementwise kernels sit in griddepcontrol.wait holding thread slots the persistent conv CTAs then wait for
+  static const bool on = [] { const char* e = getenv("V2V_PDL"); return e && e[0] == '1'; }();
+  return on;
+}
+
 int device_sm_count() {
   static int n = 0;
   if (!n) {
@@ -500,8 +509,7 @@ cudaError_t launch_conv_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  conv_umma_kernel<<<p.grid, 64 + 128 * p.EG, smem, stream>>>(tmA, tmB, p);
-  return cudaGetLastError();
+  return launch_pdl(conv_umma_kernel, dim3(p.grid), dim3(64 + 128 * p.EG), smem, stream, tmA, tmB, p);
 }
 
 }  // namespace v2v

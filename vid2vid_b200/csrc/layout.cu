@@ -21,6 +21,7 @@ __device__ __forceinline__ int reflect_i(int i, int n) {
 template <int CT>
 __global__ void __launch_bounds__(256) import_nchw_kernel(ImportParams p) {
   __shared__ float tile[CT][129];
+  pdl_prologue();
   const float* src = reinterpret_cast<const float*>(p.io[p.slot]);
   const ActDesc& o = p.out;
   const int Wpad = o.W + o.pad_l + o.pad_r, Hpad = o.H + o.pad_t + o.pad_b;
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(256) import_nchw_kernel(ImportParams p) {
 // block (32, 8): tile of 128 x positions x 32 channels at one (n, y).
 __global__ void __launch_bounds__(256) export_nchw_kernel(ExportParams p) {
   __shared__ float tile[32][129];
+  pdl_prologue();
   float* dst = reinterpret_cast<float*>(p.io[p.slot]);
   const ActDesc& a = p.in;
   const int xt = blockIdx.x * 128;
@@ -131,10 +133,10 @@ cudaError_t launch_import_nchw(const ImportParams& p, cudaStream_t stream) {
   dim3 block(32, 8);
   if (o.C <= 16) {
     dim3 grid((Wpad + 127) / 128, Hpad * o.N, 1);
-    import_nchw_kernel<16><<<grid, block, 0, stream>>>(p);
+    return launch_pdl(import_nchw_kernel<16>, grid, block, 0, stream, p);
   } else {
     dim3 grid((Wpad + 127) / 128, Hpad * o.N, (o.C + 63) / 64);
-    import_nchw_kernel<64><<<grid, block, 0, stream>>>(p);
+    return launch_pdl(import_nchw_kernel<64>, grid, block, 0, stream, p);
   }
   return cudaGetLastError();
 }
@@ -142,8 +144,7 @@ cudaError_t launch_import_nchw(const ImportParams& p, cudaStream_t stream) {
 cudaError_t launch_export_nchw(const ExportParams& p, cudaStream_t stream) {
   const ActDesc& a = p.in;
   dim3 grid((a.W + 127) / 128, a.H * a.N, (a.Cvalid + 31) / 32), block(32, 8);
-  export_nchw_kernel<<<grid, block, 0, stream>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(export_nchw_kernel, grid, block, 0, stream, p);
 }
 
 cudaError_t launch_pack_weights(const PackParams& p, cudaStream_t stream) {

@@ -21,6 +21,7 @@ __device__ __forceinline__ double warp_sum_d(double v) {
 
 // One warp per channel (4 channels per block): lanes stride the per-CTA partial rows, fp64 shuffle reduction.
 __global__ void __launch_bounds__(128) stats_finalize_kernel(FinalizeParams p) {
+  pdl_prologue();
   const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (c >= p.C) return;
@@ -138,6 +139,7 @@ __device__ __forceinline__ void apply_item(const ApplyParams& p, int vecs, int W
 }
 
 __global__ void __launch_bounds__(256) norm_apply_kernel(ApplyParams p) {
+  pdl_prologue();
   const int vecs = p.out.C / 8;
   const int Hpad = p.out.H + p.out.pad_t + p.out.pad_b, Wpad = p.out.W + p.out.pad_l + p.out.pad_r;
   const unsigned total = (unsigned)p.out.N * Hpad * Wpad * vecs;        // < 2^31 checked by the launcher
@@ -171,6 +173,7 @@ __device__ __forceinline__ size_t row_off(const RowAddr& r, int x) {            
 
 template <int NADD>
 __global__ void __launch_bounds__(256) norm_apply_rows_kernel(ApplyParams p, int xt, int ppb) {
+  pdl_prologue();
   const int vecs = p.out.C >> 3;
   const int t = threadIdx.x;
   if (t >= ppb * vecs) return;
@@ -381,8 +384,7 @@ static inline int grid_for(long long total, int block) {
 }
 
 cudaError_t launch_stats_finalize(const FinalizeParams& p, cudaStream_t stream) {
-  stats_finalize_kernel<<<(p.C + 3) / 4, 128, 0, stream>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(stats_finalize_kernel, dim3((p.C + 3) / 4), dim3(128), 0, stream, p);
 }
 
 cudaError_t launch_norm_apply(const ApplyParams& p, cudaStream_t stream) {
@@ -403,11 +405,11 @@ cudaError_t launch_norm_apply(const ApplyParams& p, cudaStream_t stream) {
       const int ppb = 256 / vecs;                     // pixels per block pass
       const int xt = ppb * 8;                         // 8 items per thread
       dim3 grid((Wpad + xt - 1) / xt, p.out.N * Hpad);
-      if (p.n_add == 0) norm_apply_rows_kernel<0><<<grid, 256, 0, stream>>>(p, xt, ppb);
-      else if (p.n_add == 1) norm_apply_rows_kernel<1><<<grid, 256, 0, stream>>>(p, xt, ppb);
-      else norm_apply_rows_kernel<2><<<grid, 256, 0, stream>>>(p, xt, ppb);
+      if (p.n_add == 0) return launch_pdl(norm_apply_rows_kernel<0>, grid, dim3(256), 0, stream, p, xt, ppb);
+      if (p.n_add == 1) return launch_pdl(norm_apply_rows_kernel<1>, grid, dim3(256), 0, stream, p, xt, ppb);
+      return launch_pdl(norm_apply_rows_kernel<2>, grid, dim3(256), 0, stream, p, xt, ppb);
     } else {
-      norm_apply_kernel<<<grid_for(total, 256), 256, 0, stream>>>(p);
+      return launch_pdl(norm_apply_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, p);
     }
   }
   return cudaGetLastError();

@@ -183,4 +183,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return *reinterpret_cast<uint32_t*>(&v);
 }
 
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor is still running; griddepcontrol.wait blocks until every prerequisite grid has completed and
+// its memory is visible (a no-op for a normal launch), launch_dependents lets the NEXT kernel in the stream begin its
+// own prologue.  Every kernel of a plan calls pdl_prologue() before its first global-memory access, so the chain is
+// transitively ordered and only launch latency / prologues (barrier init, TMEM allocation) overlap.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 }  // namespace v2v

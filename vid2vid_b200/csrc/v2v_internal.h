@@ -192,4 +192,19 @@ cudaError_t launch_pack_weights(const PackParams& p, cudaStream_t stream);
 cudaError_t launch_composite(const CompositeParams& p, cudaStream_t stream);
 int device_sm_count();
 
+
+// Host side of PDL: launch with the programmatic-stream-serialization attribute (captured into the CUDA graph as a
+// programmatic dependency) when V2V_PDL=1; plain serialised launches otherwise (the default, see pdl_enabled()).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 }  // namespace v2v

@@ -47,6 +47,7 @@ __device__ __forceinline__ float bilerp(const float* pl, const Bilerp& b, int W)
 }
 
 __global__ void composite_kernel(CompositeParams p) {
+  pdl_prologue();
   const size_t HW = (size_t)p.H * p.W;
   const size_t total = (size_t)p.N * HW;
   float* raw = reinterpret_cast<float*>(p.io[p.s_raw]);          // in: tanh head output; out: composited
@@ -116,7 +117,7 @@ static inline int grid1d(size_t total) {
 }
 
 cudaError_t launch_composite(const CompositeParams& p, cudaStream_t stream) {
-  composite_kernel<<<grid1d((size_t)p.N * p.H * p.W), 256, 0, stream>>>(p);
+  return launch_pdl(composite_kernel, dim3(grid1d((size_t)p.N * p.H * p.W)), dim3(256), 0, stream, p);
   return cudaGetLastError();
 }
 
