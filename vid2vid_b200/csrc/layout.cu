@@ -42,15 +42,24 @@ __global__ void __launch_bounds__(256) import_nchw_kernel(ImportParams p) {
     xs[sx] = x;
     zero_px[sx] = (xp >= Wpad) || ((yhalo || xhalo) && p.pad_mode != PAD_REFLECT);
   }
-  for (int cc = threadIdx.y; cc < CT; cc += 8) {
-    const int c = cblk + cc;
-    const bool cv = c < o.Cvalid;
-    const float* row = src + (((size_t)n * p.C_src + p.c_off + (cv ? c : 0)) * o.H + y) * o.W;
-    float v[4];
+  // two channels per pass: 8 independent 4-byte loads in flight per thread (one channel per pass left the kernel
+  // latency bound at ~50 % of the HBM rate)
+  for (int cc = threadIdx.y; cc < CT; cc += 16) {
+    float v[2][4];
 #pragma unroll
-    for (int sx = 0; sx < 4; ++sx) v[sx] = (cv && !zero_px[sx]) ? __ldg(row + xs[sx]) : 0.f;
+    for (int h = 0; h < 2; ++h) {
+      const int c = cblk + cc + 8 * h;
+      const bool cv = (cc + 8 * h < CT) && c < o.Cvalid;
+      const float* row = src + (((size_t)n * p.C_src + p.c_off + (cv ? c : 0)) * o.H + y) * o.W;
 #pragma unroll
-    for (int sx = 0; sx < 4; ++sx) tile[cc][sx * 32 + threadIdx.x] = v[sx];
+      for (int sx = 0; sx < 4; ++sx) v[h][sx] = (cv && !zero_px[sx]) ? __ldg(row + xs[sx]) : 0.f;
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (cc + 8 * h < CT) {
+#pragma unroll
+        for (int sx = 0; sx < 4; ++sx) tile[cc + 8 * h][sx * 32 + threadIdx.x] = v[h][sx];
+      }
   }
   __syncthreads();
   // write: lane -> channel pair (CT = 64) or (pixel parity, channel pair) (CT = 16)
@@ -84,6 +93,7 @@ __global__ void __launch_bounds__(256) export_nchw_kernel(ExportParams p) {
   const int cblk = blockIdx.z * 32;
   // read: lane -> channel pair (16 pairs) x 2 pixels
   const int cp = threadIdx.x & 15, sub = threadIdx.x >> 4;
+#pragma unroll
   for (int px = threadIdx.y * 2 + sub; px < 128; px += 16) {
     const int x = xt + px, c = cblk + 2 * cp;
     float2 v = make_float2(0.f, 0.f);
