@@ -108,6 +108,28 @@ struct MmaCtx {
   int group_bytes, b_tx, NS, t_first, t_step;
 };
 
+
+template <bool kWarpWide, int KMMA>
+__device__ __forceinline__ void issue_taps(const ConvKernelParams& p, uint32_t tmem_d, uint32_t al, uint32_t bl, uint32_t a_hi,
+                                           uint32_t b_hi, uint32_t idesc, uint32_t first, uint32_t a_step, uint32_t b_step,
+                                           uint32_t a_wrap) {
+  const int RW = p.RW;
+  for (int r0 = 0; r0 < p.R; r0 += RW, al += a_wrap) {
+    for (int r = 0; r < RW; ++r, al += a_step, bl += b_step) {
+      if (kWarpWide ? elect_one_sync() : true) {
+        const uint64_t ad = ((uint64_t)a_hi << 32) | al, bd = ((uint64_t)b_hi << 32) | bl;
+        umma_bf16(tmem_d, ad, bd, idesc, first);
+        if (KMMA >= 2) umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
+        if (KMMA >= 4) {
+          umma_bf16(tmem_d, ad + 4, bd + 4, idesc, 1u);
+          umma_bf16(tmem_d, ad + 6, bd + 6, idesc, 1u);
+        }
+      }
+      first = 1u;
+    }
+  }
+}
+
 // The tcgen05.mma issue loop.  kWarpWide = false: called by ONE elected lane, which runs the whole loop (no re-election
 // or warp synchronisation on the issue path; descriptors live in vector registers and are moved to uniform registers
 // per MMA).  kWarpWide = true: all 32 lanes walk the loop in lock step, so ptxas can keep the descriptor arithmetic on
@@ -160,26 +182,11 @@ __device__ __forceinline__ void mma_role(const ConvKernelParams& p, const MmaCtx
           uint32_t first = (s0 + i) > 0 ? 1u : 0u;
           uint32_t al = a_lo0 + ((a_base & 0x3FFFF) >> 4), bl = bl0;
           // tap r reads the patch shifted by (r / RW) patch rows and (r % RW) pixels; K = 16 bf16 = 32 bytes per MMA,
-          // kc/16 MMAs per smem row (fixed trip counts keep the issue loop tight)
-          for (int r0 = 0; r0 < p.R; r0 += p.RW, al += a_wrap) {
-            for (int r = 0; r < p.RW; ++r, al += a_step, bl += b_step) {
-              if (kWarpWide ? elect_one_sync() : true) {
-                const uint64_t ad = ((uint64_t)a_hi << 32) | al, bd = ((uint64_t)b_hi << 32) | bl;
-                if (p.kmma == 4) {
-                  umma_bf16(tmem_d, ad, bd, idesc, first);
-                  umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
-                  umma_bf16(tmem_d, ad + 4, bd + 4, idesc, 1u);
-                  umma_bf16(tmem_d, ad + 6, bd + 6, idesc, 1u);
-                } else if (p.kmma == 2) {
-                  umma_bf16(tmem_d, ad, bd, idesc, first);
-                  umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
-                } else {
-                  umma_bf16(tmem_d, ad, bd, idesc, first);
-                }
-              }
-              first = 1u;
-            }
-          }
+          // kc/16 MMAs per smem row.  The trip-count switch sits outside the tap loops: the issuing thread has ~40
+          // cycles per MMA for small-N layers, every instruction in the loop body counts.
+          if (p.kmma == 4) issue_taps<kWarpWide, 4>(p, tmem_d, al, bl, a_hi, b_hi, idesc, first, a_step, b_step, a_wrap);
+          else if (p.kmma == 2) issue_taps<kWarpWide, 2>(p, tmem_d, al, bl, a_hi, b_hi, idesc, first, a_step, b_step, a_wrap);
+          else issue_taps<kWarpWide, 1>(p, tmem_d, al, bl, a_hi, b_hi, idesc, first, a_step, b_step, a_wrap);
         }
       }
       if (kWarpWide ? elect_one_sync() : true) {

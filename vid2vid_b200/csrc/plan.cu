@@ -89,9 +89,6 @@ static bool choose_patch2d(const v2v_conv_desc& c, bool head, int N, int grid_h,
   const long long m_total = tiles * N;
   const int sms = device_sm_count();
   const int kc_max = std::min(Cp, 64);
-  // 7x7 filters over <= 32 channels: 49 taps of 32/64-byte rows from one patch were slower than row tiles (per frame:
-  // 32->3 heads 0.85 vs 0.77 ms, 16->3 0.35 vs 0.27, 6->32 stem 0.33 vs 0.27), while 64->3 gained (0.31 vs 0.38)
-  if (taps > 9 && kc_max < 64) return false;
   // (1) resident weights with the natural N tile, (2) with a halved N tile when a CTA walks >= 4 M tiles (streaming the
   // weights again for every tile costs more L2 traffic than the second pass over the activations)
   for (int pass = 0; pass < 2; ++pass) {
