@@ -111,6 +111,17 @@ class ClockSampler(threading.Thread):
                 'samples': len(sm)}
 
 
+def reduce_times(times_ms, world, device='cpu'):
+    """Device-timed durations -> the slowest rank's (replicas finish when the last one does).  One all-reduce(MAX) on the
+    job's process group (NCCL on the GPU box, gloo in the CPU tests); the data path itself has no collective."""
+    import torch
+    t = torch.tensor(list(times_ms), device=device, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
 def peaks():
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
@@ -192,10 +203,7 @@ def run_ours(args, rank, world, local_rank):
     h2d = 2 * tG * wl['H'] * wl['W'] * 4
     d2h = 3 * wl['H'] * wl['W'] * 4
 
-    times = torch.tensor([ms_dev, ms_e2e], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    ms_dev, ms_e2e = times.tolist()
+    ms_dev, ms_e2e = reduce_times([ms_dev, ms_e2e], world, dev)
     if rank != 0:
         return
 

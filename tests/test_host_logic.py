@@ -163,6 +163,38 @@ def test_plan_describe_layouts():
     assert any(c['R'] == 7 for c in convs) and any(c['phases'] == 4 for c in convs)
 
 
+def _cfg4_convs(scale, h, w):
+    from vid2vid_b200.plan import Plan
+    g = NW.build_netG(_street_opt(n_scales_spatial=3), scale)
+    p = Plan(0)
+    g._describe(p, 1, h, w)
+    return p.describe()['convs']
+
+
+def test_kernel_configuration_choices():
+    """The tiling / K-block / M-blocking decisions DESIGN.md describes, as the lowering makes them for cfg4."""
+    def pick(convs, **kw):
+        out = [c for c in convs if all(c[k] == v for k, v in kw.items())]
+        assert out, kw
+        return out
+    c0, c2 = _cfg4_convs(0, 256, 512), _cfg4_convs(2, 1024, 2048)
+    # 1024->1024 3x3 @32x64: 2-D patch (16x8 tiles, all 9 taps from one patch), weights streamed in 32-channel K blocks
+    for c in pick(c0, Cin=1024, Cout=1024):
+        assert (c['TH'], c['TW'], c['R'], c['kc'], c['BN'], c['resident'], c['MG']) == (16, 8, 9, 32, 128, 0, 1)
+        assert c['units'] == 128                       # 16 M tiles x 8 N tiles: one wave on 148 SMs
+    # 64->64 3x3 @512x1024: 2-D patch with resident weights
+    for c in pick(c2, Cin=64, Cout=64, stride=1):
+        assert (c['TH'], c['TW'], c['R'], c['kc'], c['resident']) == (16, 8, 9, 64, 1)
+    # the 7x7 stems over the 108-channel input: row tiles, streamed weights, 2 x-adjacent tiles per weight pass
+    for c in pick(c2, Cin=108, Cout=48) + pick(c0, Cin=108, Cout=192):
+        assert (c['TH'], c['TW'], c['R'], c['MG'], c['resident'], c['BN'], c['kc']) == (1, 128, 7, 2, 0, 64, 64)
+    for c in pick(_cfg4_convs(1, 512, 1024), Cin=108, Cout=96):
+        assert (c['MG'], c['BN'], c['kc']) == (2, 96, 32)          # exact N tile for 96 output channels
+    # every configuration respects the TMEM budget: 2 stages x MG accumulators x max(32, BN) columns <= 512
+    for c in c0 + c2:
+        assert 2 * c['MG'] * max(32, c['BN']) <= 512 and c['EG'] in (1, 2) and c['CG'] >= 1 and c['SG'] >= 2
+
+
 def test_conv_macs_discriminators():
     """image D (39 ch) 42.54 GMAC and temporal D (13 ch) 37.93 GMAC per forward at 1024x512, num_D 3."""
     from vid2vid_b200.plan import Plan
