@@ -444,6 +444,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // 16 * (l / 16) .. +15 (banks 17 r + 16 (l / 16) + l % 16: conflict free) and one xor-16 shuffle joins
             // the two half sums.  Lanes 0-15 keep the first pass, lanes 16-31 the second: lane l owns column l.
             float s_keep = 0.f, q_keep = 0.f;
+            if (p.dbg & 16) {
+              // register-only variant (recursive-halving shuffles, 2 x 31 per chunk): no shared-memory traffic, which
+              // the tensor core's operand reads compete for in the small-N layers
+              float v2[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v2[j] = v[j] * v[j];
+              s_keep = warp_transpose_reduce(v, lane);
+              q_keep = warp_transpose_reduce(v2, lane);
+            } else
 #pragma unroll
             for (int h2 = 0; h2 < 2; ++h2) {
               __syncwarp();
