@@ -488,11 +488,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if ((p.dbg & 4) && blockIdx.x == 0 && threadIdx.x == 0) {
     const long long t0 = g_trace[0][0][0];
     for (int it = 0; it < 24; ++it)
-      printf("trace it=%2d prod: start %6lld issued %6lld | mma: start %6lld tmem_empty %6lld first_a %6lld [p1 top %6lld waited %6lld fenced %6lld descs %6lld] done %6lld | epi: start %6lld full %6lld ld0 %6lld stored %6lld stats %6lld bar %6lld done %6lld\n", it,
-             g_trace[0][it][0] - t0, g_trace[0][it][2] - t0, g_trace[1][it][0] - t0, g_trace[1][it][1] - t0, g_trace[1][it][2] - t0,
-             g_trace[1][it][4] - t0, g_trace[1][it][5] - t0, g_trace[1][it][6] - t0, g_trace[1][it][7] - t0,
-             g_trace[1][it][3] - t0, g_trace[2][it][0] - t0, g_trace[2][it][1] - t0, g_trace[2][it][3] - t0, g_trace[2][it][4] - t0,
-             g_trace[2][it][5] - t0, g_trace[2][it][6] - t0, g_trace[2][it][2] - t0);
+      printf("trace it=%2d prod: start %6lld issued %6lld | mma: start %6lld tmem_empty %6lld first_a %6lld done %6lld | "
+             "epi: start %6lld full %6lld ld(last tile) %6lld stored %6lld stats %6lld done %6lld\n", it,
+             g_trace[0][it][0] - t0, g_trace[0][it][2] - t0, g_trace[1][it][0] - t0, g_trace[1][it][1] - t0,
+             g_trace[1][it][2] - t0, g_trace[1][it][3] - t0, g_trace[2][it][0] - t0, g_trace[2][it][1] - t0,
+             g_trace[2][it][3] - t0, g_trace[2][it][4] - t0, g_trace[2][it][5] - t0, g_trace[2][it][2] - t0);
   }
 }
 
