@@ -130,10 +130,43 @@ def dump_keys():
     print('state_dict_keys.json', {k: len(v) for k, v in out.items()})
 
 
+def flownet2_golden():
+    """Reference FlowNet2 (with the op stand-ins of ref_shim.install_flownet2_ops) and the FlowNet wrapper's
+    compute_flow_and_conf on seeded inputs, with the deterministic weights of flownet2_oracle.det_state_dict ->
+    tests/golden/flownet2_keys.json + flownet2_small.npz."""
+    import json
+    import types
+    from oracle import flownet2_oracle as FO
+    F2 = ref_shim.flownet2_class()
+    net = F2().eval()
+    keys = [[k, list(v.shape)] for k, v in net.state_dict().items()]
+    with open(os.path.join(OUT, 'flownet2_keys.json'), 'w') as f:
+        json.dump(keys, f)
+    net.load_state_dict(FO.det_state_dict(keys, seed=7))
+    g = torch.Generator().manual_seed(11)
+    pair = torch.rand(1, 3, 2, 64, 128, generator=g)
+    base = torch.rand(1, 3, 80, 64, generator=g)                    # height 80: exercises the resize-to-64 path
+    im1, im2 = base, torch.roll(base, shifts=(1, 2), dims=(2, 3)) * 0.9 + 0.05
+    from models.flownet import FlowNet                              # noqa (reference module)
+    from models.flownet2_pytorch.networks.resample2d_package.resample2d import Resample2d   # noqa
+    stub = types.SimpleNamespace(flowNet=net, resample=Resample2d())
+    stub.norm = lambda t: FlowNet.norm(stub, t)
+    with torch.no_grad():
+        flow = net(pair)
+        wflow, wconf = FlowNet.compute_flow_and_conf(stub, im1, im2)
+    out = dict(pair=_np(pair), flow=_np(flow), im1=_np(im1), im2=_np(im2), wflow=_np(wflow), wconf=_np(wconf))
+    path = os.path.join(OUT, 'flownet2_small.npz')
+    np.savez_compressed(path, **out)
+    print('flownet2_small %7.1f KB flow rms %.3f wflow rms %.3f conf mean %.3f' % (
+        os.path.getsize(path) / 1024, float(flow.pow(2).mean().sqrt()), float(wflow.pow(2).mean().sqrt()), float(wconf.mean())))
+
+
 if __name__ == '__main__':
     names = sys.argv[1:] or (list(C.CASES) + ['keys'])
     for n in names:
         if n == 'keys':
             dump_keys()
+        elif n == 'flownet2':
+            flownet2_golden()
         else:
             run_case(n, C.CASES[n])

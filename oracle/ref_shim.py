@@ -79,3 +79,58 @@ def make_model_G(opt, single_G=None):
     with contextlib.redirect_stdout(io.StringIO()):
         m.initialize(opt)
     return m
+
+
+def install_flownet2_ops():
+    """Harness-level stand-ins for the three pybind11 extensions the reference's FlowNet2 imports (`correlation_cuda`,
+    `resample2d_cuda`, `channelnorm_cuda`: CUDA only, they do not build against the installed torch): the same
+    `forward(...)` entry points, computed by oracle/flowops_oracle.c on CPU tensors.  Also replaces
+    `Correlation.forward`, which instantiates a legacy (non-static) autograd Function that current PyTorch refuses to
+    run (networks/correlation_package/correlation.py:6-30,56-60); the replacement performs the identical single call.
+    No reference arithmetic outside those extensions is touched."""
+    install()
+    import types
+    import numpy as np
+    import torch
+    from oracle import flowops
+
+    def _np(t):
+        return np.ascontiguousarray(t.detach().cpu().numpy(), dtype=np.float32)
+
+    corr = types.ModuleType('correlation_cuda')
+
+    def corr_forward(in1, in2, rbot1, rbot2, out, pad, k, max_disp, s1, s2, corr_type):
+        r = torch.from_numpy(flowops.correlation(_np(in1), _np(in2), pad, k, max_disp, s1, s2))
+        out.resize_(r.shape).copy_(r)
+        return 1
+    corr.forward = corr_forward
+    res = types.ModuleType('resample2d_cuda')
+
+    def res_forward(in1, in2, out, kernel_size):
+        out.copy_(torch.from_numpy(flowops.resample2d(_np(in1), _np(in2), kernel_size)))
+        return 1
+    res.forward = res_forward
+    cn = types.ModuleType('channelnorm_cuda')
+
+    def cn_forward(in1, out, norm_deg):
+        out.copy_(torch.from_numpy(flowops.channelnorm(_np(in1), norm_deg)))
+        return 1
+    cn.forward = cn_forward
+    sys.modules.setdefault('correlation_cuda', corr)
+    sys.modules.setdefault('resample2d_cuda', res)
+    sys.modules.setdefault('channelnorm_cuda', cn)
+
+    from models.flownet2_pytorch.networks.correlation_package import correlation as ref_corr   # noqa (reference module)
+
+    def forward(self, input1, input2):
+        out = input1.new()
+        sys.modules['correlation_cuda'].forward(input1, input2, input1.new(), input2.new(), out, self.pad_size, self.kernel_size,
+                                                self.max_displacement, self.stride1, self.stride2, self.corr_multiply)
+        return out
+    ref_corr.Correlation.forward = forward
+
+
+def flownet2_class():
+    install_flownet2_ops()
+    from models.flownet2_pytorch import models as ref_models   # noqa (reference module)
+    return ref_models.FlowNet2
