@@ -371,3 +371,54 @@ class ModelGOracle:
             feats = (out[4], out[5], out[6])
             self.fake_B_prev[si] = torch.cat([self.fake_B_prev[si][1:], fake_B])  # :228
         return fake_B, pyr[0][0, -1]
+
+    def _generate(self, s, a, prevs, mask, feats, raw_only):
+        opt = self.opt
+        if s == 0:
+            return composite_generator(self.sds[0], a, prevs, mask, raw_only, n_downsampling=opt.n_downsample_G,
+                                       n_blocks=opt.n_blocks, use_fg_model=opt.fg, no_flow=opt.no_flow, norm=opt.norm,
+                                       align_corners=self.align_corners)
+        return composite_local_generator(self.sds[s], a, prevs, mask, feats[0], feats[1], feats[2], raw_only,
+                                         n_blocks_local=opt.n_blocks_local, use_fg_model=opt.fg, no_flow=opt.no_flow,
+                                         norm=opt.norm, scale=s, align_corners=self.align_corners)
+
+    def train_forward(self, input_A, input_B, inst_A, fake_B_prev=None, n_frames_load=1):
+        """Vid2VidModelG.forward in training (vid2vid_model_G.py:114-140) with generate_frame_train (:142-196) and the
+        training branch of generate_first_frame (:231-251), single process (no GPU pipeline, dummy_bs = 0), forward
+        values only (detach points do not change them).  input_A / inst_A: (b, n_frames_load + tG - 1, 1, H, W) label
+        and instance ids, input_B: the real frames.  Returns the reference's 7-tuple: fake_B (b, n_frames_load, 3, H, W),
+        fake_B_raw, flow, weight, real_A[:, tG-1:], real_B[:, tG-2:], fake_B_prev pyramid for the next call."""
+        opt = self.opt
+        tG = opt.n_frames_G
+        real_A = encode_input(input_A, inst_A, opt.label_nc, opt.use_instance)
+        b = real_A.size(0)
+        first = fake_B_prev is None
+        if first:                                                                 # :231-248
+            if opt.no_first_img:
+                prev = torch.zeros(b, tG - 1, opt.output_nc, real_A.size(3), real_A.size(4))
+            else:
+                prev = input_B[:, :tG - 1]                                         # training: the first frames are given
+            fake_B_prev = build_pyr(prev, self.n_scales)
+        pyr_B = [p for p in fake_B_prev]
+        pyr_A = build_pyr(real_A, self.n_scales)                                  # :151
+        raws, flows, weights = [], [], []
+        for t in range(n_frames_load):                                            # :155
+            feats = (None, None, None)
+            for s in range(self.n_scales):                                        # :161-162
+                si = self.n_scales - 1 - s
+                rA = pyr_A[si]
+                h, w = rA.shape[-2:]
+                a = rA[:, t:t + tG].reshape(b, -1, h, w)                          # :167
+                prevs = pyr_B[si][:, t:t + tG - 1].reshape(b, -1, h, w)           # :170-173
+                mask = compute_mask(rA, t + tG - 1, opt.fg_labels) if opt.fg else None   # :176
+                out = self._generate(s, a, prevs, mask, feats, opt.no_first_img and first)
+                feats = (out[4], out[5], out[6])
+                pyr_B[si] = torch.cat([pyr_B[si], out[0].unsqueeze(1)], dim=1)     # :191
+                if s == self.n_scales - 1:                                        # :192-196
+                    raws.append(out[3].unsqueeze(1))
+                    if out[1] is not None:
+                        flows.append(out[1].unsqueeze(1))
+                        weights.append(out[2].unsqueeze(1))
+        cat = lambda l: torch.cat(l, dim=1) if l else None
+        next_prev = [B[:, -tG + 1:] for B in pyr_B]                               # :137
+        return (pyr_B[0][:, tG - 1:], cat(raws), cat(flows), cat(weights), real_A[:, tG - 1:], input_B[:, tG - 2:], next_prev)

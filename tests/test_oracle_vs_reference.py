@@ -10,6 +10,7 @@ import torch
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), '..'))
 from oracle import ref_shim, generator_oracle as GO          # noqa: E402
 from vid2vid_b200.utils import make_opt, det_fill_, synth_label_sequence   # noqa: E402
+import cases                                                  # noqa: E402
 
 pytestmark = pytest.mark.skipif(not ref_shim.available(), reason='reference tree not mounted')
 
@@ -105,3 +106,40 @@ def test_model_G_inference_multiscale():
         o_B, o_A = orc.inference(A, A)
         _close(ref_B, o_B)
         _close(ref_A, o_A)
+
+
+@pytest.mark.parametrize('no_first_img', [False, True])
+def test_model_G_training_forward(no_first_img):
+    """Vid2VidModelG.forward / generate_frame_train (vid2vid_model_G.py:114-196): two frames per call, two calls (the
+    second continues from the returned fake_B_prev pyramid), two spatial scales, foreground branch.  Batch 1, as the
+    reference trains: its build_pyr `.view`s a time slice of the clip, which only works for one clip per batch."""
+    opt = make_opt(label_nc=5, use_instance=True, fg=True, fg_labels=[2], n_scales_spatial=2, ngf=8, n_blocks=2,
+                   n_blocks_local=1, n_downsample_G=2, gpu_ids=[0], n_gpus_gen=1, isTrain=True, no_first_img=no_first_img,
+                   max_frames_per_gpu=2, batchSize=1, dataroot='City')
+    m = ref_shim.make_model_G(opt)
+    assert m.n_frames_load == 2
+    det_fill_(m.netG0, seed=20)
+    det_fill_(m.netG1, seed=21)
+    cases.condition_flow_heads(m.netG0, 0.05)
+    cases.condition_flow_heads(m.netG1, 0.05)
+    orc = GO.ModelGOracle(opt, [m.netG0.state_dict(), m.netG1.state_dict()])
+    tG, T = opt.n_frames_G, 2 * 2 + opt.n_frames_G - 1
+    seq = synth_label_sequence(T, 32, 64, label_nc=5, block=4, seed=4)
+    g = torch.Generator().manual_seed(6)
+    real = torch.rand(1, T, 3, 32, 64, generator=g) * 2 - 1
+    prev_ref = prev_orc = None
+    for call in range(2):
+        sl = slice(call * 2, call * 2 + 2 + tG - 1)
+        with torch.no_grad():
+            A, B = seq[:, sl].contiguous(), real[:, sl].contiguous()     # the data loader hands over contiguous clips
+            r = m.forward(A, B, A, prev_ref)
+            o = orc.train_forward(A, B, A, prev_orc, n_frames_load=2)
+        for name, a, b in zip(['fake_B', 'fake_B_raw', 'flow', 'weight', 'real_A', 'real_B'], r[:6], o[:6]):
+            assert (a is None) == (b is None), name
+            if a is not None:
+                assert a.shape == b.shape, (name, a.shape, b.shape)
+                _close(a, b)
+        assert r[0].shape == (1, 2, 3, 32, 64)
+        for a, b in zip(r[6], o[6]):
+            _close(a, b)
+        prev_ref, prev_orc = r[6], o[6]
