@@ -143,3 +143,36 @@ def test_model_G_training_forward(no_first_img):
         for a, b in zip(r[6], o[6]):
             _close(a, b)
         prev_ref, prev_orc = r[6], o[6]
+
+
+def test_oracle_gradients_match_reference():
+    """The oracle is plain differentiable PyTorch over the state_dict tensors, so autograd through it is the CPU
+    reference for the backward kernels (dgrad / wgrad / norm / warp) of the training rows: for one scalar objective
+    built from every output of the coarse generator, d/d(parameters), d/d(previous frames) and d/d(input) must agree
+    with the gradients the reference module produces."""
+    N = ref_shim.networks()
+    opt = make_opt(ngf=8, n_blocks=2, fg=True, n_downsample_G=2, gpu_ids=[])
+    net = det_fill_(N.define_G(18, 3, 6, 8, 'composite', 2, 'batch', 0, [], opt), seed=31)
+    cases.condition_flow_heads(net, 0.05)
+    inp, img_prev, mask = _inputs(6, 16, 32, seed=2)
+    g = torch.Generator().manual_seed(9)
+
+    def objective(outs, cot):
+        return sum((o * c).sum() for o, c in zip(outs, cot) if o is not None)
+
+    x_r, p_r = inp.clone().requires_grad_(True), img_prev.clone().requires_grad_(True)
+    ref = net(x_r, p_r, mask, None, None, None, False)
+    cot = [torch.randn(o.shape, generator=g) if o is not None else None for o in ref]
+    objective(ref, cot).backward()
+    ref_grads = {k: v.grad.clone() for k, v in net.named_parameters()}
+
+    sd = {k: v.detach().clone().requires_grad_(v.dtype.is_floating_point and k in ref_grads) for k, v in net.state_dict().items()}
+    x_o, p_o = inp.clone().requires_grad_(True), img_prev.clone().requires_grad_(True)
+    out = GO.composite_generator(sd, x_o, p_o, mask, False, n_downsampling=2, n_blocks=2, use_fg_model=True)
+    objective(out, cot).backward()
+    for k, gr in ref_grads.items():
+        scale = max(1.0, float(gr.abs().max()))
+        assert sd[k].grad is not None, k
+        assert float((sd[k].grad - gr).abs().max()) <= 2e-4 * scale, (k, float((sd[k].grad - gr).abs().max()), scale)
+    for a, b in ((x_o.grad, x_r.grad), (p_o.grad, p_r.grad)):
+        assert float((a - b).abs().max()) <= 2e-4 * max(1.0, float(b.abs().max()))
