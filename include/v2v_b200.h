@@ -35,6 +35,13 @@ enum { V2V_PAD_NONE = 0, V2V_PAD_ZERO = 1, V2V_PAD_REFLECT = 2 };
 enum { V2V_ACT_NONE = 0, V2V_ACT_RELU = 1, V2V_ACT_LRELU = 2, V2V_ACT_TANH = 3, V2V_ACT_SIGMOID = 4 };
 enum { V2V_NORM_NONE = 0, V2V_NORM_BATCH = 1, V2V_NORM_INSTANCE = 2 };
 enum { V2V_IMPL_UMMA = 0, V2V_IMPL_SIMT = 1 };
+/* Arithmetic of the convolution stack (accumulation is fp32 in both):
+ *   V2V_PREC_BF16    operands rounded to bf16, one tcgen05.mma per K block ("fast"; ~2^-9 relative operand error)
+ *   V2V_PREC_BF16X3  fp32-class: every operand x is carried as hi = bf16(x), lo = bf16(x - hi) and the kernel accumulates
+ *                    A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (three MMAs per K block, ~2^-17 relative); raw conv outputs and
+ *                    norm statistics stay fp32.  This is the mode whose results are compared with the fp32 reference
+ *                    (nn.Conv2d in fp32, models/networks.py:132-183) at a stated fp32-class tolerance. */
+enum { V2V_PREC_BF16 = 0, V2V_PREC_BF16X3 = 1 };
 
 int v2v_version(void);
 const char* v2v_last_error(void);
@@ -133,6 +140,8 @@ typedef struct v2v_head_channel {
 
 int v2v_plan_create(int device, int conv_impl /* V2V_IMPL_* */, v2v_plan** out);
 int v2v_plan_destroy(v2v_plan* plan);
+/* Select V2V_PREC_* (default V2V_PREC_BF16); must precede the first v2v_g_* call. */
+int v2v_plan_set_precision(v2v_plan* plan, int precision);
 
 /* Channels [c_off, c_off + C) of the fp32 NCHW tensor (N, C_src, H, W) bound to IO slot `slot`. */
 int v2v_g_input(v2v_plan* plan, int slot, int N, int C_src, int c_off, int C, int H, int W, int* value_out);

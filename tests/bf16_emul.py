@@ -10,7 +10,12 @@ from vid2vid_b200 import networks as NW
 from vid2vid_b200 import _lib as L
 
 
+ROUND = [True]      # False: no rounding anywhere and fp64 arithmetic -- the exact reference the precise mode is compared with
+
+
 def r16(t):
+    if not ROUND[0]:
+        return t.double()
     return t.to(torch.bfloat16).to(torch.float32)
 
 
@@ -28,7 +33,7 @@ def _act(x, act, slope):
 
 def _conv(x, conv, pmode, pad, with_bias):
     w = r16(conv.weight.detach().float())
-    b = conv.bias.detach().float() if (with_bias and conv.bias is not None) else None
+    b = conv.bias.detach().to(w.dtype) if (with_bias and conv.bias is not None) else None
     if isinstance(conv, nn.ConvTranspose2d):
         return F.conv_transpose2d(x, w, b, stride=conv.stride, padding=conv.padding, output_padding=conv.output_padding)
     if pmode == L.PAD_REFLECT and pad:
@@ -41,7 +46,7 @@ def _norm(raw, norm):
     if isinstance(norm, nn.BatchNorm2d):
         mean = raw.mean(dim=(0, 2, 3), keepdim=True)
         var = raw.var(dim=(0, 2, 3), unbiased=False, keepdim=True)
-        g, b = norm.weight.detach().view(1, -1, 1, 1), norm.bias.detach().view(1, -1, 1, 1)
+        g, b = norm.weight.detach().view(1, -1, 1, 1).to(raw.dtype), norm.bias.detach().view(1, -1, 1, 1).to(raw.dtype)
     else:
         mean = raw.mean(dim=(2, 3), keepdim=True)
         var = raw.var(dim=(2, 3), unbiased=False, keepdim=True)

@@ -14,13 +14,30 @@ from vid2vid_b200.utils import det_fill_, synth_label_sequence
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 
-# Stated tolerance of the bf16-operand / fp32-accumulate path against the fp32 reference:
-# images and masks live in [-1,1] / [0,1]; flow is in pixels (x20 head scale); features are O(1).
-# (max |d|, mean |d|); `flow` limits are relative to the reference rms (it carries the x20 head scale).
-TOL = {
-    'img_final': (0.30, 0.02), 'img_raw': (0.15, 0.015), 'weight': (0.08, 0.01), 'flow': (0.15, 0.03),
-    'img_feat': (0.5, 0.03), 'flow_feat': (0.5, 0.03), 'img_fg_feat': (0.5, 0.03), 'out': (0.12, 0.015),
+# Stated tolerances against the fp32 reference, (max |d|, mean |d|); images and masks live in [-1,1] / [0,1],
+# features are O(1) (rms ~0.7), flow is in pixels and carries the x20*2^s head scale.
+#   precise (split-bf16 x3, the product default): fp32-class -- images 5e-3, features 1e-3, flow 0.02 px ABSOLUTE.
+#   fast (bf16 operands): flow limits are relative to the reference rms.
+TOLS = {
+    'precise': {'img_final': (5e-3, 3e-4), 'img_raw': (5e-3, 3e-4), 'weight': (1e-3, 1e-4), 'flow': (0.02, 0.004),
+                'img_feat': (1e-3, 1e-4), 'flow_feat': (1e-3, 1e-4), 'img_fg_feat': (1e-3, 1e-4), 'out': (2e-3, 2e-4)},
+    'fast': {'img_final': (0.30, 0.02), 'img_raw': (0.15, 0.015), 'weight': (0.08, 0.01), 'flow': (0.15, 0.03),
+             'img_feat': (0.5, 0.03), 'flow_feat': (0.5, 0.03), 'img_fg_feat': (0.5, 0.03), 'out': (0.12, 0.015)},
 }
+TOL = dict(TOLS['precise'])
+MODE = ['precise']
+
+
+@pytest.fixture(autouse=True, params=['precise', 'fast'])
+def mode(request):
+    from vid2vid_b200 import networks as NW
+    old = NW.DEFAULT_PRECISION
+    NW.set_default_precision(request.param)
+    MODE[0] = request.param
+    TOL.clear()
+    TOL.update(TOLS[request.param])
+    yield request.param
+    NW.set_default_precision(old)
 
 
 def load(name):
@@ -31,7 +48,7 @@ def report(name, key, out, gold):
     d = np.abs(out - gold)
     rms = np.sqrt((gold ** 2).mean())
     print('%-12s %-12s max|d|=%.4f mean|d|=%.5f  ref rms=%.3f' % (name, key, d.max(), d.mean(), rms))
-    if key == 'flow':
+    if key == 'flow' and MODE[0] == 'fast':
         return d.max() / rms, d.mean() / rms
     return d.max(), d.mean()
 
@@ -73,7 +90,7 @@ def test_cfg1_full_width_generator():
         if key + '_sub' in gold:
             mx, mn = report('cfg1', key, t[:, :, ::ss, ::ss].numpy(), gold[key + '_sub'])
             cm = np.abs(t.mean(dim=(2, 3)).numpy() - gold[key + '_cmean']).max()
-            assert cm < 0.02, (key, cm)
+            assert cm < (0.02 if MODE[0] == 'fast' else 2e-3 * (20 if key == 'flow' else 1)), (key, cm)
         else:
             mx, mn = report('cfg1', key, t.numpy(), gold[key])
         if mx > TOL[key][0] or mn > TOL[key][1]:
@@ -110,6 +127,8 @@ def test_generator_simt_vs_umma_same_plan():
         d = (a - b).abs()
         print('%-12s umma-vs-simt max|d|=%.4f mean|d|=%.5f' % (key, d.max().item(), d.mean().item()))
         lim = 0.03 * b.pow(2).mean().sqrt().item() if key == 'flow' else (2e-2 if key == 'img_final' else 1e-2)
+        if MODE[0] == 'precise':
+            lim = 0.004 if key == 'flow' else 1e-4
         assert d.mean().item() < lim, key
 
 
@@ -131,8 +150,8 @@ def test_multiscale_discriminator_vs_reference_fixture():
             d = np.abs(t.cpu().numpy() - gk)
             rms = np.sqrt((gk ** 2).mean())
             print('D tower %d layer %d: max|d|=%.4f mean|d|=%.5f ref rms=%.3f' % (i, j, d.max(), d.mean(), rms))
-            # bf16 operands, <= 5 layers deep: mean error within 2 %% of the layer's rms
-            if d.mean() > 0.02 * max(rms, 0.05):
+            # bf16 operands, <= 5 layers deep: mean error within 2 %% of the layer's rms (precise: 1e-4)
+            if d.mean() > (0.02 if MODE[0] == 'fast' else 1e-4) * max(rms, 0.05):
                 bad.append((i, j, d.mean(), rms))
     assert not bad, bad
 
@@ -152,7 +171,7 @@ def test_cfg2_full_size_vs_oracle():
     bad = []
     for key, o, r in zip(C.GEN_OUT_NAMES, out, ref):
         mx, mn = report('cfg2', key, o.cpu().numpy(), r.numpy())
-        if mx > TOL[key][0] * 1.5 or mn > TOL[key][1]:
+        if mx > TOL[key][0] * (1.5 if MODE[0] == 'fast' else 1.0) or mn > TOL[key][1]:
             bad.append((key, mx, mn))
     assert not bad, bad
 

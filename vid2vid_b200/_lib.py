@@ -13,6 +13,7 @@ PAD_NONE, PAD_ZERO, PAD_REFLECT = 0, 1, 2
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH, ACT_SIGMOID = 0, 1, 2, 3, 4
 NORM_NONE, NORM_BATCH, NORM_INSTANCE = 0, 1, 2
 IMPL_UMMA, IMPL_SIMT = 0, 1
+PREC_BF16, PREC_BF16X3 = 0, 1
 
 
 class ConvDesc(C.Structure):
@@ -35,12 +36,12 @@ class HeadChannel(C.Structure):
 _lib = None
 LAUNCHES = [0]      # kernels launched through this binding (bench.py's gpu_launches)
 
-# every symbol include/v2v_b200.h declares (tests/test_abi.py checks the list against the header)
+# every symbol include/v2v_b200.h declares (tests/test_host_logic.py checks the list against the header)
 SYMBOLS = [
     'v2v_version', 'v2v_last_error',
     'v2v_correlation_out_shape', 'v2v_correlation_forward', 'v2v_resample2d_forward', 'v2v_channelnorm_forward',
     'v2v_resample_forward', 'v2v_onehot_edges', 'v2v_avgpool3s2', 'v2v_fg_mask',
-    'v2v_plan_create', 'v2v_plan_destroy', 'v2v_g_input', 'v2v_g_conv', 'v2v_g_norm_act', 'v2v_g_norm_act_slice', 'v2v_g_conv_act',
+    'v2v_plan_create', 'v2v_plan_destroy', 'v2v_plan_set_precision', 'v2v_g_input', 'v2v_g_conv', 'v2v_g_norm_act', 'v2v_g_norm_act_slice', 'v2v_g_conv_act',
     'v2v_g_head', 'v2v_g_export', 'v2v_g_composite', 'v2v_plan_finalize', 'v2v_plan_repack', 'v2v_plan_run',
     'v2v_plan_profile', 'v2v_plan_num_kernels', 'v2v_plan_conv_macs', 'v2v_plan_workspace_bytes', 'v2v_plan_describe',
     'v2v_conv_tap_table',
@@ -62,6 +63,7 @@ def lib():
     l.v2v_plan_describe.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
     l.v2v_plan_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
     l.v2v_plan_destroy.argtypes = [C.c_void_p]
+    l.v2v_plan_set_precision.argtypes = [C.c_void_p, C.c_int]
     l.v2v_g_input.argtypes = [C.c_void_p] + [C.c_int] * 7 + [C.POINTER(C.c_int)]
     l.v2v_g_conv.argtypes = [C.c_void_p, C.c_int, C.POINTER(ConvDesc), C.POINTER(C.c_int)]
     l.v2v_g_norm_act.argtypes = [C.c_void_p, C.c_int, C.POINTER(NormDesc), C.c_int, C.c_float, C.c_int, C.c_int,

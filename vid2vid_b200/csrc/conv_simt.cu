@@ -36,11 +36,17 @@ __global__ void conv_simt_kernel(ActDesc in, const bf16* __restrict__ w, int Kto
       for (int r = 0; r < p.R; ++r) {
         const int yy = gy + grp.dy + r / p.RW, xx = gx + grp.dx + r % p.RW;
         if (yy < 0 || yy >= in.Hp || xx < 0 || xx >= in.Wp) continue;   // TMA zero fill
-        const bf16* a = in.base + ((((size_t)n * in.P + grp.plane) * in.Hp + yy) * in.Wp + xx) * in.C;
-        const bf16* b = w + (size_t)co * Ktotal + (size_t)(grp.tap0 + r) * p.Cp;
+        const bf16* a = in.base + ((((size_t)n * in.P + grp.plane) * in.Hp + yy) * in.Wp + xx) * in.Cs();
+        const bf16* b = w + (size_t)co * Ktotal * (p.split ? 2 : 1) + (size_t)(grp.tap0 + r) * p.Cp;
         for (int c = 0; c < p.Cp; c += 2) {
-          const float2 av = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + c));
-          const float2 bv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b + c));
+          float2 av = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + c));
+          float2 bv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b + c));
+          if (p.split) {     // precise plans: the same three products the tensor-core kernel accumulates
+            const float2 al = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a + in.C + c));
+            const float2 bl = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(b + Ktotal + c));
+            acc = fmaf(al.x, bv.x, acc); acc = fmaf(av.x, bl.x, acc);
+            acc = fmaf(al.y, bv.y, acc); acc = fmaf(av.y, bl.y, acc);
+          }
           acc = fmaf(av.x, bv.x, acc);
           acc = fmaf(av.y, bv.y, acc);
         }
@@ -52,22 +58,26 @@ __global__ void conv_simt_kernel(ActDesc in, const bf16* __restrict__ w, int Kto
       v = simt_act(v, p.head_act[co], p.lrelu_slope) * p.head_scale[co];
       reinterpret_cast<float*>(p.io[p.head_slot[co]])[p.head_off[co] + (size_t)n * p.head_bstride[co] + (size_t)oy * p.out_W + ox] = v;
     } else if (p.epi == EPI_RAW_STATS) {
-      reinterpret_cast<bf16*>(p.out)[(((size_t)n * p.out_H + oy) * p.out_W + ox) * p.out_C + co] =
-          __float2bfloat16_rn(acc);
+      const size_t oi = (((size_t)n * p.out_H + oy) * p.out_W + ox) * p.out_C + co;
+      if (p.out_f32) reinterpret_cast<float*>(p.out)[oi] = acc;
+      else reinterpret_cast<bf16*>(p.out)[oi] = __float2bfloat16_rn(acc);
     } else {
       float v = simt_act(acc + (p.bias ? p.bias[co] : 0.f), p.act, p.lrelu_slope);
-      p.out_act.base[p.out_act.offset(n, oy, ox) + co] = __float2bfloat16_rn(v);
+      const size_t oi = p.out_act.offset(n, oy, ox) + co;
+      if (p.out_act.split) split_bf16(v, p.out_act.base[oi], p.out_act.base[oi + p.out_act.C]);
+      else p.out_act.base[oi] = __float2bfloat16_rn(v);
     }
   }
 }
 
 // Per-channel (sum, sumsq) of a raw NHWC bf16 tensor, one partial row per image:
 // stats[(n*2 + {0,1}) * C + c].  Used with the SIMT conv (the tcgen05 epilogue produces these itself).
-__global__ void raw_stats_kernel(const bf16* __restrict__ raw, int HW, int C, int Cs, float* __restrict__ stats) {
+__global__ void raw_stats_kernel(const void* __restrict__ raw_, int f32, int HW, int C, int Cs, float* __restrict__ stats) {
   const int n = blockIdx.y, c = blockIdx.x;
   float s = 0.f, q = 0.f;
   for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-    float v = __bfloat162float(raw[((size_t)n * HW + i) * C + c]);
+    const size_t e = ((size_t)n * HW + i) * C + c;
+    float v = f32 ? reinterpret_cast<const float*>(raw_)[e] : __bfloat162float(reinterpret_cast<const bf16*>(raw_)[e]);
     s += v; q += v * v;
   }
   __shared__ float ss[256], sq[256];
@@ -94,7 +104,7 @@ cudaError_t launch_conv_simt(const ActDesc& in, const bf16* wpacked, int Ktotal,
 
 cudaError_t launch_raw_stats(const RawDesc& raw, float* stats, int stats_C, cudaStream_t stream) {
   dim3 grid(raw.Cvalid, raw.N);
-  raw_stats_kernel<<<grid, 256, 0, stream>>>(raw.base, raw.H * raw.W, raw.C, stats_C, stats);
+  raw_stats_kernel<<<grid, 256, 0, stream>>>(raw.base, raw.f32, raw.H * raw.W, raw.C, stats_C, stats);
   return cudaGetLastError();
 }
 

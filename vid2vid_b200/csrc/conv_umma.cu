@@ -143,6 +143,8 @@ __device__ __forceinline__ void mma_role(const ConvKernelParams& p, const MmaCtx
   const uint32_t a_step = (uint32_t)(p.row_bytes >> 4), b_step = (uint32_t)(cx.b_tx >> 4);
   const uint32_t a_wrap = (uint32_t)(((p.PW - p.RW) * p.row_bytes) >> 4);     // to the next patch row
   const uint32_t sBres_u32 = smem_u32(cx.sBres);
+  const int npass = p.split ? 3 : 1;
+  const uint32_t a_half16 = (uint32_t)(p.a_half_bytes >> 4), b_half16 = (uint32_t)(p.b_half_bytes >> 4);
   // descriptors differ only in the 14-bit (address >> 4) field of the low word
   const uint32_t a_hi = (uint32_t)(make_kmajor_desc(0, p.sbo_a_bytes, p.layout_type) >> 32);
   const uint32_t b_hi = (uint32_t)(make_kmajor_desc(0, p.sbo_bytes, p.layout_type) >> 32);
@@ -184,9 +186,15 @@ __device__ __forceinline__ void mma_role(const ConvKernelParams& p, const MmaCtx
           // tap r reads the patch shifted by (r / RW) patch rows and (r % RW) pixels; K = 16 bf16 = 32 bytes per MMA,
           // kc/16 MMAs per smem row.  The trip-count switch sits outside the tap loops: the issuing thread has ~40
           // cycles per MMA for small-N layers, every instruction in the loop body counts.
-          if (p.kmma == 4) issue_taps<kWarpWide, 4>(p, tmem_d, al, bl, a_hi, b_hi, idesc, first, a_step, b_step, a_wrap);
-          else if (p.kmma == 2) issue_taps<kWarpWide, 2>(p, tmem_d, al, bl, a_hi, b_hi, idesc, first, a_step, b_step, a_wrap);
-          else issue_taps<kWarpWide, 1>(p, tmem_d, al, bl, a_hi, b_hi, idesc, first, a_step, b_step, a_wrap);
+          // precise plans: npass = 3 accumulates A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (the lo halves sit a_half / b_half
+          // bytes further in the same slots)
+          for (int ps = 0; ps < npass; ++ps) {
+            const uint32_t alp = al + (ps == 1 ? a_half16 : 0u), blp = bl + (ps == 2 ? b_half16 : 0u);
+            if (p.kmma == 4) issue_taps<kWarpWide, 4>(p, tmem_d, alp, blp, a_hi, b_hi, idesc, first, a_step, b_step, a_wrap);
+            else if (p.kmma == 2) issue_taps<kWarpWide, 2>(p, tmem_d, alp, blp, a_hi, b_hi, idesc, first, a_step, b_step, a_wrap);
+            else issue_taps<kWarpWide, 1>(p, tmem_d, alp, blp, a_hi, b_hi, idesc, first, a_step, b_step, a_wrap);
+            first = 1u;
+          }
         }
       }
       if (kWarpWide ? elect_one_sync() : true) {
@@ -260,6 +268,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int gs = 0;
       uint32_t gpar = 0, gen = 0;
       int prev_key = -1;
+      const int nhalf = p.split ? 2 : 1;
       UnitIter un;
       un.init(p, t_first, t_step);
       for (int pit = 0; un.valid(p); un.next(p), ++pit) {
@@ -270,13 +279,14 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.b_resident && un.key != prev_key) {
           if (prev_key >= 0) gen ^= 1;
           mbar_wait(bres_empty, gen ^ 1);                      // all MMAs that read the previous weight set retired
-          mbar_expect_tx(bres_full, (uint32_t)nsteps * p.R * b_tx);
+          mbar_expect_tx(bres_full, (uint32_t)nsteps * p.R * b_tx * nhalf);
           int sidx = 0;
           for (int g = ph.group_begin; g < ph.group_end; ++g)
             for (int cb = 0; cb < p.cblocks; ++cb, ++sidx)
-              for (int r = 0; r < p.R; ++r)
-                tma_load_2d(sBres + (size_t)sidx * p.b_slot_bytes + (size_t)r * b_tx, &tmB, bres_full,
-                            (p.groups[g].tap0 + r) * p.Cp + cb * p.kc, n0);
+              for (int hf = 0; hf < nhalf; ++hf)
+                for (int r = 0; r < p.R; ++r)
+                  tma_load_2d(sBres + (size_t)sidx * p.b_slot_bytes + (size_t)hf * p.b_half_bytes + (size_t)r * b_tx, &tmB,
+                              bres_full, hf * p.Khalf + (p.groups[g].tap0 + r) * p.Cp + cb * p.kc, n0);
         }
         prev_key = un.key;
         int g = ph.group_begin, cb = 0;
@@ -284,16 +294,19 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int n = min(p.CG, nsteps - s0);
           uint8_t* base = sG + (size_t)gs * group_bytes;
           mbar_wait(&g_empty[gs], gpar ^ 1);
-          mbar_expect_tx(&g_full[gs], (uint32_t)n * (p.MG * a_tx + (p.b_resident ? 0 : p.R * b_tx)));
+          mbar_expect_tx(&g_full[gs], (uint32_t)n * nhalf * (p.MG * a_tx + (p.b_resident ? 0 : p.R * b_tx)));
           for (int i = 0; i < n; ++i) {
             const ConvGroup grp = p.groups[g];
             for (int j = 0; j < p.MG; ++j)
-              tma_load_5d(base + (size_t)(i * p.MG + j) * p.a_slot_bytes, &tmA, &g_full[gs], cb * p.kc,
-                          x0 + j * p.TW + grp.dx, y0 + grp.dy, grp.plane, un.img);
+              for (int hf = 0; hf < nhalf; ++hf)      // lo half: channels [Cp, 2 Cp) of the pixel
+                tma_load_5d(base + (size_t)(i * p.MG + j) * p.a_slot_bytes + (size_t)hf * p.a_half_bytes, &tmA, &g_full[gs],
+                            hf * p.Cp + cb * p.kc, x0 + j * p.TW + grp.dx, y0 + grp.dy, grp.plane, un.img);
             if (!p.b_resident) {
               uint8_t* bb = base + (size_t)p.CG * p.MG * p.a_slot_bytes + (size_t)i * p.b_slot_bytes;
-              for (int r = 0; r < p.R; ++r)
-                tma_load_2d(bb + (size_t)r * b_tx, &tmB, &g_full[gs], (grp.tap0 + r) * p.Cp + cb * p.kc, n0);
+              for (int hf = 0; hf < nhalf; ++hf)
+                for (int r = 0; r < p.R; ++r)
+                  tma_load_2d(bb + (size_t)hf * p.b_half_bytes + (size_t)r * b_tx, &tmB, &g_full[gs],
+                              hf * p.Khalf + (grp.tap0 + r) * p.Cp + cb * p.kc, n0);
             }
             if (++cb == p.cblocks) { cb = 0; ++g; }
           }
@@ -366,11 +379,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int ox = gx * p.ox_mul + ph.ox_add;
         const uint32_t taddr = tmem_base + (my_as * p.MG + jt) * acc_cols + (static_cast<uint32_t>(q * 32) << 16);
         bf16* dst = nullptr;
+        float* dstf = nullptr;
         if (valid && p.epi != EPI_HEAD_F32) {
-          if (p.epi == EPI_RAW_STATS)
-            dst = reinterpret_cast<bf16*>(p.out) + (((size_t)n_img * p.out_H + oy) * p.out_W + ox) * p.out_C;
-          else
+          const size_t pix_off = (((size_t)n_img * p.out_H + oy) * p.out_W + ox) * p.out_C;
+          if (p.epi == EPI_RAW_STATS) {
+            if (p.out_f32) dstf = reinterpret_cast<float*>(p.out) + pix_off;
+            else dst = reinterpret_cast<bf16*>(p.out) + pix_off;
+          } else {
             dst = p.out_act.base + p.out_act.offset(n_img, oy, ox);
+          }
         }
 
         if (p.epi == EPI_HEAD_F32) {
@@ -425,15 +442,38 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
           if (valid && !(p.dbg & 2)) {
+            if (dstf) {                                // precise plan: fp32 raw output
 #pragma unroll
-            for (int qv = 0; qv < 4; ++qv) {
-              if (col0 + qv * 8 < p.out_C) {
-                uint4 pk;
-                pk.x = pack_bf16x2(v[qv * 8 + 0], v[qv * 8 + 1]);
-                pk.y = pack_bf16x2(v[qv * 8 + 2], v[qv * 8 + 3]);
-                pk.z = pack_bf16x2(v[qv * 8 + 4], v[qv * 8 + 5]);
-                pk.w = pack_bf16x2(v[qv * 8 + 6], v[qv * 8 + 7]);
-                *reinterpret_cast<uint4*>(dst + col0 + qv * 8) = pk;
+              for (int qv = 0; qv < 8; ++qv)
+                if (col0 + qv * 4 < p.out_C)
+                  *reinterpret_cast<float4*>(dstf + col0 + qv * 4) = make_float4(v[qv * 4], v[qv * 4 + 1], v[qv * 4 + 2], v[qv * 4 + 3]);
+            } else if (p.epi == EPI_ACT_BF16 && p.out_act.split) {
+#pragma unroll
+              for (int qv = 0; qv < 4; ++qv) {
+                if (col0 + qv * 8 < p.out_C) {
+                  float lo[8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) lo[j] = v[qv * 8 + j] - __bfloat162float(__float2bfloat16_rn(v[qv * 8 + j]));
+                  uint4 pk, pl;
+                  pk.x = pack_bf16x2(v[qv * 8 + 0], v[qv * 8 + 1]); pl.x = pack_bf16x2(lo[0], lo[1]);
+                  pk.y = pack_bf16x2(v[qv * 8 + 2], v[qv * 8 + 3]); pl.y = pack_bf16x2(lo[2], lo[3]);
+                  pk.z = pack_bf16x2(v[qv * 8 + 4], v[qv * 8 + 5]); pl.z = pack_bf16x2(lo[4], lo[5]);
+                  pk.w = pack_bf16x2(v[qv * 8 + 6], v[qv * 8 + 7]); pl.w = pack_bf16x2(lo[6], lo[7]);
+                  *reinterpret_cast<uint4*>(dst + col0 + qv * 8) = pk;
+                  *reinterpret_cast<uint4*>(dst + p.out_act.C + col0 + qv * 8) = pl;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int qv = 0; qv < 4; ++qv) {
+                if (col0 + qv * 8 < p.out_C) {
+                  uint4 pk;
+                  pk.x = pack_bf16x2(v[qv * 8 + 0], v[qv * 8 + 1]);
+                  pk.y = pack_bf16x2(v[qv * 8 + 2], v[qv * 8 + 3]);
+                  pk.z = pack_bf16x2(v[qv * 8 + 4], v[qv * 8 + 5]);
+                  pk.w = pack_bf16x2(v[qv * 8 + 6], v[qv * 8 + 7]);
+                  *reinterpret_cast<uint4*>(dst + col0 + qv * 8) = pk;
+                }
               }
             }
           }

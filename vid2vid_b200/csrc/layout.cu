@@ -68,16 +68,22 @@ __global__ void __launch_bounds__(256) import_nchw_kernel(ImportParams p) {
       const int xo = xt + px;
       if (xo >= Wpad) break;
       if (cblk + 2 * (int)threadIdx.x >= o.C) continue;
-      const uint32_t pk = pack_bf16x2(tile[2 * threadIdx.x][px], tile[2 * threadIdx.x + 1][px]);
-      *reinterpret_cast<uint32_t*>(o.base + o.offset(n, yp - o.pad_t, xo - o.pad_l) + cblk + 2 * threadIdx.x) = pk;
+      const float f0 = tile[2 * threadIdx.x][px], f1 = tile[2 * threadIdx.x + 1][px];
+      bf16* d = o.base + o.offset(n, yp - o.pad_t, xo - o.pad_l) + cblk + 2 * threadIdx.x;
+      *reinterpret_cast<uint32_t*>(d) = pack_bf16x2(f0, f1);
+      if (o.split) *reinterpret_cast<uint32_t*>(d + o.C) = pack_bf16x2(f0 - __bfloat162float(__float2bfloat16_rn(f0)),
+                                                                      f1 - __bfloat162float(__float2bfloat16_rn(f1)));
     }
   } else {
     const int cp = threadIdx.x & 7, sub = threadIdx.x >> 3;         // 8 channel pairs x 4 pixels per warp row
     for (int px = threadIdx.y * 4 + sub; px < 128; px += 32) {
       const int xo = xt + px;
       if (xo >= Wpad || cblk + 2 * cp >= o.C) continue;
-      const uint32_t pk = pack_bf16x2(tile[2 * cp][px], tile[2 * cp + 1][px]);
-      *reinterpret_cast<uint32_t*>(o.base + o.offset(n, yp - o.pad_t, xo - o.pad_l) + cblk + 2 * cp) = pk;
+      const float f0 = tile[2 * cp][px], f1 = tile[2 * cp + 1][px];
+      bf16* d = o.base + o.offset(n, yp - o.pad_t, xo - o.pad_l) + cblk + 2 * cp;
+      *reinterpret_cast<uint32_t*>(d) = pack_bf16x2(f0, f1);
+      if (o.split) *reinterpret_cast<uint32_t*>(d + o.C) = pack_bf16x2(f0 - __bfloat162float(__float2bfloat16_rn(f0)),
+                                                                      f1 - __bfloat162float(__float2bfloat16_rn(f1)));
     }
   }
 }
@@ -97,7 +103,14 @@ __global__ void __launch_bounds__(256) export_nchw_kernel(ExportParams p) {
   for (int px = threadIdx.y * 2 + sub; px < 128; px += 16) {
     const int x = xt + px, c = cblk + 2 * cp;
     float2 v = make_float2(0.f, 0.f);
-    if (x < a.W && c < a.C) v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(a.base + a.offset(n, y, x) + c));
+    if (x < a.W && c < a.C) {
+      const bf16* sp = a.base + a.offset(n, y, x) + c;
+      v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sp));
+      if (a.split) {
+        const float2 l = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sp + a.C));
+        v.x += l.x; v.y += l.y;
+      }
+    }
     tile[2 * cp][px] = v.x;
     tile[2 * cp + 1][px] = v.y;
   }
@@ -133,7 +146,8 @@ __global__ void pack_weights_kernel(PackParams p) {
         v = p.w[wi];
       }
     }
-    p.out[idx] = __float2bfloat16_rn(v);
+    if (p.split) split_bf16(v, p.out[(size_t)co * 2 * K + k], p.out[(size_t)co * 2 * K + K + k]);
+    else p.out[idx] = __float2bfloat16_rn(v);
   }
 }
 

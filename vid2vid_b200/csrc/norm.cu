@@ -77,6 +77,17 @@ __global__ void __launch_bounds__(128) stats_finalize_kernel(FinalizeParams p) {
   }
 }
 
+__device__ __forceinline__ void bf16x8_to_float(const uint4& r, float (&f)[8]) {
+  const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { float2 a = __bfloat1622float2(rp[j]); f[2 * j] = a.x; f[2 * j + 1] = a.y; }
+}
+__device__ __forceinline__ void bf16x8_add(const uint4& r, float (&f)[8]) {
+  const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { float2 a = __bfloat1622float2(rp[j]); f[2 * j] += a.x; f[2 * j + 1] += a.y; }
+}
+
 __device__ __forceinline__ int reflect_idx(int i, int n) {   // nn.ReflectionPad2d index map
   if (i < 0) i = -i;
   if (i >= n) i = 2 * (n - 1) - i;
@@ -102,12 +113,17 @@ __device__ __forceinline__ void apply_item(const ApplyParams& p, int vecs, int W
     if (p.pad_mode == PAD_REFLECT) { y = reflect_idx(y, p.out.H); x = reflect_idx(x, p.out.W); }
     else zero = true;
   }
+  uint4 ol = make_uint4(0, 0, 0, 0);
   if (!zero) {
-    const uint4 r = *reinterpret_cast<const uint4*>(p.raw.base + (((size_t)n * p.raw.H + y) * p.raw.W + x) * p.raw.C + c0);
+    const size_t ri = (((size_t)n * p.raw.H + y) * p.raw.W + x) * p.raw.C + c0;
     float f[8];
-    const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { float2 a = __bfloat1622float2(rp[j]); f[2 * j] = a.x; f[2 * j + 1] = a.y; }
+    if (p.raw.f32) {
+      const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.raw.base) + ri);
+      const float4 f0 = rp[0], f1 = rp[1];
+      f[0] = f0.x; f[1] = f0.y; f[2] = f0.z; f[3] = f0.w; f[4] = f1.x; f[5] = f1.y; f[6] = f1.z; f[7] = f1.w;
+    } else {
+      bf16x8_to_float(*reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.raw.base) + ri), f);
+    }
     if (p.scale) {
       const float* sc = p.scale + (size_t)n * p.scale_stride + c0;
       const float* sh = p.shift + (size_t)n * p.scale_stride + c0;
@@ -124,18 +140,25 @@ __device__ __forceinline__ void apply_item(const ApplyParams& p, int vecs, int W
     for (int a = 0; a < p.n_add; ++a) {
       const ActDesc& ad = p.add[a];
       if (c0 < ad.C) {
-        const uint4 q = *reinterpret_cast<const uint4*>(ad.base + ad.offset(n, y, x) + c0);
-        const __nv_bfloat162* qp = reinterpret_cast<const __nv_bfloat162*>(&q);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { float2 b = __bfloat1622float2(qp[j]); f[2 * j] += b.x; f[2 * j + 1] += b.y; }
+        const bf16* ap = ad.base + ad.offset(n, y, x) + c0;
+        bf16x8_add(*reinterpret_cast<const uint4*>(ap), f);
+        if (ad.split) bf16x8_add(*reinterpret_cast<const uint4*>(ap + ad.C), f);
       }
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) if (c0 + j >= p.raw.Cvalid) f[j] = 0.f;
     o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
     o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+    if (p.out.split) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] -= __bfloat162float(__float2bfloat16_rn(f[j]));
+      ol.x = pack_bf16x2(f[0], f[1]); ol.y = pack_bf16x2(f[2], f[3]);
+      ol.z = pack_bf16x2(f[4], f[5]); ol.w = pack_bf16x2(f[6], f[7]);
+    }
   }
-  *reinterpret_cast<uint4*>(p.out.base + p.out.offset(n, yp - p.out.pad_t, xp - p.out.pad_l) + c0) = o;
+  bf16* op = p.out.base + p.out.offset(n, yp - p.out.pad_t, xp - p.out.pad_l) + c0;
+  *reinterpret_cast<uint4*>(op) = o;
+  if (p.out.split) *reinterpret_cast<uint4*>(op + p.out.C) = ol;
 }
 
 __global__ void __launch_bounds__(256) norm_apply_kernel(ApplyParams p) {
@@ -152,16 +175,16 @@ __global__ void __launch_bounds__(256) norm_apply_kernel(ApplyParams p) {
 // 64-bit index arithmetic per item: the grid-stride kernel above issues ~260 instructions per 16-byte item (ncu:
 // issue slots 77 % busy, IPC 3.1, 2.7 TB/s) and is instruction bound, this one ~45.
 // Consecutive threads cover the C * 2 contiguous bytes of a pixel, then the next pixel: loads and stores are coalesced.
-struct RowAddr { size_t base; int xs; size_t plane; int parity, C, pad_l; };
+struct RowAddr { size_t base; int xs; size_t plane; int parity, C, pad_l; };   // C = bf16 elements per pixel
 __device__ __forceinline__ RowAddr row_addr(const ActDesc& a, int n, int y) {     // y relative to the interior
   RowAddr r;
   const int yp = y + a.pad_t;
-  r.parity = a.parity; r.C = a.C; r.pad_l = a.pad_l;
+  r.parity = a.parity; r.C = a.Cs(); r.pad_l = a.pad_l;
   if (a.parity) {
-    r.base = (((size_t)n * 4 + ((yp & 1) << 1)) * a.Hp + (yp >> 1)) * a.Wp * (size_t)a.C;
-    r.plane = (size_t)a.Hp * a.Wp * a.C;
+    r.base = (((size_t)n * 4 + ((yp & 1) << 1)) * a.Hp + (yp >> 1)) * a.Wp * (size_t)a.Cs();
+    r.plane = (size_t)a.Hp * a.Wp * a.Cs();
   } else {
-    r.base = ((size_t)n * a.Hp + yp) * a.Wp * (size_t)a.C;
+    r.base = ((size_t)n * a.Hp + yp) * a.Wp * (size_t)a.Cs();
     r.plane = 0;
   }
   return r;
@@ -171,8 +194,12 @@ __device__ __forceinline__ size_t row_off(const RowAddr& r, int x) {            
   return r.parity ? r.base + (xp & 1) * r.plane + (size_t)(xp >> 1) * r.C : r.base + (size_t)xp * r.C;
 }
 
-template <int NADD>
+// PREC (precise plans): raw is fp32 (two 16-byte loads per item), addends and the output are [hi | lo] bf16 pairs
+// (two 16-byte loads / stores per item, C elements apart); batches of 2 items instead of 4 keep the same bytes in flight.
+template <int NADD, bool PREC>
 __global__ void __launch_bounds__(256) norm_apply_rows_kernel(ApplyParams p, int xt, int ppb) {
+  constexpr int NB = PREC ? 2 : 4;          // items per batch
+  constexpr int NW = PREC ? 2 : 1;          // 16-byte words per item and tensor
   pdl_prologue();
   const int vecs = p.out.C >> 3;
   const int t = threadIdx.x;
@@ -194,7 +221,10 @@ __global__ void __launch_bounds__(256) norm_apply_rows_kernel(ApplyParams p, int
     sc[j] = cv ? (p.scale ? __ldg(p.scale + (size_t)n * p.scale_stride + c0 + j) : 1.f) : 0.f;
     sh[j] = (cv && p.scale) ? __ldg(p.shift + (size_t)n * p.scale_stride + c0 + j) : 0.f;
   }
-  const bf16* raw_row = p.raw.base + ((size_t)n * p.raw.H + (zero_row ? 0 : y)) * p.raw.W * (size_t)p.raw.C + c0;
+  const size_t eb = PREC ? 4 : 2;
+  const char* raw_row = reinterpret_cast<const char*>(p.raw.base) +
+                        (((size_t)n * p.raw.H + (zero_row ? 0 : y)) * p.raw.W * (size_t)p.raw.C + c0) * eb;
+  const size_t raw_px = (size_t)p.raw.C * eb;
   const RowAddr out_row = row_addr(p.out, n, yp - p.out.pad_t);
   RowAddr add_row[2];
   bool add_on[2];
@@ -204,35 +234,48 @@ __global__ void __launch_bounds__(256) norm_apply_rows_kernel(ApplyParams p, int
     if (add_on[a]) add_row[a] = row_addr(p.add[a], n, y);
   }
   const int x_end = min(Wpad, (int)(blockIdx.x + 1) * xt);
-  // Batches of 4 items: all loads of a batch are issued before the first use, so a thread keeps up to 4 (x3 with two
-  // addends) 16-byte loads in flight -- one load per thread leaves the kernel latency bound (~21 KB in flight per SM
-  // against the ~35 KB HBM3e needs at 6.5 TB/s).
-  for (int xb = blockIdx.x * xt + pl; xb < x_end; xb += 4 * ppb) {
-    uint4 r[4], q0[NADD > 0 ? 4 : 1], q1[NADD > 1 ? 4 : 1];
-    bool live[4];
+  // Batches of NB items: all loads of a batch are issued before the first use, so a thread keeps several 16-byte loads
+  // in flight -- one load per thread leaves the kernel latency bound (~21 KB in flight per SM against the ~35 KB HBM3e
+  // needs at 6.5 TB/s).
+  for (int xb = blockIdx.x * xt + pl; xb < x_end; xb += NB * ppb) {
+    uint4 r[NB][NW], q0[NADD > 0 ? NB : 1][NW], q1[NADD > 1 ? NB : 1][NW];
+    bool live[NB];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < NB; ++b) {
       const int xp = xb + b * ppb;
       int x = xp - p.out.pad_l;
       const bool xhalo = (x < 0 || x >= p.out.W);
       live[b] = xp < x_end && !(zero_row || (xhalo && !reflect));
       if (reflect) x = reflect_idx(x, p.out.W);
       if (live[b]) {
-        r[b] = *reinterpret_cast<const uint4*>(raw_row + (size_t)x * p.raw.C);
-        if (NADD > 0 && add_on[0]) q0[NADD > 0 ? b : 0] = *reinterpret_cast<const uint4*>(p.add[0].base + row_off(add_row[0], x) + c0);
-        if (NADD > 1 && add_on[1]) q1[NADD > 1 ? b : 0] = *reinterpret_cast<const uint4*>(p.add[1].base + row_off(add_row[1], x) + c0);
+        const uint4* rp = reinterpret_cast<const uint4*>(raw_row + (size_t)x * raw_px);
+#pragma unroll
+        for (int w = 0; w < NW; ++w) r[b][w] = rp[w];
+        if (NADD > 0 && add_on[0]) {
+          const bf16* ap = p.add[0].base + row_off(add_row[0], x) + c0;
+          q0[NADD > 0 ? b : 0][0] = *reinterpret_cast<const uint4*>(ap);
+          if (PREC) q0[NADD > 0 ? b : 0][NW - 1] = *reinterpret_cast<const uint4*>(ap + p.add[0].C);
+        }
+        if (NADD > 1 && add_on[1]) {
+          const bf16* ap = p.add[1].base + row_off(add_row[1], x) + c0;
+          q1[NADD > 1 ? b : 0][0] = *reinterpret_cast<const uint4*>(ap);
+          if (PREC) q1[NADD > 1 ? b : 0][NW - 1] = *reinterpret_cast<const uint4*>(ap + p.add[1].C);
+        }
       }
     }
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
+    for (int b = 0; b < NB; ++b) {
       const int xp = xb + b * ppb;
       if (xp >= x_end) break;
-      uint4 o = make_uint4(0, 0, 0, 0);
+      uint4 o = make_uint4(0, 0, 0, 0), ol = make_uint4(0, 0, 0, 0);
       if (live[b]) {
         float f[8];
-        const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&r[b]);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { float2 a = __bfloat1622float2(rp[j]); f[2 * j] = a.x; f[2 * j + 1] = a.y; }
+        if (PREC) {
+          const float4 f0 = *reinterpret_cast<const float4*>(&r[b][0]), f1 = *reinterpret_cast<const float4*>(&r[b][NW - 1]);
+          f[0] = f0.x; f[1] = f0.y; f[2] = f0.z; f[3] = f0.w; f[4] = f1.x; f[5] = f1.y; f[6] = f1.z; f[7] = f1.w;
+        } else {
+          bf16x8_to_float(r[b][0], f);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], sc[j], sh[j]);
         if (p.act == ACT_RELU) {
@@ -243,14 +286,12 @@ __global__ void __launch_bounds__(256) norm_apply_rows_kernel(ApplyParams p, int
           for (int j = 0; j < 8; ++j) f[j] = f[j] > 0.f ? f[j] : f[j] * p.slope;
         }
         if (NADD > 0 && add_on[0]) {
-          const __nv_bfloat162* qp = reinterpret_cast<const __nv_bfloat162*>(&q0[NADD > 0 ? b : 0]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { float2 v2 = __bfloat1622float2(qp[j]); f[2 * j] += v2.x; f[2 * j + 1] += v2.y; }
+          bf16x8_add(q0[NADD > 0 ? b : 0][0], f);
+          if (PREC) bf16x8_add(q0[NADD > 0 ? b : 0][NW - 1], f);
         }
         if (NADD > 1 && add_on[1]) {
-          const __nv_bfloat162* qp = reinterpret_cast<const __nv_bfloat162*>(&q1[NADD > 1 ? b : 0]);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { float2 v2 = __bfloat1622float2(qp[j]); f[2 * j] += v2.x; f[2 * j + 1] += v2.y; }
+          bf16x8_add(q1[NADD > 1 ? b : 0][0], f);
+          if (PREC) bf16x8_add(q1[NADD > 1 ? b : 0][NW - 1], f);
         }
         if (NADD > 0) {        // addends may carry values in channels the raw tensor does not have: keep the padding zero
 #pragma unroll
@@ -258,8 +299,16 @@ __global__ void __launch_bounds__(256) norm_apply_rows_kernel(ApplyParams p, int
         }
         o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]);
         o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+        if (PREC) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] -= __bfloat162float(__float2bfloat16_rn(f[j]));
+          ol.x = pack_bf16x2(f[0], f[1]); ol.y = pack_bf16x2(f[2], f[3]);
+          ol.z = pack_bf16x2(f[4], f[5]); ol.w = pack_bf16x2(f[6], f[7]);
+        }
       }
-      *reinterpret_cast<uint4*>(p.out.base + row_off(out_row, xp - p.out.pad_l) + c0) = o;
+      bf16* op = p.out.base + row_off(out_row, xp - p.out.pad_l) + c0;
+      *reinterpret_cast<uint4*>(op) = o;
+      if (PREC) *reinterpret_cast<uint4*>(op + p.out.C) = ol;
     }
   }
 }
@@ -345,7 +394,7 @@ __global__ void __launch_bounds__(256) norm_apply_fused_kernel(ApplyParams p) {
       else zero = true;
     }
     if (!zero) {
-      const uint4 r = *reinterpret_cast<const uint4*>(p.raw.base + (((size_t)n * p.raw.H + y) * p.raw.W + x) * p.raw.C + c0);
+      const uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.raw.base) + (((size_t)n * p.raw.H + y) * p.raw.W + x) * p.raw.C + c0);
       float fv[8];
       const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
@@ -391,7 +440,9 @@ cudaError_t launch_norm_apply(const ApplyParams& p, cudaStream_t stream) {
   const long long total = (long long)p.out.N * (p.out.H + p.out.pad_t + p.out.pad_b) *
                           (p.out.W + p.out.pad_l + p.out.pad_r) * (p.out.C / 8);
   if (total >= (1LL << 31)) return cudaErrorInvalidValue;
-  if (p.fused) {
+  const bool prec = p.raw.f32 != 0;
+  if (prec != (p.out.split != 0)) return cudaErrorInvalidValue;      // precise plans: fp32 raw <-> split activations
+  if (p.fused && !prec) {
     const int groups = (p.out.C + 63) / 64;
     int gx = grid_for(total / groups + 1, 256);
     gx = std::max(1, std::min(gx, (148 * 8) / groups + 1));      // few, long-lived blocks: the prologue runs once per block
@@ -405,9 +456,14 @@ cudaError_t launch_norm_apply(const ApplyParams& p, cudaStream_t stream) {
       const int ppb = 256 / vecs;                     // pixels per block pass
       const int xt = ppb * 8;                         // 8 items per thread
       dim3 grid((Wpad + xt - 1) / xt, p.out.N * Hpad);
-      if (p.n_add == 0) return launch_pdl(norm_apply_rows_kernel<0>, grid, dim3(256), 0, stream, p, xt, ppb);
-      if (p.n_add == 1) return launch_pdl(norm_apply_rows_kernel<1>, grid, dim3(256), 0, stream, p, xt, ppb);
-      return launch_pdl(norm_apply_rows_kernel<2>, grid, dim3(256), 0, stream, p, xt, ppb);
+      if (prec) {
+        if (p.n_add == 0) return launch_pdl(norm_apply_rows_kernel<0, true>, grid, dim3(256), 0, stream, p, xt, ppb);
+        if (p.n_add == 1) return launch_pdl(norm_apply_rows_kernel<1, true>, grid, dim3(256), 0, stream, p, xt, ppb);
+        return launch_pdl(norm_apply_rows_kernel<2, true>, grid, dim3(256), 0, stream, p, xt, ppb);
+      }
+      if (p.n_add == 0) return launch_pdl(norm_apply_rows_kernel<0, false>, grid, dim3(256), 0, stream, p, xt, ppb);
+      if (p.n_add == 1) return launch_pdl(norm_apply_rows_kernel<1, false>, grid, dim3(256), 0, stream, p, xt, ppb);
+      return launch_pdl(norm_apply_rows_kernel<2, false>, grid, dim3(256), 0, stream, p, xt, ppb);
     } else {
       return launch_pdl(norm_apply_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, p);
     }

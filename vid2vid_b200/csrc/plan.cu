@@ -78,7 +78,8 @@ static const int kResidentMax = 150 * 1024;
 // start address advanced by (ky * PW + kx) rows and a group stride (SBO) of PW rows.  Each input pixel is then fetched
 // ~1.4x (3x3) instead of 3x (row tiles with horizontal reuse) or 9x (one box per tap).  Feasible when a step's weights
 // (all taps of one K block) fit next to the patch, double buffered, or the whole (phase, N tile) weight set stays resident.
-static bool choose_patch2d(const v2v_conv_desc& c, bool head, int N, int grid_h, int grid_w, int* kc_out, int* bn_out, int* res_out) {
+// sp = 2 for precise plans: every operand slot holds a hi and a lo half, so all byte counts double.
+static bool choose_patch2d(const v2v_conv_desc& c, bool head, int N, int grid_h, int grid_w, int sp, int* kc_out, int* bn_out, int* res_out) {
   const char* e = getenv("V2V_PATCH2D");
   if (e && e[0] == '0') return false;
   if (c.transposed || c.stride != 1 || c.kh * c.kw == 1 || grid_w < 8) return false;
@@ -97,8 +98,8 @@ static bool choose_patch2d(const v2v_conv_desc& c, bool head, int N, int grid_h,
     static const bool half_ok = [] { const char* e = getenv("V2V_P2D_HALF"); return e && e[0] == '1'; }();
     if (pass == 1 && (!half_ok || bn0 < 128 || m_total < 4LL * sms)) break;
     if (m_total <= sms) break;
-    const long long res_bytes = (long long)(Cp / kc_max) * round_up_i(taps * bn * kc_max * 2, 1024);
-    const int patch = round_up_i(PH * PW * kc_max * 2, 1024);
+    const long long res_bytes = (long long)sp * (Cp / kc_max) * round_up_i(taps * bn * kc_max * 2, 1024);
+    const int patch = sp * round_up_i(PH * PW * kc_max * 2, 1024);
     if (res_bytes <= kResidentMax && kSmemBudget - res_bytes >= 2 * patch) {
       *kc_out = kc_max; *bn_out = bn; *res_out = 1;
       return true;
@@ -110,15 +111,17 @@ static bool choose_patch2d(const v2v_conv_desc& c, bool head, int N, int grid_h,
   // 54 us here vs 51 us row tiles even before M blocking), and K blocks below 32 channels turn the 49 taps of a 7x7
   // filter into 1 KB TMA boxes (108->32 @1024x2048: 2.16 ms vs 1.49 ms).
   if (m_total >= 4LL * sms) return false;
-  for (int kc = kc_max; kc >= 32; kc >>= 1) {
-    if (Cp % kc) continue;
-    const int patch = round_up_i(PH * PW * kc * 2, 1024), bstep = round_up_i(taps * bn0 * kc * 2, 1024);
-    if (2 * (patch + bstep) <= kSmemBudget) { *kc_out = kc; *bn_out = bn0; *res_out = 0; return true; }
-  }
+  // (precise plans: halve the N tile before going below 32-channel K blocks; 32-byte rows ingest badly)
+  for (int bn = bn0; bn >= (sp == 2 && !head ? std::min(bn0, 64) : bn0); bn >>= 1)
+    for (int kc = kc_max; kc >= 32; kc >>= 1) {
+      if (Cp % kc) continue;
+      const int patch = sp * round_up_i(PH * PW * kc * 2, 1024), bstep = sp * round_up_i(taps * bn * kc * 2, 1024);
+      if (2 * (patch + bstep) <= kSmemBudget) { *kc_out = kc; *bn_out = bn; *res_out = 0; return true; }
+    }
   return false;
 }
 
-static int conv_geometry(const v2v_conv_desc& c, bool head, int N, int H, int W, bool allow_reuse, ConvGeom* g) {
+static int conv_geometry(const v2v_conv_desc& c, bool head, int N, int H, int W, bool allow_reuse, int sp, ConvGeom* g) {
   memset(g, 0, sizeof(*g));
   V2V_REQUIRE(c.kh >= 1 && c.kw >= 1 && c.kh * c.kw <= V2V_MAX_TAPS, V2V_ERR_UNSUPPORTED, "kernel %dx%d unsupported",
               c.kh, c.kw);
@@ -143,7 +146,7 @@ static int conv_geometry(const v2v_conv_desc& c, bool head, int N, int H, int W,
   g->TH = 128 / g->TW;
   g->R = 1;
   int ng = 0;
-  if (allow_reuse && choose_patch2d(c, head, N, g->grid_h, g->grid_w, &g->patch2d_kc, &g->patch2d_bn, &g->patch2d_resident)) {
+  if (allow_reuse && choose_patch2d(c, head, N, g->grid_h, g->grid_w, sp, &g->patch2d_kc, &g->patch2d_bn, &g->patch2d_resident)) {
     g->n_phases = 1;
     g->TH = 16; g->TW = 8;
     g->R = c.kh * c.kw; g->RW = c.kw;
@@ -260,6 +263,8 @@ using namespace v2v;
 struct v2v_plan {
   int device = 0;
   int impl = V2V_IMPL_UMMA;
+  int precise = 0;            // V2V_PREC_BF16X3: split activations / weights, fp32 raw tensors, 3 MMAs per K block
+  int sp() const { return precise ? 2 : 1; }
   bool allow_reuse = true;
   bool lowered = false, finalized = false;
   std::vector<Value> values;
@@ -302,9 +307,10 @@ static CUtensorMapSwizzle swizzle_for(int kc) {
 static int make_tmap_act(CUtensorMap* tm, const ActDesc& a, int box_w, int box_h, int kc) {
   EncodeTiledFn fn = get_encode_fn();
   V2V_REQUIRE(fn, V2V_ERR_STATE, "cuTensorMapEncodeTiled not available from the driver");
-  cuuint64_t dims[5] = {(cuuint64_t)a.C, (cuuint64_t)a.Wp, (cuuint64_t)a.Hp, (cuuint64_t)a.P, (cuuint64_t)a.N};
-  cuuint64_t strides[4] = {(cuuint64_t)a.C * 2, (cuuint64_t)a.Wp * a.C * 2, (cuuint64_t)a.Hp * a.Wp * a.C * 2,
-                           (cuuint64_t)a.P * a.Hp * a.Wp * a.C * 2};
+  const cuuint64_t cs = (cuuint64_t)a.Cs();      // precise plans: [hi | lo] halves, the lo half at channel coordinate C
+  cuuint64_t dims[5] = {cs, (cuuint64_t)a.Wp, (cuuint64_t)a.Hp, (cuuint64_t)a.P, (cuuint64_t)a.N};
+  cuuint64_t strides[4] = {cs * 2, (cuuint64_t)a.Wp * cs * 2, (cuuint64_t)a.Hp * a.Wp * cs * 2,
+                           (cuuint64_t)a.P * a.Hp * a.Wp * cs * 2};
   cuuint32_t box[5] = {(cuuint32_t)kc, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, a.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -314,7 +320,7 @@ static int make_tmap_act(CUtensorMap* tm, const ActDesc& a, int box_w, int box_h
   return 0;
 }
 
-static int make_tmap_w(CUtensorMap* tm, bf16* w, int Ktotal, int Cout, int BN, int kc) {
+static int make_tmap_w(CUtensorMap* tm, bf16* w, int Ktotal /* columns, both halves */, int Cout, int BN, int kc) {
   EncodeTiledFn fn = get_encode_fn();
   V2V_REQUIRE(fn, V2V_ERR_STATE, "cuTensorMapEncodeTiled not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)Ktotal, (cuuint64_t)Cout};
@@ -328,8 +334,9 @@ static int make_tmap_w(CUtensorMap* tm, bf16* w, int Ktotal, int Cout, int BN, i
   return 0;
 }
 
-static ActDesc make_act(const Value& v, const Req& r) {
+static ActDesc make_act(const Value& v, const Req& r, int split) {
   ActDesc a{};
+  a.split = split;
   a.base = nullptr;
   a.N = v.N; a.H = v.H; a.W = v.W; a.Cvalid = v.C; a.C = pad_channels(v.C);
   a.pad_t = r.pads[0]; a.pad_l = r.pads[1]; a.pad_b = r.pads[2]; a.pad_r = r.pads[3];
@@ -362,7 +369,7 @@ static int lower(v2v_plan* P) {
   for (auto& op : P->gops) {
     if (op.kind == G_CONV || op.kind == G_CONV_ACT || op.kind == G_HEAD) {
       Value& vin = P->values[op.value_in];
-      int rc = conv_geometry(op.conv, op.kind == G_HEAD, vin.N, vin.H, vin.W, P->allow_reuse, &op.geom);
+      int rc = conv_geometry(op.conv, op.kind == G_HEAD, vin.N, vin.H, vin.W, P->allow_reuse, P->sp(), &op.geom);
       if (rc) return rc;
       op.req_index = add_req(vin, conv_req(op.conv, op.geom));
       const v2v_conv_desc& c = op.conv;
@@ -379,7 +386,7 @@ static int lower(v2v_plan* P) {
     if (v.reqs.empty()) { Req r{}; r.mode = PAD_NONE; v.reqs.push_back(r); }
     v.bufs.clear();
     for (auto& r : v.reqs) {
-      P->acts.push_back(make_act(v, r));
+      P->acts.push_back(make_act(v, r, P->precise));
       P->act_pad_mode.push_back(r.mode);
       v.bufs.push_back((int)P->acts.size() - 1);
     }
@@ -401,6 +408,8 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   kp.Cp = pad_channels(op.conv.Cin);
   kp.kc = std::min(kp.Cp, 64);
   kp.MG = 1;
+  const int sp = P->sp();
+  kp.split = P->precise;
   const bool p2d = g.patch2d_kc > 0;
   if (p2d) { kp.kc = g.patch2d_kc; if (op.kind != G_HEAD) kp.BN = g.patch2d_bn; }
   const int m_tiles = kp.N * kp.tiles_x * kp.tiles_y;
@@ -418,16 +427,19 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   bool mblock = false;
   if (!p2d && !op.conv.transposed && op.conv.stride == 1 && g.R >= 5 && g.n_phases == 1 && op.kind != G_HEAD &&
       m_tiles >= 4 * device_sm_count() &&
-      (long long)op.conv.kh * op.conv.kw * kp.Cp * std::min(64, kp.BN) * 2 > kResidentMax) {   // cannot stay resident
+      (long long)sp * op.conv.kh * op.conv.kw * kp.Cp * std::min(64, kp.BN) * 2 > kResidentMax) {   // cannot stay resident
     int c_kc = std::min(kp.Cp, 64), c_bn = std::min(64, round_up(op.conv.Cout, 32)), c_mg = 2;
     if (round_up(op.conv.Cout, 32) == 96 && kp.Cp % 32 == 0) { c_kc = 32; c_bn = 96; }
     if (const char* ef = getenv("V2V_FORCE")) sscanf(ef, "%d,%d,%d", &c_kc, &c_bn, &c_mg);      // timing experiments
     const char* em = getenv("V2V_MG");
     if (em && atoi(em) == 0) c_mg = 0;                                                           // V2V_MG=0: off
-    const int a_slot = round_up((g.TW + g.R - 1) * g.TH * c_kc * 2, 1024), b_slot = round_up(g.R * c_bn * c_kc * 2, 1024);
-    if (c_mg >= 1 && kp.Cp % c_kc == 0 && c_bn % 32 == 0 && c_bn <= 128 && kp.tiles_x % c_mg == 0 &&
-        2 * c_mg * std::max(32, c_bn) <= 512 && 2 * (c_mg * a_slot + b_slot) <= kSmemBudget) {
-      kp.kc = c_kc; kp.BN = c_bn; kp.MG = c_mg; mblock = true;
+    // precise plans double every slot: fall back through smaller K blocks / N tiles until two stages fit
+    const int cand[4][3] = {{c_kc, c_bn, c_mg}, {32, c_bn, c_mg}, {32, 64, c_mg}, {32, 64, 1}};
+    for (int ci = 0; ci < (sp == 2 ? 4 : 1) && !mblock; ++ci) {
+      const int t_kc = cand[ci][0], t_bn = cand[ci][1], t_mg = cand[ci][2];
+      if (t_mg < 1 || kp.Cp % t_kc || t_bn % 32 || t_bn > 128 || kp.tiles_x % t_mg || 2 * t_mg * std::max(32, t_bn) > 512) continue;
+      const int a_slot = sp * round_up((g.TW + g.R - 1) * g.TH * t_kc * 2, 1024), b_slot = sp * round_up(g.R * t_bn * t_kc * 2, 1024);
+      if (2 * (t_mg * a_slot + b_slot) <= kSmemBudget) { kp.kc = t_kc; kp.BN = t_bn; kp.MG = t_mg; mblock = true; }
     }
   }
   kp.cblocks = kp.Cp / kp.kc;
@@ -440,7 +452,8 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   kp.PH = p2d ? g.TH + op.conv.kh - 1 : g.TH;
   kp.sbo_bytes = 8 * kp.row_bytes;
   kp.sbo_a_bytes = p2d ? kp.PW * kp.row_bytes : 8 * kp.row_bytes;
-  kp.a_slot_bytes = round_up(kp.PW * kp.PH * kp.row_bytes, 1024);
+  kp.a_half_bytes = round_up(kp.PW * kp.PH * kp.row_bytes, 1024);
+  kp.a_slot_bytes = sp * kp.a_half_bytes;
   // Epilogue groups: layers whose K loop is shorter than the epilogue of a tile (small Cin * taps) are epilogue bound
   // with one group; statistics allow at most 2 groups (order-independent atomic adds need <= 2 addends per element).
   {
@@ -450,8 +463,10 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   // shared-memory budget: 227 KB - epilogue scratch (12.5 KB per group) - alignment slack - barriers
   const int budget = kSmemBudget;
   // a weight slot holds the R taps served by one activation patch; keep >= 2 slots + 3 patches in the budget
-  while (!p2d && !mblock && g.R > 1 && kp.BN > 32 && 2 * g.R * kp.BN * kp.row_bytes + 3 * kp.a_slot_bytes > budget) kp.BN /= 2;
-  kp.b_slot_bytes = round_up(g.R * kp.BN * kp.row_bytes, 1024);
+  while (!p2d && !mblock && g.R > 1 && kp.BN > 32 && 2 * sp * g.R * kp.BN * kp.row_bytes + 3 * kp.a_slot_bytes > budget)
+    kp.BN = std::max(32, kp.BN / 2 / 32 * 32);
+  kp.b_half_bytes = round_up(g.R * kp.BN * kp.row_bytes, 1024);
+  kp.b_slot_bytes = sp * kp.b_half_bytes;
   kp.n_tiles = (kp.Cout + kp.BN - 1) / kp.BN;
   kp.m_total = kp.N * (kp.tiles_x / kp.MG) * kp.tiles_y;       // M units: MG consecutive x tiles each
   kp.total_tiles = kp.m_total * kp.n_tiles * g.n_phases;
@@ -478,7 +493,7 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
     const int avail = budget - (kp.b_resident ? nB * kp.b_slot_bytes : 0);
     const int nslots = std::max(2, avail / slot);
     const int steps = max_phase_groups * kp.cblocks;
-    const int est = kp.MG * g.R * kp.kmma * std::max(40, kp.BN / 2);
+    const int est = (kp.split ? 3 : 1) * kp.MG * g.R * kp.kmma * std::max(40, kp.BN / 2);
     int cg;
     if (steps * est <= 6000 && 2 * steps <= nslots) cg = steps;           // one group per tile, double buffered
     else {
@@ -504,6 +519,7 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   kp.lrelu_slope = op.slope;
   kp.act = op.act;
   op.Cp = kp.Cp; op.Ktotal = op.conv.kh * op.conv.kw * kp.Cp;
+  kp.Khalf = op.Ktotal;
 }
 
 static int pack_one(const GOp& op, cudaStream_t stream) {
@@ -511,7 +527,7 @@ static int pack_one(const GOp& op, cudaStream_t stream) {
   pp.w = op.conv.weight; pp.transposed = op.conv.transposed;
   pp.w2 = op.conv.Cout2 > 0 ? op.conv.weight2 : nullptr; pp.Cout1 = op.conv.Cout - op.conv.Cout2;
   pp.Cout = op.conv.Cout; pp.Cin = op.conv.Cin; pp.kh = op.conv.kh; pp.kw = op.conv.kw;
-  pp.Cp = op.Cp; pp.ntaps = op.conv.kh * op.conv.kw;
+  pp.Cp = op.Cp; pp.ntaps = op.conv.kh * op.conv.kw; pp.split = op.kp.split;
   for (int ky = 0; ky < op.conv.kh; ++ky)
     for (int kx = 0; kx < op.conv.kw; ++kx) { pp.tap_ky[ky * op.conv.kw + kx] = (int8_t)ky; pp.tap_kx[ky * op.conv.kw + kx] = (int8_t)kx; }
   pp.out = op.wpacked;
@@ -563,6 +579,13 @@ int v2v_plan_create(int device, int conv_impl, v2v_plan** out) {
   return 0;
 }
 
+int v2v_plan_set_precision(v2v_plan* p, int precision) {
+  V2V_REQUIRE(p && !p->lowered && p->gops.empty(), V2V_ERR_STATE, "set the precision before describing the plan");
+  V2V_REQUIRE(precision == V2V_PREC_BF16 || precision == V2V_PREC_BF16X3, V2V_ERR_INVALID, "unknown precision %d", precision);
+  p->precise = (precision == V2V_PREC_BF16X3);
+  return 0;
+}
+
 int v2v_plan_destroy(v2v_plan* p) {
   if (!p) return 0;
   if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
@@ -603,7 +626,7 @@ static int check_conv(v2v_plan* p, int value_in, const v2v_conv_desc* c) {
 int v2v_g_conv(v2v_plan* p, int value_in, const v2v_conv_desc* c, int* raw_out) {
   int rc = check_conv(p, value_in, c); if (rc) return rc;
   V2V_REQUIRE(raw_out, V2V_ERR_INVALID, "null raw_out");
-  ConvGeom g; rc = conv_geometry(*c, false, p->values[value_in].N, p->values[value_in].H, p->values[value_in].W, p->allow_reuse, &g); if (rc) return rc;
+  ConvGeom g; rc = conv_geometry(*c, false, p->values[value_in].N, p->values[value_in].H, p->values[value_in].W, p->allow_reuse, p->sp(), &g); if (rc) return rc;
   GOp op; op.kind = G_CONV; op.value_in = value_in; op.conv = *c;
   Raw r{}; r.N = p->values[value_in].N; r.H = g.out_h; r.W = g.out_w; r.C = c->Cout; r.conv_op = (int)p->gops.size();
   p->raws.push_back(r);
@@ -644,7 +667,7 @@ int v2v_g_norm_act(v2v_plan* p, int raw_in, const v2v_norm_desc* norm, int act, 
 int v2v_g_conv_act(v2v_plan* p, int value_in, const v2v_conv_desc* c, int act, float slope, int* value_out) {
   int rc = check_conv(p, value_in, c); if (rc) return rc;
   V2V_REQUIRE(value_out, V2V_ERR_INVALID, "null value_out");
-  ConvGeom g; rc = conv_geometry(*c, false, p->values[value_in].N, p->values[value_in].H, p->values[value_in].W, p->allow_reuse, &g); if (rc) return rc;
+  ConvGeom g; rc = conv_geometry(*c, false, p->values[value_in].N, p->values[value_in].H, p->values[value_in].W, p->allow_reuse, p->sp(), &g); if (rc) return rc;
   GOp op; op.kind = G_CONV_ACT; op.value_in = value_in; op.conv = *c; op.act = act; op.slope = slope;
   op.value_out = new_value(p, p->values[value_in].N, g.out_h, g.out_w, c->Cout);
   p->gops.push_back(op);
@@ -706,14 +729,15 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
     GOp& op = P->gops[i];
     if (op.kind == G_CONV || op.kind == G_CONV_ACT || op.kind == G_HEAD) {
       fill_conv_params(P, op);
-      w_off[i] = take((size_t)op.conv.Cout * op.Ktotal * sizeof(bf16));
+      w_off[i] = take((size_t)P->sp() * op.conv.Cout * op.Ktotal * sizeof(bf16));
       if (op.kind == G_CONV) {
         Raw& r = P->raws[op.raw];
         r.desc.N = r.N; r.desc.H = r.H; r.desc.W = r.W; r.desc.Cvalid = r.C; r.desc.C = round_up(r.C, 8);
+        r.desc.f32 = P->precise;
         if (P->impl == V2V_IMPL_UMMA) { r.tiles_per_img = op.kp.grid; r.num_phases = op.kp.num_phases; }
         else { r.tiles_per_img = 1; r.num_phases = 1; }
         r.stats_rows = r.num_phases * r.N * r.tiles_per_img;
-        raw_off[op.raw].raw = take(r.desc.elems() * sizeof(bf16));
+        raw_off[op.raw].raw = take(r.desc.elems() * r.desc.elem_bytes());
         raw_off[op.raw].scale = take((size_t)r.N * r.C * sizeof(float));
         raw_off[op.raw].shift = take((size_t)r.N * r.C * sizeof(float));
       }
@@ -733,7 +757,7 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
   for (size_t i = 0; i < P->acts.size(); ++i) P->acts[i].base = reinterpret_cast<bf16*>(base + act_off[i]);
   for (size_t i = 0; i < P->raws.size(); ++i) {
     Raw& r = P->raws[i];
-    r.desc.base = reinterpret_cast<bf16*>(base + raw_off[i].raw);
+    r.desc.base = base + raw_off[i].raw;
     r.stats = reinterpret_cast<float*>(base + raw_off[i].stats);
     r.scale = reinterpret_cast<float*>(base + raw_off[i].scale);
     r.shift = reinterpret_cast<float*>(base + raw_off[i].shift);
@@ -766,7 +790,7 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
         kp.io = P->io_dev;
         if (op.kind == G_CONV) {
           Raw& r = P->raws[op.raw];
-          kp.epi = EPI_RAW_STATS; kp.out = r.desc.base; kp.out_C = r.desc.C;
+          kp.epi = EPI_RAW_STATS; kp.out = r.desc.base; kp.out_C = r.desc.C; kp.out_f32 = r.desc.f32;
           kp.stats = r.stats; kp.stats_C = r.C; kp.bias = nullptr;
         } else if (op.kind == G_CONV_ACT) {
           const Value& vo = P->values[op.value_out];
@@ -785,7 +809,7 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
         }
         if (P->impl == V2V_IMPL_UMMA) {
           rc = make_tmap_act(&op.tmA, ain, kp.PW, kp.PH, kp.kc); if (rc) return rc;
-          rc = make_tmap_w(&op.tmB, op.wpacked, op.Ktotal, op.conv.Cout, kp.BN, kp.kc); if (rc) return rc;
+          rc = make_tmap_w(&op.tmB, op.wpacked, P->sp() * op.Ktotal, op.conv.Cout, kp.BN, kp.kc); if (rc) return rc;
         }
         rc = pack_one(op, stream); if (rc) return rc;
         XOp x; x.kind = X_CONV; x.gop = (int)i;
@@ -826,7 +850,8 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
           XOp a; a.kind = X_APPLY;
           ApplyParams& ap = a.app;
           ap.raw = r.desc;
-          ap.raw.base = r.desc.base + op.n_off; ap.raw.Cvalid = op.cC;       // channel slice, full row stride
+          ap.raw.base = reinterpret_cast<uint8_t*>(r.desc.base) + (size_t)op.n_off * r.desc.elem_bytes();
+          ap.raw.Cvalid = op.cC;                                               // channel slice, full row stride
           ap.scale = op.norm.kind != V2V_NORM_NONE ? r.scale + op.n_off : nullptr; ap.shift = r.shift + op.n_off;
           ap.scale_stride = r.C;
           ap.act = op.act; ap.slope = op.slope;
@@ -957,10 +982,10 @@ int64_t v2v_plan_describe(const v2v_plan* P_, char* buf, int64_t cap) {
     snprintf(t, sizeof(t),
              "%s{\"kind\":%d,\"Cin\":%d,\"Cout\":%d,\"k\":[%d,%d],\"stride\":%d,\"transposed\":%d,\"in\":%d,\"TH\":%d,\"TW\":%d,"
              "\"R\":%d,\"groups\":%d,\"phases\":%d,\"grid\":[%d,%d],\"out\":[%d,%d],"
-             "\"BN\":%d,\"kc\":%d,\"MG\":%d,\"CG\":%d,\"SG\":%d,\"resident\":%d,\"EG\":%d,\"units\":%d}",
+             "\"BN\":%d,\"kc\":%d,\"MG\":%d,\"CG\":%d,\"SG\":%d,\"resident\":%d,\"EG\":%d,\"units\":%d,\"split\":%d}",
              first ? "" : ",", (int)op.kind, op.conv.Cin, op.conv.Cout, op.conv.kh, op.conv.kw, op.conv.stride, op.conv.transposed,
              op.value_in, g.TH, g.TW, g.R, g.n_groups, g.n_phases, g.grid_h, g.grid_w, g.out_h, g.out_w,
-             kp.BN, kp.kc, kp.MG, kp.CG, kp.SG, kp.b_resident, kp.EG, kp.total_units);
+             kp.BN, kp.kc, kp.MG, kp.CG, kp.SG, kp.b_resident, kp.EG, kp.total_units, kp.split);
     s += t;
     first = false;
   }
@@ -979,7 +1004,7 @@ int v2v_conv_tap_table(const v2v_conv_desc* conv, int H, int W, int allow_reuse,
                        int* pads, int* parity, int* grid_hw, int* out_hw, int* mul) {
   V2V_REQUIRE(conv, V2V_ERR_INVALID, "null conv");
   ConvGeom g;
-  int rc = conv_geometry(*conv, false, 1, H, W, allow_reuse != 0, &g);
+  int rc = conv_geometry(*conv, false, 1, H, W, allow_reuse != 0, 1, &g);
   if (rc) return rc;
   *n_groups = g.n_groups; R[0] = g.R; R[1] = g.RW; *n_phases = g.n_phases; *parity = g.parity; *mul = g.mul;
   for (int i = 0; i < g.n_groups; ++i) { plane[i] = g.groups[i].plane; dy[i] = g.groups[i].dy; dx[i] = g.groups[i].dx; tap0[i] = g.groups[i].tap0; }

@@ -17,6 +17,11 @@ typedef __nv_bfloat16 bf16;
 //   parity == 1 :  [n][(yp&1)*2 + (xp&1)][yp>>1][xp>>1][c]   plane dims Hp x Wp (= ceil(padded/2))
 // C is the padded channel count (16, 32, or a multiple of 64; channels >= Cvalid are zero): one K block of the
 // implicit GEMM is min(C, 64) channels = one shared-memory row of 32 / 64 / 128 bytes (TMA swizzle 32B / 64B / 128B).
+//
+// Precise plans (split == 1, "bf16x3"): every value x is stored as the bf16 pair hi = bf16(x), lo = bf16(x - hi)
+// (16 mantissa bits together), a pixel holding [hi channels 0..C) | lo channels 0..C)]: 2*C bf16 per pixel.  The conv
+// kernel then accumulates A_hi*B_hi + A_lo*B_hi + A_hi*B_lo in fp32 (three tcgen05.mma per K block; the dropped lo*lo
+// term is 2^-18 relative), which makes the conv stack fp32-class while staying on the bf16 tensor pipe.
 struct ActDesc {
   bf16* base;
   int N, H, W;          // logical (unpadded) extent
@@ -25,22 +30,26 @@ struct ActDesc {
   int pad_t, pad_l, pad_b, pad_r;
   int parity;           // 0 / 1
   int P, Hp, Wp;        // planes and plane extent
-  __host__ __device__ size_t elems() const { return (size_t)N * P * Hp * Wp * C; }
-  __host__ __device__ size_t offset(int n, int y, int x) const {   // element offset of channel 0
+  int split;            // 1: [hi | lo] bf16 pair per value (precise plans)
+  __host__ __device__ int Cs() const { return C << split; }        // bf16 elements per pixel
+  __host__ __device__ size_t elems() const { return (size_t)N * P * Hp * Wp * Cs(); }
+  __host__ __device__ size_t offset(int n, int y, int x) const {   // element offset of channel 0 (hi half)
     int yp = y + pad_t, xp = x + pad_l;
     if (parity) {
       int pl = ((yp & 1) << 1) | (xp & 1);
-      return ((((size_t)n * 4 + pl) * Hp + (yp >> 1)) * Wp + (xp >> 1)) * C;
+      return ((((size_t)n * 4 + pl) * Hp + (yp >> 1)) * Wp + (xp >> 1)) * Cs();
     }
-    return (((size_t)n * Hp + yp) * Wp + xp) * C;
+    return (((size_t)n * Hp + yp) * Wp + xp) * Cs();
   }
 };
 
-// Raw conv output: dense NHWC bf16, C = channel stride (multiple of 8).
+// Raw conv output: dense NHWC, C = channel stride (multiple of 8); bf16, or fp32 in precise plans.
 struct RawDesc {
-  bf16* base;
+  void* base;
   int N, H, W, C, Cvalid;
+  int f32;              // element type: 0 bf16, 1 fp32
   __host__ __device__ size_t elems() const { return (size_t)N * H * W * C; }
+  __host__ __device__ size_t elem_bytes() const { return f32 ? 4 : 2; }
 };
 
 enum PadMode { PAD_NONE = 0, PAD_ZERO = 1, PAD_REFLECT = 2 };
@@ -80,6 +89,10 @@ struct ConvKernelParams {
   int CG, SG;                        // K-loop steps per barrier / commit group, group slots in the ring
   int MG, mg_total, total_units;     // M tiles accumulated side by side per weight pass (work unit), units per key, all units
   int num_phases;
+  int split;                         // precise plan: A and B slots hold a hi and a lo half; 3 MMAs per (tap, K block)
+  int a_half_bytes, b_half_bytes;    // byte offset of the lo half inside an A / B slot
+  int Khalf;                         // taps * Cp: column offset of the lo half in the packed weight matrix
+  int out_f32;                       // EPI_RAW_STATS: raw output element type (1 = fp32)
   ConvPhase phases[V2V_MAX_PHASES];
   ConvGroup groups[V2V_MAX_TAPS];
   // epilogue
@@ -170,6 +183,7 @@ struct PackParams {
   int Cout, Cin, kh, kw;
   int Cp, ntaps;
   int8_t tap_ky[V2V_MAX_TAPS], tap_kx[V2V_MAX_TAPS];   // filter coordinates of packed tap t
+  int split;               // 1: [Cout][2][ntaps * Cp] (hi row half, then lo row half)
   bf16* out;               // [Cout][ntaps * Cp]
 };
 
@@ -184,6 +198,12 @@ struct CompositeParams {
 };
 
 cudaError_t launch_raw_stats(const RawDesc& raw, float* stats, int stats_C, cudaStream_t stream);
+
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi)
+__device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
 cudaError_t launch_stats_finalize(const FinalizeParams& p, cudaStream_t stream);
 cudaError_t launch_norm_apply(const ApplyParams& p, cudaStream_t stream);
 cudaError_t launch_import_nchw(const ImportParams& p, cudaStream_t stream);

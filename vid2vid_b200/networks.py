@@ -12,6 +12,7 @@ tensor, as the reference does at inference because it never calls .eval() on G/D
 """
 import copy
 import functools
+import os
 
 import torch
 import torch.nn as nn
@@ -231,12 +232,27 @@ def _can_pair(mods_a, mods_b):
             ca.kernel_size == cb.kernel_size and ca.stride == cb.stride and ca.out_channels % 8 == 0)
 
 
+# Arithmetic of the conv stack (include/v2v_b200.h V2V_PREC_*): 'precise' = split-bf16 3-MMA, fp32-class -- the mode
+# the parity tests against the fp32 reference and the headline benchmark use; 'fast' = plain bf16 operands.
+DEFAULT_PRECISION = os.environ.get('V2V_PRECISION', 'precise')
+
+
+def set_default_precision(mode):
+    global DEFAULT_PRECISION
+    assert mode in ('fast', 'precise')
+    DEFAULT_PRECISION = mode
+
+
 class _Planned(nn.Module):
     """Caches one plan per input-shape key; re-packs weights when parameters were modified in place
     and rebuilds when their storage moved (.cuda(), .to())."""
 
     align_corners = False   # installed-PyTorch grid_sample default; True = PyTorch-0.4 semantics (App. B #2)
     use_cuda_graph = True
+    precision = None        # None: DEFAULT_PRECISION at plan-build time; or 'fast' / 'precise' per module
+
+    def _precision(self):
+        return self.precision or DEFAULT_PRECISION
 
     def _plans(self):
         if '_plan_cache' not in self.__dict__:
@@ -252,11 +268,13 @@ class _Planned(nn.Module):
 
     def _get_plan(self, key, device, build):
         ptrs, ver = self._signature()
+        key = key + (self._precision(),)
         ent = self._plans().get(key)
         if ent is not None and ent['ptrs'] != ptrs:
             ent = None
         if ent is None:
-            plan = Plan(device.index if device.index is not None else torch.cuda.current_device())
+            plan = Plan(device.index if device.index is not None else torch.cuda.current_device(),
+                        precision=self._precision())
             build(plan)
             plan.finalize()
             ent = {'plan': plan, 'ptrs': ptrs, 'ver': ver}
@@ -265,10 +283,6 @@ class _Planned(nn.Module):
             ent['plan'].repack()
             ent['ver'] = ver
         return ent['plan']
-
-    def _bump_versions_done(self, key):
-        # running stats are updated in place by our kernels (not through torch), versions unchanged
-        pass
 
     @staticmethod
     def _require_cuda(*ts):
@@ -642,7 +656,7 @@ class MultiscaleDiscriminator(_Planned):
         def build(p):
             shapes_box['s'] = self._describe(p, d, N, H, W)
         plan = self._get_plan(key, x.device, build)
-        shapes = self._plans()[key].setdefault('shapes', shapes_box.get('s'))
+        shapes = self._plans()[key + (self._precision(),)].setdefault('shapes', shapes_box.get('s'))
         outs = [torch.empty((N, c, h, w), device=x.device, dtype=torch.float32) for (c, h, w) in shapes]
         io = [x] + [o if (self.getIntermFeat or j == len(outs) - 1) else None for j, o in enumerate(outs)]
         plan.run(io, self.use_cuda_graph)

@@ -57,12 +57,14 @@ def norm_desc(m):
 
 
 class Plan:
-    def __init__(self, device=0, impl=None):
+    def __init__(self, device=0, impl=None, precision='fast'):
         if impl is None:
             impl = L.IMPL_SIMT if os.environ.get('V2V_CONV_IMPL') == 'simt' else L.IMPL_UMMA
         self._h = C.c_void_p()
         self.device = device
+        self.precision = precision
         L.check(L.lib().v2v_plan_create(device, impl, C.byref(self._h)))
+        L.check(L.lib().v2v_plan_set_precision(self._h, {'fast': L.PREC_BF16, 'precise': L.PREC_BF16X3}[precision]))
         self._keep = []
         self.finalized = False
         self.n_slots = 0
