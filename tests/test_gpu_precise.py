@@ -29,6 +29,9 @@ from vid2vid_b200.utils import det_fill_, make_opt, synth_label_sequence
 pytestmark = pytest.mark.gpu
 
 IMG_MAX, FLOW_MAX_PX, FEAT_REL = 5e-3, 0.02, 1e-3
+# Single recurrent steps from GENERATED previous frames: with random weights the previous frame is noise-like (gradients of
+# O(1) per pixel), so the warp turns the <= 0.02 px flow tolerance into up to 0.02 of image error at isolated pixels.
+IMG_STEP_MAX, IMG_STEP_MEAN = 2e-2, 1e-3
 
 
 def _model(opt, seed, flow_scale=1.0):
@@ -151,9 +154,10 @@ def test_cfg2_32_recurrent_frames_single_step_error_does_not_grow():
                 ref, _ = orc.inference(A, A)
         fb, _ = m.inference(A, None, A)
         if t in checked:
-            worst.append(_cmp('cfg2 frame %2d (single step)' % t, fb, ref, IMG_MAX))
-    # no growth: the last checked frames are not worse than 4x the first ones (they are independent single steps)
-    assert max(worst[-3:]) <= 4 * max(worst[:3]) + 1e-4, worst
+            worst.append(_cmp('cfg2 frame %2d (single step)' % t, fb, ref, IMG_STEP_MAX))
+            assert (fb.cpu() - ref).abs().mean().item() <= IMG_STEP_MEAN
+    # no growth: the last checked frames are not worse than 3x the early generated-state ones (independent single steps)
+    assert max(worst[-3:]) <= 3 * max(worst[1:4]) + 1e-4, worst
 
 
 def test_free_running_divergence_tracks_the_fp32_noise_floor():

@@ -22,7 +22,7 @@ template <int CT>
 __global__ void __launch_bounds__(256) import_nchw_kernel(ImportParams p) {
   __shared__ float tile[CT][129];
   pdl_prologue();
-  const float* src = reinterpret_cast<const float*>(p.io[p.slot]);
+  const float* src = p.direct ? p.direct : reinterpret_cast<const float*>(p.io[p.slot]);
   const ActDesc& o = p.out;
   const int Wpad = o.W + o.pad_l + o.pad_r, Hpad = o.H + o.pad_t + o.pad_b;
   const int xt = blockIdx.x * 128;
@@ -52,7 +52,11 @@ __global__ void __launch_bounds__(256) import_nchw_kernel(ImportParams p) {
       const bool cv = (cc + 8 * h < CT) && c < o.Cvalid;
       const float* row = src + (((size_t)n * p.C_src + p.c_off + (cv ? c : 0)) * o.H + y) * o.W;
 #pragma unroll
-      for (int sx = 0; sx < 4; ++sx) v[h][sx] = (cv && !zero_px[sx]) ? __ldg(row + xs[sx]) : 0.f;
+      for (int sx = 0; sx < 4; ++sx) {
+        float t = (cv && !zero_px[sx]) ? __ldg(row + xs[sx]) : 0.f;
+        if (p.act == ACT_LRELU) t = t > 0.f ? t : t * p.slope;
+        v[h][sx] = t;
+      }
     }
 #pragma unroll
     for (int h = 0; h < 2; ++h)
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(256) import_nchw_kernel(ImportParams p) {
 __global__ void __launch_bounds__(256) export_nchw_kernel(ExportParams p) {
   __shared__ float tile[32][129];
   pdl_prologue();
-  float* dst = reinterpret_cast<float*>(p.io[p.slot]);
+  float* dst = p.direct ? p.direct : reinterpret_cast<float*>(p.io[p.slot]);
   const ActDesc& a = p.in;
   const int xt = blockIdx.x * 128;
   const int y = blockIdx.y % a.H, n = blockIdx.y / a.H;
@@ -149,6 +153,55 @@ __global__ void pack_weights_kernel(PackParams p) {
     if (p.split) split_bf16(v, p.out[(size_t)co * 2 * K + k], p.out[(size_t)co * 2 * K + K + k]);
     else p.out[idx] = __float2bfloat16_rn(v);
   }
+}
+
+// torch.cat along channels: one thread per (padded pixel of out, source channel), channel fastest.
+__global__ void __launch_bounds__(256) act_copy_kernel(CopyParams p) {
+  pdl_prologue();
+  const ActDesc& o = p.out;
+  const ActDesc& a = p.in;
+  const int Wpad = o.W + o.pad_l + o.pad_r, Hpad = o.H + o.pad_t + o.pad_b, C = a.Cvalid;
+  const size_t total = (size_t)o.N * Hpad * Wpad * C;
+  for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % C);
+    size_t t = idx / C;
+    const int xp = (int)(t % Wpad); t /= Wpad;
+    const int yp = (int)(t % Hpad);
+    const int n = (int)(t / Hpad);
+    int y = yp - o.pad_t, x = xp - o.pad_l;
+    const bool halo = (y < 0 || y >= o.H || x < 0 || x >= o.W);
+    bf16 hi = __float2bfloat16_rn(0.f), lo = hi;
+    if (!halo || p.pad_mode == PAD_REFLECT) {
+      if (halo) { y = reflect_i(y, o.H); x = reflect_i(x, o.W); }
+      const bf16* sp = a.base + a.offset(n, y, x) + c;
+      hi = sp[0];
+      if (a.split) lo = sp[a.C];
+    }
+    bf16* dp = o.base + o.offset(n, yp - o.pad_t, xp - o.pad_l) + p.c_off + c;
+    dp[0] = hi;
+    if (o.split) dp[o.C] = lo;
+  }
+}
+
+// scale = 1, shift = bias for the normalise pass of a norm-less biased convolution
+__global__ void bias_affine_kernel(float* scale, float* shift, const float* bias, int N, int C, int stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * C) return;
+  const int n = i / C, c = i - n * C;
+  scale[(size_t)n * stride + c] = 1.f;
+  shift[(size_t)n * stride + c] = bias ? bias[c] : 0.f;
+}
+
+cudaError_t launch_act_copy(const CopyParams& p, cudaStream_t stream) {
+  const size_t total = (size_t)p.out.N * (p.out.H + p.out.pad_t + p.out.pad_b) * (p.out.W + p.out.pad_l + p.out.pad_r) * p.in.Cvalid;
+  size_t b = (total + 255) / 256;
+  if (b > 148 * 16) b = 148 * 16;
+  return launch_pdl(act_copy_kernel, dim3((unsigned)(b ? b : 1)), dim3(256), 0, stream, p);
+}
+
+cudaError_t launch_bias_affine(float* scale, float* shift, const float* bias, int N, int C, int stride, cudaStream_t stream) {
+  bias_affine_kernel<<<(N * C + 255) / 256, 256, 0, stream>>>(scale, shift, bias, N, C, stride);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_import_nchw(const ImportParams& p, cudaStream_t stream) {

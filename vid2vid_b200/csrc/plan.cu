@@ -70,7 +70,7 @@ struct ConvGeom {
 
 
 static inline int round_up_i(int a, int b) { return round_up(a, b); }
-static const int kSmemBudget = 196 * 1024;      // operand slots + resident weights (epilogue scratch and barriers excluded)
+static const int kSmemBudget = 200 * 1024;      // operand slots + resident weights (227 KB - 2 x 12.5 KB epilogue scratch - alignment - barriers)
 static const int kResidentMax = 150 * 1024;
 
 // 2-D patch mode (stride-1 filters): a tile of 16 rows x 8 pixels makes every 8-row core-matrix group of the A operand
@@ -98,11 +98,15 @@ static bool choose_patch2d(const v2v_conv_desc& c, bool head, int N, int grid_h,
     static const bool half_ok = [] { const char* e = getenv("V2V_P2D_HALF"); return e && e[0] == '1'; }();
     if (pass == 1 && (!half_ok || bn0 < 128 || m_total < 4LL * sms)) break;
     if (m_total <= sms) break;
-    const long long res_bytes = (long long)sp * (Cp / kc_max) * round_up_i(taps * bn * kc_max * 2, 1024);
-    const int patch = sp * round_up_i(PH * PW * kc_max * 2, 1024);
-    if (res_bytes <= kResidentMax && kSmemBudget - res_bytes >= 2 * patch) {
-      *kc_out = kc_max; *bn_out = bn; *res_out = 1;
-      return true;
+    // precise plans also try 32-channel K blocks: the resident weight set is the same size, the two patch stages halve
+    for (int kc = kc_max; kc >= (sp == 2 ? 32 : kc_max); kc >>= 1) {
+      if (Cp % kc) continue;
+      const long long res_bytes = (long long)sp * (Cp / kc) * round_up_i(taps * bn * kc * 2, 1024);
+      const int patch = sp * round_up_i(PH * PW * kc * 2, 1024);
+      if (res_bytes <= kResidentMax && kSmemBudget - res_bytes >= 2 * patch) {
+        *kc_out = kc; *bn_out = bn; *res_out = 1;
+        return true;
+      }
     }
   }
   // Streamed weights: only when a CTA sees few M tiles (the weights pass through once per unit either way, and the
@@ -221,7 +225,7 @@ struct Raw {
   std::vector<int> running_done;   // channel offsets whose running stats already have an updating launch
 };
 
-enum GKind { G_INPUT, G_CONV, G_NORM_ACT, G_CONV_ACT, G_HEAD, G_EXPORT, G_COMPOSITE };
+enum GKind { G_INPUT, G_CONV, G_NORM_ACT, G_CONV_ACT, G_HEAD, G_EXPORT, G_COMPOSITE, G_CONCAT, G_CORR };
 struct GOp {
   GKind kind;
   // input
@@ -236,6 +240,9 @@ struct GOp {
   int n_off = 0, cC = 0;     // G_NORM_ACT: channel slice [n_off, n_off + cC) of the raw
   v2v_head_channel head[V2V_MAX_HEAD];
   CompositeParams comp{};
+  std::vector<int> cat_in;   // G_CONCAT: source values in channel order
+  int value_in2 = -1;        // G_CORR: second operand
+  int corr[5] = {0, 0, 0, 0, 0};   // pad, kernel, max_disp, stride1, stride2
   // lowered
   bf16* wpacked = nullptr; int Ktotal = 0, Cp = 0;
   double macs = 0.0;
@@ -243,7 +250,7 @@ struct GOp {
   ConvKernelParams kp{};
 };
 
-enum XKind { X_IMPORT, X_CONV, X_RAWSTATS, X_FINALIZE, X_APPLY, X_EXPORT, X_COMPOSITE, X_MEMSET };
+enum XKind { X_IMPORT, X_CONV, X_RAWSTATS, X_FINALIZE, X_APPLY, X_EXPORT, X_COMPOSITE, X_MEMSET, X_COPY, X_CORR };
 struct XOp {
   XKind kind;
   int gop = -1;
@@ -252,6 +259,8 @@ struct XOp {
   FinalizeParams fin{};
   ApplyParams app{};
   CompositeParams comp{};
+  CopyParams copy{};
+  CorrParams corr{};
   RawDesc rawd{}; float* stats = nullptr; int stats_C = 0;
   void* ms_ptr = nullptr; size_t ms_bytes = 0;
 };
@@ -275,6 +284,8 @@ struct v2v_plan {
   std::vector<XOp> xops;
   int n_slots = 0;
   double conv_macs = 0.0;
+  struct BiasAffine { float* scale; float* shift; const float* bias; int N, C, stride; };
+  std::vector<BiasAffine> bias_affines;   // norm-less biased convs routed through the normalise pass (scale 1, shift bias)
   // device
   void* arena = nullptr; size_t arena_bytes = 0;
   void** io_dev = nullptr;
@@ -380,6 +391,11 @@ static int lower(v2v_plan* P) {
       for (int k = 0; k < 2; ++k) if (op.add[k] >= 0) P->values[op.add[k]].interior_use = true;
     } else if (op.kind == G_EXPORT) {
       P->values[op.value_in].interior_use = true;
+    } else if (op.kind == G_CONCAT) {
+      for (int v : op.cat_in) P->values[v].interior_use = true;
+    } else if (op.kind == G_CORR) {
+      P->values[op.value_in].interior_use = true;
+      P->values[op.value_in2].interior_use = true;
     }
   }
   for (auto& v : P->values) {
@@ -463,6 +479,24 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   // shared-memory budget: 227 KB - epilogue scratch (12.5 KB per group) - alignment slack - barriers
   const int budget = kSmemBudget;
   // a weight slot holds the R taps served by one activation patch; keep >= 2 slots + 3 patches in the budget
+  if (sp == 2 && !p2d && !mblock && g.R > 1) {
+    // precise plans: every slot doubles.  N tiles below 64 make the (3x) MMAs issue bound, so try (K block, N tile) in the
+    // order (kc, BN), (kc, BN/2 >= 64), (32, BN), (32, BN/2 >= 64) before falling through to the generic halving
+    const int bn0 = kp.BN, kc0 = kp.kc;
+    bool ok = false;
+    for (int t = 0; t < 4 && !ok; ++t) {
+      const int t_kc = (t & 2) ? 32 : kc0, t_bn = (t & 1) ? bn0 / 2 : bn0;
+      if (t_kc > kc0 || kp.Cp % t_kc || ((t & 1) && (t_bn < 64 || t_bn % 32))) continue;
+      const int a_sl = sp * round_up(kp.PW * kp.PH * t_kc * 2, 1024);
+      if (2 * sp * g.R * t_bn * t_kc * 2 + 3 * a_sl <= budget) {
+        kp.kc = t_kc; kp.BN = t_bn; ok = true;
+        kp.cblocks = kp.Cp / kp.kc; kp.row_bytes = kp.kc * 2; kp.kmma = kp.kc / 16;
+        kp.layout_type = kp.kc == 64 ? 2 : (kp.kc == 32 ? 4 : 6);
+        kp.sbo_bytes = 8 * kp.row_bytes; kp.sbo_a_bytes = 8 * kp.row_bytes;
+        kp.a_half_bytes = round_up(kp.PW * kp.PH * kp.row_bytes, 1024); kp.a_slot_bytes = sp * kp.a_half_bytes;
+      }
+    }
+  }
   while (!p2d && !mblock && g.R > 1 && kp.BN > 32 && 2 * sp * g.R * kp.BN * kp.row_bytes + 3 * kp.a_slot_bytes > budget)
     kp.BN = std::max(32, kp.BN / 2 / 32 * 32);
   kp.b_half_bytes = round_up(g.R * kp.BN * kp.row_bytes, 1024);
@@ -548,6 +582,11 @@ static int run_xop(v2v_plan* P, const XOp& x, cudaStream_t s) {
     case X_COMPOSITE: V2V_CUDA(launch_composite(x.comp, s)); break;
     case X_RAWSTATS: V2V_CUDA(launch_raw_stats(x.rawd, x.stats, x.stats_C, s)); break;
     case X_MEMSET: V2V_CUDA(cudaMemsetAsync(x.ms_ptr, 0, x.ms_bytes, s)); break;
+    case X_COPY: V2V_CUDA(launch_act_copy(x.copy, s)); break;
+    case X_CORR:
+      V2V_CUDA(launch_correlation(x.corr.in1, x.corr.in2, x.corr.out, x.corr.N, x.corr.C, x.corr.H, x.corr.W, x.corr.pad, x.corr.k,
+                                  x.corr.max_disp, x.corr.s1, x.corr.s2, s));
+      break;
     case X_CONV: {
       const GOp& op = P->gops[x.gop];
       if (P->impl == V2V_IMPL_UMMA) V2V_CUDA(launch_conv_umma(op.tmA, op.tmB, op.kp, s));
@@ -685,6 +724,45 @@ int v2v_g_head(v2v_plan* p, int value_in, const v2v_conv_desc* c, const v2v_head
   return 0;
 }
 
+int v2v_g_concat(v2v_plan* p, const int* values, int n, int* value_out) {
+  V2V_REQUIRE(p && !p->lowered && values && n >= 1 && value_out, V2V_ERR_STATE, "plan already lowered or null");
+  GOp op; op.kind = G_CONCAT;
+  int C = 0;
+  for (int i = 0; i < n; ++i) {
+    V2V_REQUIRE(values[i] >= 0 && values[i] < (int)p->values.size(), V2V_ERR_INVALID, "bad value id %d", values[i]);
+    const Value& a = p->values[values[i]], &a0 = p->values[values[0]];
+    V2V_REQUIRE(a.N == a0.N && a.H == a0.H && a.W == a0.W, V2V_ERR_INVALID, "concat operands differ in extent");
+    C += a.C;
+    op.cat_in.push_back(values[i]);
+  }
+  const int N0 = p->values[values[0]].N, H0 = p->values[values[0]].H, W0 = p->values[values[0]].W;
+  op.value_out = new_value(p, N0, H0, W0, C);
+  p->gops.push_back(op);
+  *value_out = op.value_out;
+  return 0;
+}
+
+int v2v_g_correlation(v2v_plan* p, int value_a, int value_b, int pad_size, int kernel_size, int max_displacement, int stride1,
+                      int stride2, int act, float slope, int* value_out) {
+  V2V_REQUIRE(p && !p->lowered && value_out, V2V_ERR_STATE, "plan already lowered or null");
+  V2V_REQUIRE(value_a >= 0 && value_a < (int)p->values.size() && value_b >= 0 && value_b < (int)p->values.size(), V2V_ERR_INVALID,
+              "bad value id");
+  const Value a = p->values[value_a], b = p->values[value_b];
+  V2V_REQUIRE(a.N == b.N && a.C == b.C && a.H == b.H && a.W == b.W, V2V_ERR_INVALID, "correlation operands differ in shape");
+  V2V_REQUIRE(kernel_size == 1 && stride1 == 1 && pad_size == max_displacement, V2V_ERR_UNSUPPORTED,
+              "correlation: only kernel 1, stride1 1, pad == max displacement (FlowNetC.py:31)");
+  V2V_REQUIRE(act == V2V_ACT_NONE || act == V2V_ACT_LRELU, V2V_ERR_UNSUPPORTED, "correlation: activation must be none / LeakyReLU");
+  int oc, oh, ow;
+  int rc = v2v_correlation_out_shape(a.H, a.W, pad_size, kernel_size, max_displacement, stride1, stride2, &oc, &oh, &ow);
+  if (rc) return rc;
+  GOp op; op.kind = G_CORR; op.value_in = value_a; op.value_in2 = value_b; op.act = act; op.slope = slope;
+  op.corr[0] = pad_size; op.corr[1] = kernel_size; op.corr[2] = max_displacement; op.corr[3] = stride1; op.corr[4] = stride2;
+  op.value_out = new_value(p, a.N, oh, ow, oc);
+  p->gops.push_back(op);
+  *value_out = op.value_out;
+  return 0;
+}
+
 int v2v_g_export(v2v_plan* p, int value, int slot) {
   V2V_REQUIRE(p && !p->lowered, V2V_ERR_STATE, "plan already lowered or null");
   V2V_REQUIRE(value >= 0 && value < (int)p->values.size() && slot >= 0, V2V_ERR_INVALID, "bad export");
@@ -743,6 +821,12 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
       }
     }
   }
+  std::vector<size_t> corr_off(P->gops.size(), 0);
+  for (size_t i = 0; i < P->gops.size(); ++i)
+    if (P->gops[i].kind == G_CORR) {
+      const Value& a = P->values[P->gops[i].value_in], &o = P->values[P->gops[i].value_out];
+      corr_off[i] = take((2 * (size_t)a.N * a.C * a.H * a.W + (size_t)o.N * o.C * o.H * o.W) * sizeof(float));
+    }
   // all norm-statistics partials live in one contiguous region that is zeroed at the start of every run
   // (a CTA only writes the (phase, image) rows it actually worked on)
   const size_t stats_begin = off;
@@ -842,8 +926,13 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
           { const char* ef = getenv("V2V_FUSE_FINALIZE"); fuse_fin = (ef && ef[0] == '1') && r.N <= 8; }
           fin_params = fp;
           if (!fuse_fin) P->xops.push_back(f);
-        } else {
-          V2V_REQUIRE(cop.conv.bias == nullptr, V2V_ERR_UNSUPPORTED, "norm-less conv with bias must use v2v_g_conv_act");
+        } else if (cop.conv.bias != nullptr) {
+          // norm-less biased conv (FlowNet2's conv / deconv / predict_flow units): the normalise pass runs with scale 1 and
+          // shift = bias, written here and after every repack
+          V2V_REQUIRE(op.n_off == 0 && cop.conv.Cout2 == 0, V2V_ERR_UNSUPPORTED, "biased norm-less conv cannot be sliced");
+          v2v_plan::BiasAffine ba{r.scale, r.shift, cop.conv.bias, r.N, r.C, r.C};
+          P->bias_affines.push_back(ba);
+          V2V_CUDA(launch_bias_affine(ba.scale, ba.shift, ba.bias, ba.N, ba.C, ba.stride, stream));
         }
         const Value& vo = P->values[op.value_out];
         for (size_t m = 0; m < vo.bufs.size(); ++m) {
@@ -852,7 +941,8 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
           ap.raw = r.desc;
           ap.raw.base = reinterpret_cast<uint8_t*>(r.desc.base) + (size_t)op.n_off * r.desc.elem_bytes();
           ap.raw.Cvalid = op.cC;                                               // channel slice, full row stride
-          ap.scale = op.norm.kind != V2V_NORM_NONE ? r.scale + op.n_off : nullptr; ap.shift = r.shift + op.n_off;
+          ap.scale = (op.norm.kind != V2V_NORM_NONE || cop.conv.bias != nullptr) ? r.scale + op.n_off : nullptr;
+          ap.shift = r.shift + op.n_off;
           ap.scale_stride = r.C;
           ap.act = op.act; ap.slope = op.slope;
           ap.n_add = 0;
@@ -877,6 +967,41 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
         P->xops.push_back(x);
         break;
       }
+      case G_CONCAT: {
+        const Value& vo = P->values[op.value_out];
+        for (size_t m = 0; m < vo.bufs.size(); ++m) {
+          int c_off = 0;
+          for (int src : op.cat_in) {
+            XOp x; x.kind = X_COPY;
+            x.copy.in = P->acts[P->values[src].bufs[0]];
+            x.copy.out = P->acts[vo.bufs[m]];
+            x.copy.c_off = c_off; x.copy.pad_mode = P->act_pad_mode[vo.bufs[m]];
+            c_off += P->values[src].C;
+            P->xops.push_back(x);
+          }
+        }
+        break;
+      }
+      case G_CORR: {
+        const Value& va = P->values[op.value_in], &vb = P->values[op.value_in2], &vo = P->values[op.value_out];
+        float* sa = reinterpret_cast<float*>(base + corr_off[i]);
+        float* sb = sa + (size_t)va.N * va.C * va.H * va.W;
+        float* so = sb + (size_t)va.N * va.C * va.H * va.W;
+        XOp ea; ea.kind = X_EXPORT; ea.exp.io = P->io_dev; ea.exp.slot = 0; ea.exp.direct = sa; ea.exp.in = P->acts[va.bufs[0]];
+        XOp eb = ea; eb.exp.direct = sb; eb.exp.in = P->acts[vb.bufs[0]];
+        P->xops.push_back(ea); P->xops.push_back(eb);
+        XOp c; c.kind = X_CORR;
+        c.corr = CorrParams{sa, sb, so, va.N, va.C, va.H, va.W, op.corr[0], op.corr[1], op.corr[2], op.corr[3], op.corr[4]};
+        P->xops.push_back(c);
+        for (size_t m = 0; m < vo.bufs.size(); ++m) {
+          XOp x; x.kind = X_IMPORT; x.gop = (int)i;
+          x.imp.io = reinterpret_cast<const void* const*>(P->io_dev); x.imp.slot = 0; x.imp.direct = so;
+          x.imp.c_off = 0; x.imp.C_src = vo.C; x.imp.act = op.act; x.imp.slope = op.slope;
+          x.imp.out = P->acts[vo.bufs[m]]; x.imp.pad_mode = P->act_pad_mode[vo.bufs[m]];
+          P->xops.push_back(x);
+        }
+        break;
+      }
     }
   }
   V2V_CUDA(cudaStreamSynchronize(stream));
@@ -889,6 +1014,7 @@ int v2v_plan_repack(v2v_plan* P, v2v_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   for (auto& op : P->gops)
     if (op.kind == G_CONV || op.kind == G_CONV_ACT || op.kind == G_HEAD) { int rc = pack_one(op, stream); if (rc) return rc; }
+  for (const auto& ba : P->bias_affines) V2V_CUDA(launch_bias_affine(ba.scale, ba.shift, ba.bias, ba.N, ba.C, ba.stride, stream));
   return 0;
 }
 

@@ -165,6 +165,8 @@ struct ApplyParams {
 struct ImportParams {
   const void* const* io;   // device IO pointer table
   int slot;
+  const float* direct;     // non-null: read this plan-internal fp32 NCHW scratch tensor instead of io[slot]
+  int act; float slope;    // activation applied on the way in (LeakyReLU after the correlation, FlowNetC.py:83-84)
   int c_off, C_src;        // channel window [c_off, c_off + out.Cvalid) of a tensor with C_src channels
   ActDesc out;
   int pad_mode;
@@ -173,7 +175,21 @@ struct ImportParams {
 struct ExportParams {
   void* const* io;
   int slot;
+  float* direct;           // non-null: write this plan-internal fp32 NCHW scratch tensor instead of io[slot]
   ActDesc in;
+};
+
+// channel-window copy between activation buffers (torch.cat along channels): out[:, c_off : c_off + in.Cvalid] = in
+struct CopyParams {
+  ActDesc in, out;
+  int c_off;
+  int pad_mode;            // PadMode of out's halo
+};
+
+// correlation_cuda.forward on plan-internal fp32 NCHW scratch tensors (FlowNetC.py:30-31,79-81)
+struct CorrParams {
+  const float* in1; const float* in2; float* out;
+  int N, C, H, W, pad, k, max_disp, s1, s2;
 };
 
 struct PackParams {
@@ -209,6 +225,9 @@ cudaError_t launch_norm_apply(const ApplyParams& p, cudaStream_t stream);
 cudaError_t launch_import_nchw(const ImportParams& p, cudaStream_t stream);
 cudaError_t launch_export_nchw(const ExportParams& p, cudaStream_t stream);
 cudaError_t launch_pack_weights(const PackParams& p, cudaStream_t stream);
+cudaError_t launch_act_copy(const CopyParams& p, cudaStream_t stream);
+cudaError_t launch_bias_affine(float* scale, float* shift, const float* bias, int N, int C, int stride, cudaStream_t stream);
+cudaError_t launch_correlation(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, cudaStream_t);
 cudaError_t launch_composite(const CompositeParams& p, cudaStream_t stream);
 int device_sm_count();
 
