@@ -8,13 +8,19 @@ A step = one steady-state generated frame (all three scales).  One process per G
 independent clips (inference has no exchange step: "replicas only", weak scaling) and reports the
 whole-job frames/s = N * K / max-over-ranks time.  Prints ONE JSON line on rank 0.
 
+The headline (`value`, `e2e`, `roofline`, `dtype`) is the PRECISE arithmetic mode (split-bf16 x3, fp32-class: the mode
+whose outputs match the fp32 reference at images 5e-3 / flow 0.02 px, tests/test_gpu_precise.py); the bf16-operand mode is
+measured in the same run and reported beside it under `fast`.
+
   value        device-resident inputs, CUDA-event timed (what the kernels can do)
-  e2e          the public API with HOST tensors: pinned label maps -> H2D, ..., generated frame -> D2H
+  e2e          the public streaming API with HOST buffers: one pinned uint8 label frame -> H2D -> ... -> uint8 RGB frame
+               (util.tensor2im on the device) -> D2H into pinned memory, every step inside the timed region
   roofline     the tcgen05 conv kernel: algorithmic conv FLOPs of a frame / summed device time of its launches
-               (per-launch CUDA events, v2v_plan_profile) against MEASURED_PEAKS.json bf16 sustained
-  cpu_baseline oracle port (PyTorch CPU restatement of the reference, oracle/generator_oracle.py) timed on the
-               host cores on one steady-state frame of the same workload
-`--impl reference` times that CPU port as the reference arm.
+               (per-launch CUDA events, v2v_plan_profile) against MEASURED_PEAKS.json dense bf16 (burst)
+  cpu_baseline the reference's own Vid2VidModelG.inference (unmodified, vendored into the git-ignored oracle/_ref by
+               oracle/make_ref.py; CPU shims of oracle/ref_shim.py) timed on the host cores on a band of one steady-state
+               frame of the same workload (kind "reference"; the oracle port, kind "port", only if no reference travelled)
+`--impl reference` times the same CPU arm as the reference line.
 """
 import argparse
 import json
@@ -127,18 +133,26 @@ def reduce_times(times_ms, world, device='cpu'):
 
 
 def peaks():
+    """(dense bf16 burst TFLOP/s, sustained TFLOP/s, HBM GB/s, source)."""
     p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(p):
         d = json.load(open(p))
-        return d.get('bf16_tflops_sustained', 1381.2), d.get('hbm_gbs', 6570.9), 'measured (MEASURED_PEAKS.json, bf16 sustained)'
-    return 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
+        return d.get('bf16_tflops', 1665.0), d.get('bf16_tflops_sustained', 1381.2), d.get('hbm_gbs', 6570.9), 'measured (MEASURED_PEAKS.json)'
+    return 1665.0, 1400.0, 6650.0, 'fallback (B200_PROFILING.md)'
 
 
 # ----------------------------------------------------------------------------------------------- ours
+MODES = ('precise', 'fast')
+DTYPE = {'precise': 'bf16x3 (split-bf16 hi/lo operands, 3 tcgen05.mma per K block, fp32 accumulate: fp32-class)',
+         'fast': 'bf16 (bf16 operands, fp32 accumulate)'}
+
+
 def run_ours(args, rank, world, local_rank):
+    import gc
     import torch
     import torch.distributed as dist
     from vid2vid_b200 import _lib as L
+    from vid2vid_b200 import networks as NW
     from vid2vid_b200.model_g import Vid2VidModelG
     from vid2vid_b200.utils import synth_label_sequence
 
@@ -150,173 +164,241 @@ def run_ours(args, rank, world, local_rank):
     torch.manual_seed(1234 + rank)
     model = Vid2VidModelG().initialize(opt)
     tG = opt.n_frames_G
-    K, Wm = args.steps, args.warmup
-    n_frames = 2 * (K + Wm) + tG + 2
-    seq = synth_label_sequence(n_frames, wl['H'], wl['W'], label_nc=35, block=64, seed=rank)   # (1, T, 1, H, W)
-    seq_pinned = seq.pin_memory()
+    K, Wm = args.steps, max(args.warmup, 3)
+    H, Wd = wl['H'], wl['W']
+    n_frames = 2 * len(MODES) * (K + Wm + tG) + 8
+    seq = synth_label_sequence(n_frames, H, Wd, label_nc=35, block=64, seed=rank)   # (1, T, 1, H, W) float ids
     seq_dev = seq.to(dev)
+    seq_u8 = seq[0, :, 0].to(torch.uint8).pin_memory()                              # (T, H, W) uint8, pinned host
+    out_u8 = torch.empty((H, Wd, 3), dtype=torch.uint8).pin_memory()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up: first-frame generator + W frames (also instantiates the CUDA graphs)
+    modes = [m for m in MODES if args.modes in ('both', m)]
     sampler = ClockSampler(local_rank)
     sampler.start()
+    res = {}
     t = 0
-    for _ in range(max(Wm, 3)):
-        A = seq_dev[:, t:t + tG]
-        model.inference(A, None, A)
-        t += 1
-    # ---- timed: device-resident inputs
-    # (a generation-2 garbage collection over the module tree costs tens of ms -- several frames -- when it lands inside
-    # a 0.4 s timed region; collect now, keep the collector off until both timed regions are done)
-    import gc
     gc.collect()
-    gc.disable()
-    barrier()
-    sampler.recording = True
-    l0 = L.LAUNCHES[0]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        A = seq_dev[:, t:t + tG]
-        model.inference(A, None, A)
-        t += 1
-    e1.record()
-    barrier()
-    ms_dev = e0.elapsed_time(e1)
-    launches = L.LAUNCHES[0] - l0
-    # ---- timed: end to end through the public API with host tensors
-    out_host = torch.empty((1, 3, wl['H'], wl['W']), dtype=torch.float32).pin_memory()
-    for _ in range(2):
-        A = seq_pinned[:, t:t + tG].to(dev, non_blocking=True)
-        fb, _ = model.inference(A, None, A)
-        out_host.copy_(fb, non_blocking=True)
-        t += 1
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record()
-    for _ in range(K):
-        A_h = seq_pinned[:, t:t + tG]
-        A = A_h.to(dev, non_blocking=True)            # H2D: label ids of the tG-frame window
-        I = A_h.to(dev, non_blocking=True)            # H2D: instance ids (same synthetic map)
-        fb, _ = model.inference(A, None, I)
-        out_host.copy_(fb, non_blocking=True)         # D2H: the generated frame (test.py's tensor2im(.cpu()))
-        t += 1
-    e3.record()
-    barrier()
+    for mode in modes:
+        NW.set_default_precision(mode)
+        # ---- warm-up: first-frame generator (first call only) + W frames; instantiates this mode's CUDA graphs
+        for _ in range(Wm):
+            A = seq_dev[:, t:t + tG]
+            model.inference(A, None, A)
+            t += 1
+        # ---- timed: device-resident inputs.  (A generation-2 garbage collection over the module tree costs tens of ms
+        # when it lands inside a sub-second timed region: collect now, keep the collector off until the regions are done.)
+        gc.collect()
+        gc.disable()
+        barrier()
+        if mode == modes[0]:
+            sampler.recording = True
+        l0 = L.LAUNCHES[0]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            A = seq_dev[:, t:t + tG]
+            model.inference(A, None, A)
+            t += 1
+        e1.record()
+        barrier()
+        ms_dev = e0.elapsed_time(e1)
+        launches = L.LAUNCHES[0] - l0
+        # ---- timed: end to end through the public streaming API with HOST buffers: one pinned uint8 label frame (and the
+        # instance-id frame: the same synthetic map) -> H2D -> window push -> inference -> tensor2im on device -> D2H uint8
+        model._win_A = None
+        for _ in range(tG + 1):
+            model.inference_stream(seq_u8[t], None, out_u8=out_u8)
+            t += 1
+        barrier()
+        e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e2.record()
+        for _ in range(K):
+            model.inference_stream(seq_u8[t], None, out_u8=out_u8)
+            t += 1
+        e3.record()
+        barrier()
+        gc.enable()
+        ms_e2e = e2.elapsed_time(e3)
+        ms_dev, ms_e2e = reduce_times([ms_dev, ms_e2e], world, dev)
+        res[mode] = dict(ms_dev=ms_dev, ms_e2e=ms_e2e, launches=launches)
     sampler.stop_flag = True
-    gc.enable()
-    ms_e2e = e2.elapsed_time(e3)
-    h2d = 2 * tG * wl['H'] * wl['W'] * 4
-    d2h = 3 * wl['H'] * wl['W'] * 4
-
-    ms_dev, ms_e2e = reduce_times([ms_dev, ms_e2e], world, dev)
+    h2d = 2 * H * Wd             # label + instance id frame, uint8
+    d2h = 3 * H * Wd             # uint8 RGB frame
     if rank != 0:
         return
 
-    # ---- roofline of the conv kernel (per-launch CUDA events over one more frame)
-    conv_ms, conv_macs, other_ms, top, conv_launches = 0.0, 0.0, 0.0, {}, 0
-    kind_ms = {}
-    for s in range(wl['n_scales']):
-        net = getattr(model, 'netG%d' % s)
-        for ent in net._plans().values():
-            for kind, ms, macs in ent['plan'].profile():
-                kind_ms[kind] = kind_ms.get(kind, 0.0) + ms
-                if kind == 1:
-                    conv_ms += ms
-                    conv_macs += macs
-                    conv_launches += 1
-                else:
-                    other_ms += ms
-    peak_tf, peak_gbs, peak_src = peaks()
-    achieved_tf = 2.0 * conv_macs / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    # ---- first-frame generator (--use_single_G; runs tG - 1 times per clip, not per frame): timed separately
+    first_ms = None
+    if model.netG_i is not None:
+        x = torch.zeros(1, 35, H, Wd, device=dev)
+        x[:, 7] = 1.0
+        model.netG_i(x)
+        torch.cuda.synchronize()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for _ in range(3):
+            model.netG_i(x)
+        f1.record()
+        torch.cuda.synchronize()
+        first_ms = f0.elapsed_time(f1) / 3
+
+    # ---- roofline of the conv kernel per mode (per-launch CUDA events over one more frame, v2v_plan_profile)
+    peak_burst, peak_sust, peak_gbs, peak_src = peaks()
     fmacs = frame_macs(args.workload)
-    frame_ms = ms_dev / K
-    # DRAM bytes per conv launch: not measurable here (needs ncu); taken from the committed ncu capture of this command
-    traffic, traffic_src = None, None
+    traffic_db = {}
     try:
-        tj = json.load(open(os.path.join(ROOT, 'profiles', 'conv_dram_traffic.json')))[args.workload]
-        traffic, traffic_src = tj['dram_bytes_per_launch_avg'], tj['source']
+        traffic_db = json.load(open(os.path.join(ROOT, 'profiles', 'conv_dram_traffic.json')))
     except Exception:
         pass
+
+    def roofline(mode):
+        conv_ms, conv_macs, other_ms, conv_launches, kind_ms = 0.0, 0.0, 0.0, 0, {}
+        for s in range(wl['n_scales']):
+            net = getattr(model, 'netG%d' % s)
+            for key, ent in net._plans().items():
+                if key[-1] != mode:
+                    continue
+                for kind, ms, macs in ent['plan'].profile():
+                    kind_ms[kind] = kind_ms.get(kind, 0.0) + ms
+                    if kind == 1:
+                        conv_ms += ms
+                        conv_macs += macs
+                        conv_launches += 1
+                    else:
+                        other_ms += ms
+        achieved = 2.0 * conv_macs / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        tj = traffic_db.get('%s_%s' % (args.workload, mode)) or (traffic_db.get(args.workload) if mode == 'fast' else None) or {}
+        passes = 3 if mode == 'precise' else 1
+        return {'bound': 'tensor', 'kernel': 'conv_umma_kernel (all launches of one frame)', 'achieved': achieved, 'peak': peak_burst,
+                'unit': 'TFLOP/s', 'frac': achieved / peak_burst,
+                'peak_source': peak_src + ': dense bf16 burst (kernels are timed one launch at a time); sustained %.1f' % peak_sust,
+                'mma_passes_per_k_block': passes,
+                'issued_tensor_tflops': achieved * passes, 'frac_of_issued_mma_work': achieved * passes / peak_burst,
+                'traffic': tj.get('dram_bytes_per_launch_avg'),
+                'traffic_unit': 'bytes per launch (dram read + write, ncu, mean over the launches of a frame)',
+                'traffic_source': tj.get('source'), 'launches_per_frame': conv_launches,
+                'algorithmic_flops_per_launch_avg': 2.0 * conv_macs / max(conv_launches, 1),
+                'avg_launch_us': 1e3 * conv_ms / max(conv_launches, 1),
+                'conv_kernel_ms_per_frame': conv_ms, 'other_kernels_ms_per_frame': other_ms,
+                'ms_by_kernel_kind': {str(k): round(v, 4) for k, v in sorted(kind_ms.items())}}
+
+    def line(mode):
+        r = res[mode]
+        frame_ms = r['ms_dev'] / K
+        return {'value': world * K / (r['ms_dev'] * 1e-3), 'unit': 'frames/s', 'ms_per_step': frame_ms, 'dtype': DTYPE[mode],
+                'e2e': {'value': world * K / (r['ms_e2e'] * 1e-3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+                        'api': 'Vid2VidModelG.inference_stream(pinned uint8 label frame) -> uint8 RGB frame in pinned host memory'},
+                'gpu_launches': r['launches'], 'roofline': roofline(mode),
+                'frame_flops_over_frame_time_tflops': 2 * fmacs / (frame_ms * 1e-3) / 1e12}
+
+    head = line(modes[0])
     out = {
         'metric': 'frames/sec at 2048x1024 inference' if args.workload == 'cfg4' else 'frames/sec inference (%s)' % args.workload,
-        'value': world * K / (ms_dev * 1e-3), 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
-        'ms_per_step': frame_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'bf16', 'data': 'synthetic 35-label blocky sequences, random-init weights (N(0,0.02))',
+        'value': head['value'], 'unit': 'frames/s', 'n_gpus': world, 'steps': K, 'warmup': Wm,
+        'ms_per_step': head['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': head['dtype'], 'data': 'synthetic 35-label blocky sequences, random-init weights (N(0,0.02))',
         'config': {'workload': wl['desc'], 'parallelism': 'replicas x%d (independent clips, no collective)' % world,
-                   'frames_per_step': 1, 'conv_flops_per_frame': 2 * fmacs,
+                   'frames_per_step': 1, 'conv_flops_per_frame': 2 * fmacs, 'precision_mode': modes[0],
                    'l2_policy': 'per-frame working set (weights 0.8 GB + activations) is far larger than the 126 MB L2'},
-        'e2e': {'value': world * K / (ms_e2e * 1e-3), 'unit': 'frames/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
-        'gpu_launches': launches,
-        'clocks': sampler.summary(),
-        'roofline': {'bound': 'tensor', 'kernel': 'conv_umma_kernel (all launches of one frame)', 'achieved': achieved_tf,
-                     'peak': peak_tf, 'unit': 'TFLOP/s', 'frac': achieved_tf / peak_tf, 'peak_source': peak_src, 'traffic': traffic,
-                     'traffic_unit': 'bytes per launch (dram read + write, ncu, mean over the launches of a frame)',
-                     'traffic_source': traffic_src, 'launches_per_frame': conv_launches,
-                     'algorithmic_flops_per_launch_avg': 2.0 * conv_macs / max(conv_launches, 1),
-                     'avg_launch_us': 1e3 * conv_ms / max(conv_launches, 1),
-                     'conv_kernel_ms_per_frame': conv_ms, 'other_kernels_ms_per_frame': other_ms,
-                     'ms_by_kernel_kind': {str(k): round(v, 4) for k, v in sorted(kind_ms.items())},
-                     'frame_flops_over_frame_time_tflops': 2 * fmacs / (frame_ms * 1e-3) / 1e12},
+        'e2e': head['e2e'], 'gpu_launches': head['gpu_launches'], 'clocks': sampler.summary(), 'roofline': head['roofline'],
+        'first_frame_generator_ms': first_ms,
     }
+    if len(modes) > 1:
+        out['fast'] = line('fast')          # the bf16-operand mode, reported beside the fp32-class headline
     if world == 1 and not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_frames_per_s(args.workload, steps=1, warm=0, budget_s=25.0)
     print(json.dumps(out))
 
 
-# ----------------------------------------------------------------------------------------------- CPU port
-def cpu_frames_per_s(workload, steps, warm, budget_s=150.0):
-    """Oracle port on the host cores.  A step is one steady-state frame of the workload restricted to a horizontal band
-    of the image (full width, height H*f, f in {1/8, 1/4, 1/2, 1}): every layer does the same work per pixel, so
-    frames/s = f / seconds-per-band.  f is the largest fraction for which steps + warm bands fit in `budget_s`
-    (calibrated on one 1/8 band); previous-frame state is zero-filled (the cost does not depend on the content)."""
+# ----------------------------------------------------------------------------------------------- CPU arm
+def _cpu_model(workload, threads):
+    """(step(H, n, seed) -> seconds per frame, kind).  kind 'reference': the UNMODIFIED reference Vid2VidModelG.inference
+    (/root/reference here, its vendored copy oracle/_ref on the GPU box) under the CPU shims of oracle/ref_shim.py;
+    kind 'port': the oracle restatement, only when no reference tree travelled."""
     import torch
-    from oracle import generator_oracle as GO
-    from vid2vid_b200 import networks as NW
     from vid2vid_b200.utils import synth_label_sequence
     wl = WORKLOADS[workload]
-    # PyTorch's CPU convolutions stop scaling (and then regress) well before 128 threads on the GPU hosts
-    cores = min(os.cpu_count(), int(os.environ.get('V2V_CPU_THREADS', '32')))
-    torch.set_num_threads(cores)
+    torch.set_num_threads(threads)
     opt = make_opt_for(workload)
     opt.gpu_ids = []
     torch.manual_seed(0)
-    sds = [NW.build_netG(opt, s).state_dict() for s in range(wl['n_scales'])]
+    from oracle import ref_shim
+    if ref_shim.available():
+        m = ref_shim.make_model_G(opt, single_G=None)
+        kind = 'reference'
 
-    def run(frac, n, seed):
-        H = max(32, int(wl['H'] * frac) // 32 * 32)
-        orc = GO.ModelGOracle(opt, sds)
-        orc.fake_B_prev = [torch.zeros(2, 3, H // 2 ** s, wl['W'] // 2 ** s) for s in range(wl['n_scales'])]
-        seq = synth_label_sequence(n + 2, H, wl['W'], label_nc=35, block=32, seed=seed)
-        t0 = time.time()
-        with torch.no_grad():
+        def run(H, n, seed):
+            m.fake_B_prev = [torch.zeros(2, 3, H // 2 ** s, wl['W'] // 2 ** s) for s in range(wl['n_scales'])]
+            seq = synth_label_sequence(n + 2, H, wl['W'], label_nc=35, block=32, seed=seed)
+            t0 = time.time()
             for t in range(n):
-                orc.inference(seq[:, t:t + 3], seq[:, t:t + 3])
-        return (time.time() - t0) / n, H
+                m.inference(seq[:, t:t + 3], None, seq[:, t:t + 3])       # runs under torch.no_grad itself
+            return (time.time() - t0) / n
+    else:
+        from oracle import generator_oracle as GO
+        from vid2vid_b200 import networks as NW
+        sds = [NW.build_netG(opt, s).state_dict() for s in range(wl['n_scales'])]
+        kind = 'port'
 
-    run(1.0 / 16, 1, 0)                              # warm the thread pool / allocator
-    t8, _ = run(1.0 / 8, 1, 1)                       # calibration
+        def run(H, n, seed):
+            orc = GO.ModelGOracle(opt, sds)
+            orc.fake_B_prev = [torch.zeros(2, 3, H // 2 ** s, wl['W'] // 2 ** s) for s in range(wl['n_scales'])]
+            seq = synth_label_sequence(n + 2, H, wl['W'], label_nc=35, block=32, seed=seed)
+            t0 = time.time()
+            with torch.no_grad():
+                for t in range(n):
+                    orc.inference(seq[:, t:t + 3], seq[:, t:t + 3])
+            return (time.time() - t0) / n
+    return run, kind
+
+
+def cpu_frames_per_s(workload, steps, warm, budget_s=150.0):
+    """The reference on the host cores.  A step is one steady-state frame of the workload restricted to a horizontal band
+    of the image (full width, height H*f, f in {1/8, 1/4, 1/2, 1}): every layer does the same work per pixel, so
+    frames/s = f / seconds-per-band.  f is the largest fraction for which steps + warm bands fit in `budget_s`
+    (calibrated on one 1/8 band); previous-frame state is zero-filled (the cost does not depend on the content).
+    Threads: PyTorch's CPU convolutions regress beyond ~32 threads on the 128-core hosts, so a 1/16 band is timed with 32
+    threads and with all cores and the faster setting is used (both numbers are reported)."""
+    import torch
+    wl = WORKLOADS[workload]
+    band = lambda f: max(32, int(wl['H'] * f) // 32 * 32)
+    all_cores = os.cpu_count()
+    cand = sorted({min(all_cores, int(os.environ.get('V2V_CPU_THREADS', '32'))), all_cores})
+    calib = {}
+    run = kind = None
+    for th in cand:
+        run, kind = _cpu_model(workload, th)
+        run(band(1.0 / 16), 1, 0)                     # warm the thread pool / allocator
+        calib[th] = run(band(1.0 / 16), 1, 1)
+    cores = min(calib, key=calib.get)
+    run, kind = _cpu_model(workload, cores)
+    t8 = run(band(1.0 / 8), 1, 1)                     # calibration of the band size
     frac = 1.0 / 16
     for f in (1.0, 0.5, 0.25, 0.125):
         if t8 * 8 * f * (steps + warm) <= budget_s:
             frac = f
             break
     if warm:
-        run(frac, warm, 2)
-    dt, H = run(frac, steps, 3)
+        run(band(frac), warm, 2)
+    Hb = band(frac)
+    dt = run(Hb, steps, 3)
     model = ''
     try:
         model = [l.split(':')[1].strip() for l in open('/proc/cpuinfo') if l.startswith('model name')][0]
     except Exception:
         pass
-    eff = H / wl['H']
-    return {'value': eff / dt, 'unit': 'frames/s', 'cores': cores, 'kind': 'port',
-            'sample': '%d step(s), each one steady-state frame of a %dx%d band (%.3f of the %s frame), torch %s CPU fp32, %d threads, %s'
-                      % (steps, wl['W'], H, eff, wl['desc'], torch.__version__, cores, model),
+    eff = Hb / wl['H']
+    return {'value': eff / dt, 'unit': 'frames/s', 'cores': cores, 'kind': kind,
+            'sample': '%d step(s), each one steady-state frame of a %dx%d band (%.3f of the %s frame) through %s, torch %s CPU fp32, '
+                      '%d threads (1/16-band calibration, s/band: %s), %s'
+                      % (steps, wl['W'], Hb, eff, wl['desc'],
+                         "the reference's own Vid2VidModelG.inference" if kind == 'reference' else 'the oracle port',
+                         torch.__version__, cores, ', '.join('%d thr %.2f' % kv for kv in sorted(calib.items())), model),
             'seconds_per_step': dt}
 
 
@@ -345,6 +427,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg4', choices=list(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', dest='no_cpu_baseline', action='store_true')
+    ap.add_argument('--modes', default='both', choices=['both', 'precise', 'fast'])
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

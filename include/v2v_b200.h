@@ -91,6 +91,34 @@ int v2v_avgpool3s2(const float* in, float* out, int P, int H, int W, v2v_stream_
 int v2v_fg_mask(const float* real_A, float* mask, int B, int T, int C, int H, int W, int t, const int* fg_labels,
                 int n_labels, v2v_stream_t stream);
 
+/* Streaming clip input (test.py:31-41 feeds a tG-frame window of label ids per generated frame, of which only the newest
+ * frame is new): window (T,H,W) float ids, oldest first, is shifted by one frame in place and `frame` (H,W; dtype 0 uint8,
+ * 1 int32, 2 float) appended.  Keeps the window resident so a step uploads one uint8 frame instead of T float ones. */
+int v2v_ids_window_push(float* window, const void* frame, int dtype, int T, int H, int W, v2v_stream_t stream);
+/* util.tensor2im (util/util.py:48-71) on the device: image (C,H,W) float in [-1,1] -> out (H,W,C) uint8
+ * = uint8(clip((image + 1) / 2 * 255, 0, 255)). */
+int v2v_tensor2im_u8(const float* image, uint8_t* out, int C, int H, int W, v2v_stream_t stream);
+
+/* FlowNet2 glue (models/flownet2_pytorch/models.py:97-160, models/flownet.py:43-58), fp32 NCHW.
+ * flownet_prep: the image pair -> x (B,6,H,W) = (pair - mean over both frames and all pixels, per sample and colour) / rgb_max,
+ *   frame 0 in channels 0-2, frame 1 in 3-5 (models.py:97-103); x1 (may be NULL) = the frame-1 half as its own contiguous
+ *   (B,3,H,W) tensor; mean_ws: B*3 floats of scratch.  Plane (frame f, sample b, colour c) = frame{f} + b*batch_stride +
+ *   c*channel_stride floats: the reference's stacked (B,3,2,H,W) `inputs` is frame1 = frame0 + H*W, strides 6*H*W / 2*H*W;
+ *   two separate (B,3,H,W) images (models/flownet.py:51) are strides 3*H*W / H*W. */
+int v2v_flownet_prep(const float* frame0, const float* frame1, int64_t batch_stride, int64_t channel_stride, float* x, float* x1,
+                     float* mean_ws, int B, int H, int W, float rgb_max, v2v_stream_t stream);
+/* F.interpolate on `planes` planes (h,w) -> (H,W): mode 0 bilinear (align_corners=False), 1 nearest; values are multiplied by
+ * `mul` first (`* div_flow`, models.py:106,118,130) -- or divided by pre_div when pre_div != 1 (FlowNetSD, models.py:142-143);
+ * out_div (may be NULL) additionally receives out / div (`/ div_flow` of the next evidence stack).  use_scale_factor: 1 when the reference passes scale_factor= (nn.Upsample, models.py:49-60),
+ * 0 when it passes size= (models/flownet.py:49-50,55-57). */
+int v2v_resize(const float* in, float* out, float* out_div, int planes, int h, int w, int H, int W, int mode, int use_scale_factor,
+               float mul, float pre_div, float div, v2v_stream_t stream);
+/* out (N,C,H,W) = a[:, c_off:c_off+C] - b   (brightness error x[:, :3] - resampled_img1, models.py:113-116) */
+int v2v_sub_channels(const float* a, const float* b, float* out, int N, int Ca, int c_off, int C, int H, int W, v2v_stream_t stream);
+/* conf (N,1,H,W) = (sum_c (im1 - warped)^2 < threshold) as 0/1 floats (models/flownet.py:52-54, threshold 0.02) */
+int v2v_flow_conf(const float* im1, const float* warped, float* conf, int N, int C, int H, int W, float threshold,
+                  v2v_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * (2) Plan runtime.
  *
@@ -147,7 +175,8 @@ int v2v_plan_set_precision(v2v_plan* plan, int precision);
 int v2v_g_input(v2v_plan* plan, int slot, int N, int C_src, int c_off, int C, int H, int W, int* value_out);
 /* Convolution of a value; result is a raw (pre-norm) tensor. */
 int v2v_g_conv(v2v_plan* plan, int value_in, const v2v_conv_desc* conv, int* raw_out);
-/* value = act(norm(raw)) + add0 + add1   (add ids may be -1).  Conv bias is folded into running_mean only. */
+/* value = act(norm(raw)) + add0 + add1   (add ids may be -1).  Conv bias is folded into running_mean only.
+ * With V2V_NORM_NONE and a biased conv the pass computes act(raw + bias) (FlowNet2's norm-less units). */
 int v2v_g_norm_act(v2v_plan* plan, int raw_in, const v2v_norm_desc* norm, int act, float slope, int add0, int add1,
                    int* value_out);
 /* Same, on output channels [c_off, c_off + C) of the raw tensor (c_off % 8 == 0): lets convolutions that share their
@@ -159,6 +188,12 @@ int v2v_g_norm_act_slice(v2v_plan* plan, int raw_in, int c_off, int C, const v2v
 int v2v_g_conv_act(v2v_plan* plan, int value_in, const v2v_conv_desc* conv, int act, float slope, int* value_out);
 /* Small-Cout head (Cout <= 16): per channel bias + activation + scale -> fp32 NCHW planes of caller tensors. */
 int v2v_g_head(v2v_plan* plan, int value_in, const v2v_conv_desc* conv, const v2v_head_channel* channels);
+/* value = torch.cat(values, dim=1) (FlowNet2's skip / evidence stacks, FlowNetC.py:105-126, models.py:117,144). */
+int v2v_g_concat(v2v_plan* plan, const int* values, int n, int* value_out);
+/* value = act(correlation_cuda.forward(a, b)) with the FlowNetC parameters (FlowNetC.py:30-31,79-84); runs the stand-alone
+ * correlation kernel on plan-internal scratch.  kernel_size 1, stride1 1, pad_size == max_displacement only. */
+int v2v_g_correlation(v2v_plan* plan, int value_a, int value_b, int pad_size, int kernel_size, int max_displacement, int stride1,
+                      int stride2, int act, float slope, int* value_out);
 /* Export a value as fp32 NCHW into the caller tensor bound to `slot`. */
 int v2v_g_export(v2v_plan* plan, int value, int slot);
 /* Fused warp / blend / fg composite on caller tensors (slots; -1 = absent).  s_raw is read (head output)

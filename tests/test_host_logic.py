@@ -207,3 +207,16 @@ def test_conv_macs_discriminators():
             tot += p.conv_macs
             h, w = (h - 1) // 2 + 1, (w - 1) // 2 + 1
         assert abs(tot / 1e9 - want) < 0.01, (nc, tot)
+
+
+def test_flownet2_state_dict_keys_match_reference():
+    """vid2vid_b200.flownet.FlowNet2 exposes exactly the reference's 220 parameters (names and shapes), so
+    FlowNet2_checkpoint.pth.tar loads unchanged (models/flownet.py:19-21)."""
+    import json
+    from vid2vid_b200 import flownet as FN
+    keys = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'flownet2_keys.json')))
+    sd = FN.FlowNet2().state_dict()
+    ours = {k: list(v.shape) for k, v in sd.items()}
+    ref = {k: s for k, s in keys}
+    assert ours == ref, (sorted(set(ours) ^ set(ref))[:10], [k for k in ref if k in ours and ours[k] != ref[k]][:10])
+    assert [k for k, _ in keys] == list(sd.keys())

@@ -14,6 +14,12 @@ cudaError_t launch_channelnorm(const float*, float*, int, int, int, int, int, cu
 cudaError_t launch_resample(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 cudaError_t launch_onehot_edges(const float*, const float*, float*, int, int, int, int, int, cudaStream_t);
 cudaError_t launch_avgpool3s2(const float*, float*, int, int, int, cudaStream_t);
+cudaError_t launch_flownet_prep(const float*, const float*, long long, long long, float*, float*, float*, int, int, int, float, cudaStream_t);
+cudaError_t launch_resize(const float*, float*, float*, int, int, int, int, int, float, float, float, float, float, int, cudaStream_t);
+cudaError_t launch_sub_channels(const float*, const float*, float*, int, int, int, int, int, int, cudaStream_t);
+cudaError_t launch_flow_conf(const float*, const float*, float*, int, int, int, int, float, cudaStream_t);
+cudaError_t launch_ids_window_push(float*, const void*, int, int, int, int, cudaStream_t);
+cudaError_t launch_tensor2im_u8(const float*, uint8_t*, int, int, int, cudaStream_t);
 struct FgLabels { int v[16]; };
 cudaError_t launch_fg_mask(const float*, float*, int, int, int, int, int, int, FgLabels, int, cudaStream_t);
 }  // namespace v2v
@@ -108,6 +114,51 @@ int v2v_fg_mask(const float* real_A, float* mask, int B, int T, int C, int H, in
     l.v[i] = fg_labels[i];
   }
   API_CUDA(launch_fg_mask(real_A, mask, B, T, C, H, W, t, l, n_labels, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int v2v_ids_window_push(float* window, const void* frame, int dtype, int T, int H, int W, v2v_stream_t stream) {
+  API_REQUIRE(window && frame && dtype >= 0 && dtype <= 2 && T >= 1 && H > 0 && W > 0, "ids_window_push: bad arguments");
+  API_CUDA(launch_ids_window_push(window, frame, dtype, T, H, W, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int v2v_tensor2im_u8(const float* image, uint8_t* out, int C, int H, int W, v2v_stream_t stream) {
+  API_REQUIRE(image && out && C > 0 && H > 0 && W > 0, "tensor2im_u8: bad arguments");
+  API_CUDA(launch_tensor2im_u8(image, out, C, H, W, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int v2v_flownet_prep(const float* frame0, const float* frame1, int64_t batch_stride, int64_t channel_stride, float* x, float* x1,
+                     float* mean_ws, int B, int H, int W, float rgb_max, v2v_stream_t stream) {
+  API_REQUIRE(frame0 && frame1 && x && mean_ws && B > 0 && H > 0 && W > 0 && rgb_max != 0.f, "flownet_prep: bad arguments");
+  API_CUDA(launch_flownet_prep(frame0, frame1, batch_stride, channel_stride, x, x1, mean_ws, B, H, W, rgb_max,
+                               reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int v2v_resize(const float* in, float* out, float* out_div, int planes, int h, int w, int H, int W, int mode, int use_scale_factor,
+               float mul, float pre_div, float div, v2v_stream_t stream) {
+  API_REQUIRE(in && out && planes > 0 && h > 0 && w > 0 && H > 0 && W > 0 && (mode == 0 || mode == 1), "resize: bad arguments");
+  API_REQUIRE((!out_div || div != 0.f) && pre_div != 0.f, "resize: division by zero");
+  // ATen area_pixel_compute_scale / compute_scales_value: 1 / scale_factor when a scale factor was given, else in / out
+  float sh, sw;
+  if (use_scale_factor) { sh = 1.0f / ((float)H / (float)h); sw = 1.0f / ((float)W / (float)w); }
+  else { sh = (float)h / (float)H; sw = (float)w / (float)W; }
+  API_CUDA(launch_resize(in, out, out_div, planes, h, w, H, W, sh, sw, mul, pre_div, div, mode, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int v2v_sub_channels(const float* a, const float* b, float* out, int N, int Ca, int c_off, int C, int H, int W, v2v_stream_t stream) {
+  API_REQUIRE(a && b && out && N > 0 && C > 0 && c_off >= 0 && c_off + C <= Ca && H > 0 && W > 0, "sub_channels: bad arguments");
+  API_CUDA(launch_sub_channels(a, b, out, N, Ca, c_off, C, H, W, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int v2v_flow_conf(const float* im1, const float* warped, float* conf, int N, int C, int H, int W, float threshold,
+                  v2v_stream_t stream) {
+  API_REQUIRE(im1 && warped && conf && N > 0 && C > 0 && H > 0 && W > 0, "flow_conf: bad arguments");
+  API_CUDA(launch_flow_conf(im1, warped, conf, N, C, H, W, threshold, reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
 

@@ -12,11 +12,16 @@
 
 namespace v2v {
 
-// one block per (b, c): fp64 sum over the 2*H*W values of colour c in both frames
-__global__ void __launch_bounds__(256) flownet_mean_kernel(const float* __restrict__ in, float* __restrict__ mean, size_t n_per) {
-  const float* p = in + (size_t)blockIdx.x * n_per;
+// one block per (b, c): fp64 sum over the 2*H*W values of colour c in both frames.  Frame f of sample b, colour c is the
+// plane f{0,1} + b * bstride + c * cstride (stacked (B,3,2,H,W) input: f1 = f0 + HW, bstride 6 HW, cstride 2 HW; two separate
+// (B,3,H,W) images: bstride 3 HW, cstride HW).
+__global__ void __launch_bounds__(256) flownet_mean_kernel(const float* __restrict__ f0, const float* __restrict__ f1, size_t bstride,
+                                                           size_t cstride, float* __restrict__ mean, size_t HW) {
+  const int b = blockIdx.x / 3, c = blockIdx.x - 3 * b;
+  const float* p0 = f0 + b * bstride + c * cstride;
+  const float* p1 = f1 + b * bstride + c * cstride;
   double s = 0.0;
-  for (size_t i = threadIdx.x; i < n_per; i += blockDim.x) s += (double)p[i];
+  for (size_t i = threadIdx.x; i < HW; i += blockDim.x) s += (double)p0[i] + (double)p1[i];
   __shared__ double sh[256];
   sh[threadIdx.x] = s;
   __syncthreads();
@@ -24,25 +29,29 @@ __global__ void __launch_bounds__(256) flownet_mean_kernel(const float* __restri
     if ((int)threadIdx.x < k) sh[threadIdx.x] += sh[threadIdx.x + k];
     __syncthreads();
   }
-  if (threadIdx.x == 0) mean[blockIdx.x] = (float)(sh[0] / (double)n_per);
+  if (threadIdx.x == 0) mean[blockIdx.x] = (float)(sh[0] / (double)(2 * HW));
 }
 
-// in (B,3,2,H,W) -> x (B,6,H,W): channel f*3 + c = (in[b,c,f] - mean[b,c]) / rgb_max
-__global__ void flownet_center_kernel(const float* __restrict__ in, const float* __restrict__ mean, float* __restrict__ x,
-                                      int B, size_t HW, float rgb_max) {
+// -> x (B,6,H,W): channel f*3 + c = (frame f colour c - mean[b,c]) / rgb_max; x1 (B,3,H,W) = the frame-1 half, contiguous
+__global__ void flownet_center_kernel(const float* __restrict__ f0, const float* __restrict__ f1, size_t bstride, size_t cstride,
+                                      const float* __restrict__ mean, float* __restrict__ x, float* __restrict__ x1, int B, size_t HW,
+                                      float rgb_max) {
   const size_t total = (size_t)B * 6 * HW;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const size_t pix = idx % HW;
     const int ch = (int)((idx / HW) % 6), b = (int)(idx / (6 * HW));
     const int f = ch / 3, c = ch - 3 * f;
-    const float v = in[(((size_t)b * 3 + c) * 2 + f) * HW + pix];
-    x[idx] = __fdiv_rn(__fsub_rn(v, mean[b * 3 + c]), rgb_max);
+    const float v = (f ? f1 : f0)[b * bstride + c * cstride + pix];
+    const float r = __fdiv_rn(__fsub_rn(v, mean[b * 3 + c]), rgb_max);
+    x[idx] = r;
+    if (f && x1) x1[((size_t)b * 3 + c) * HW + pix] = r;
   }
 }
 
 // ATen upsample_bilinear2d / upsample_nearest2d index rules (align_corners = False); scale = in / out (or 1 / scale_factor)
+// value read = in * mul, or in / pre_div when pre_div != 1 (FlowNetSD's flow is DIVIDED by div_flow, models.py:142-143)
 __global__ void resize_kernel(const float* __restrict__ in, float* __restrict__ out, float* __restrict__ out_div, int planes,
-                              int h, int w, int H, int W, float sh, float sw, float mul, float div, int nearest) {
+                              int h, int w, int H, int W, float sh, float sw, float mul, float pre_div, float div, int nearest) {
   const size_t total = (size_t)planes * H * W;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int X = (int)(idx % W), Y = (int)((idx / W) % H);
@@ -51,7 +60,7 @@ __global__ void resize_kernel(const float* __restrict__ in, float* __restrict__ 
     float v;
     if (nearest) {
       const int ys = min((int)floorf(__fmul_rn((float)Y, sh)), h - 1), xs = min((int)floorf(__fmul_rn((float)X, sw)), w - 1);
-      v = __fmul_rn(p[(size_t)ys * w + xs], mul);
+      v = pre_div != 1.f ? __fdiv_rn(p[(size_t)ys * w + xs], pre_div) : __fmul_rn(p[(size_t)ys * w + xs], mul);
     } else {
       float fy = __fsub_rn(__fmul_rn(sh, (float)Y + 0.5f), 0.5f), fx = __fsub_rn(__fmul_rn(sw, (float)X + 0.5f), 0.5f);
       if (fy < 0.f) fy = 0.f;
@@ -60,8 +69,9 @@ __global__ void resize_kernel(const float* __restrict__ in, float* __restrict__ 
       const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
       const float ly = __fsub_rn(fy, (float)y0), lx = __fsub_rn(fx, (float)x0);
       const float hy = __fsub_rn(1.f, ly), hx = __fsub_rn(1.f, lx);
-      const float v00 = __fmul_rn(p[(size_t)y0 * w + x0], mul), v01 = __fmul_rn(p[(size_t)y0 * w + x1], mul);
-      const float v10 = __fmul_rn(p[(size_t)y1 * w + x0], mul), v11 = __fmul_rn(p[(size_t)y1 * w + x1], mul);
+      float v00 = p[(size_t)y0 * w + x0], v01 = p[(size_t)y0 * w + x1], v10 = p[(size_t)y1 * w + x0], v11 = p[(size_t)y1 * w + x1];
+      if (pre_div != 1.f) { v00 = __fdiv_rn(v00, pre_div); v01 = __fdiv_rn(v01, pre_div); v10 = __fdiv_rn(v10, pre_div); v11 = __fdiv_rn(v11, pre_div); }
+      else { v00 = __fmul_rn(v00, mul); v01 = __fmul_rn(v01, mul); v10 = __fmul_rn(v10, mul); v11 = __fmul_rn(v11, mul); }
       // h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11), unfused
       const float top = __fadd_rn(__fmul_rn(hx, v00), __fmul_rn(lx, v01));
       const float bot = __fadd_rn(__fmul_rn(hx, v10), __fmul_rn(lx, v11));
@@ -103,16 +113,17 @@ static inline int grid1d(size_t total) {
   return (int)(b < cap ? (b ? b : 1) : cap);
 }
 
-cudaError_t launch_flownet_prep(const float* in, float* x, float* mean_ws, int B, int H, int W, float rgb_max, cudaStream_t s) {
+cudaError_t launch_flownet_prep(const float* f0, const float* f1, long long bstride, long long cstride, float* x, float* x1,
+                                float* mean_ws, int B, int H, int W, float rgb_max, cudaStream_t s) {
   const size_t HW = (size_t)H * W;
-  flownet_mean_kernel<<<B * 3, 256, 0, s>>>(in, mean_ws, 2 * HW);
-  flownet_center_kernel<<<grid1d((size_t)B * 6 * HW), 256, 0, s>>>(in, mean_ws, x, B, HW, rgb_max);
+  flownet_mean_kernel<<<B * 3, 256, 0, s>>>(f0, f1, (size_t)bstride, (size_t)cstride, mean_ws, HW);
+  flownet_center_kernel<<<grid1d((size_t)B * 6 * HW), 256, 0, s>>>(f0, f1, (size_t)bstride, (size_t)cstride, mean_ws, x, x1, B, HW, rgb_max);
   return cudaGetLastError();
 }
 
 cudaError_t launch_resize(const float* in, float* out, float* out_div, int planes, int h, int w, int H, int W, float sh, float sw,
-                          float mul, float div, int nearest, cudaStream_t s) {
-  resize_kernel<<<grid1d((size_t)planes * H * W), 256, 0, s>>>(in, out, out_div, planes, h, w, H, W, sh, sw, mul, div, nearest);
+                          float mul, float pre_div, float div, int nearest, cudaStream_t s) {
+  resize_kernel<<<grid1d((size_t)planes * H * W), 256, 0, s>>>(in, out, out_div, planes, h, w, H, W, sh, sw, mul, pre_div, div, nearest);
   return cudaGetLastError();
 }
 

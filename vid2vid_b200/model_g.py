@@ -98,6 +98,51 @@ class Vid2VidModelG(nn.Module):
                 fake_B = self.generate_frame_infer(real_A[self.n_scales - 1 - s], s)
         return fake_B, real_A[0][0, -1]
 
+    # ------------------------------------------------------------------ streaming inference (one new frame per call)
+    _DT = {torch.uint8: 0, torch.int32: 1, torch.float32: 2}
+
+    def inference_stream(self, label_frame, inst_frame=None, out_u8=None):
+        """Same computation as inference() for a clip fed frame by frame: `label_frame` / `inst_frame` are the NEWEST
+        (H, W) id maps (uint8, int32 or float32; host -- ideally pinned -- or device).  The tG-frame id window that
+        test.py:31-41 re-sends every step stays resident on the device, so a step uploads one frame.  The first tG - 1
+        calls only fill the window and return None.  Returns the generated frame (1, 3, H, W) float, or, when `out_u8`
+        (a (H, W, 3) uint8 tensor, host or device) is given, util.tensor2im's uint8 image written into it
+        (computed on the device; util/util.py:48-71 does it on the CPU after copying the float frame back)."""
+        import ctypes as C
+        from . import _lib as L
+        tG = self.opt.n_frames_G
+        H, W = label_frame.shape[-2:]
+        dev = self.device_
+        if getattr(self, '_win_A', None) is None or self._win_A.shape[-2:] != (H, W):
+            self._win_A = torch.zeros(1, tG, 1, H, W, device=dev)
+            self._win_I = torch.zeros(1, tG, 1, H, W, device=dev) if self.opt.use_instance else None
+            self._win_n = 0
+        for win, fr in ((self._win_A, label_frame), (self._win_I, inst_frame if inst_frame is not None else label_frame)):
+            if win is None:
+                continue
+            fr = fr.to(dev, non_blocking=True).contiguous()
+            if fr.dtype not in self._DT:
+                raise TypeError('id maps must be uint8, int32 or float32')
+            L.check(L.lib().v2v_ids_window_push(C.c_void_p(win.data_ptr()), C.c_void_p(fr.data_ptr()), self._DT[fr.dtype], tG, H, W,
+                                                L.current_stream_ptr()))
+            L.LAUNCHES[0] += 1
+        self._win_n += 1
+        if self._win_n < tG:
+            return None
+        fake_B, _ = self.inference(self._win_A, None, self._win_I)
+        if out_u8 is None:
+            return fake_B
+        if getattr(self, '_u8_dev', None) is None or self._u8_dev.shape[:2] != (H, W):
+            self._u8_dev = torch.empty(H, W, fake_B.shape[1], dtype=torch.uint8, device=dev)
+        L.check(L.lib().v2v_tensor2im_u8(C.c_void_p(fake_B.data_ptr()), C.c_void_p(self._u8_dev.data_ptr()), fake_B.shape[1], H, W,
+                                         L.current_stream_ptr()))
+        L.LAUNCHES[0] += 1
+        if out_u8.is_cuda:
+            out_u8.copy_(self._u8_dev)
+        else:
+            out_u8.copy_(self._u8_dev, non_blocking=True)
+        return out_u8
+
     def generate_frame_infer(self, real_A, s):
         """vid2vid_model_G.py:211-229."""
         tG = self.opt.n_frames_G

@@ -93,6 +93,8 @@ class Plan:
 
     def norm_act(self, raw, ndesc, act=L.ACT_NONE, slope=0.0, adds=(), c_off=0, Cn=None):
         v = C.c_int()
+        if len(adds) > 2:
+            raise NotImplementedError('at most two addends per normalise pass')
         adds = list(adds) + [-1, -1]
         self._keep.append(ndesc)
         if Cn is None:
@@ -116,6 +118,19 @@ class Plan:
             self.n_slots = max(self.n_slots, slot + 1)
         self._keep += [desc, arr]
         L.check(L.lib().v2v_g_head(self._h, vin, C.byref(desc), arr))
+
+    def concat(self, values):
+        arr = (C.c_int * len(values))(*values)
+        v = C.c_int()
+        L.check(L.lib().v2v_g_concat(self._h, arr, len(values), C.byref(v)))
+        return v.value
+
+    def correlation(self, va, vb, pad_size=20, kernel_size=1, max_displacement=20, stride1=1, stride2=2, act=L.ACT_NONE,
+                    slope=0.0):
+        v = C.c_int()
+        L.check(L.lib().v2v_g_correlation(self._h, va, vb, pad_size, kernel_size, max_displacement, stride1, stride2, act, slope,
+                                          C.byref(v)))
+        return v.value
 
     def export(self, v, slot):
         L.check(L.lib().v2v_g_export(self._h, v, slot))
