@@ -99,6 +99,23 @@ int v2v_ids_window_push(float* window, const void* frame, int dtype, int T, int 
  * = uint8(clip((image + 1) / 2 * 255, 0, 255)). */
 int v2v_tensor2im_u8(const float* image, uint8_t* out, int C, int H, int W, v2v_stream_t stream);
 
+/* Losses of the training step (models/vid2vid_model_D.py:117-140,199-213; criteria models/networks.py:731-812) and the
+ * backward of the helpers they differentiate through.  `out` / `grad_out` are 1-element device tensors (no host sync);
+ * sum_ws: one double of scratch.
+ *   l1_loss: out = mean |a*m - b*m| over N*C*H*W; mask (N,1,H,W) broadcast over channels or NULL (plain L1); b may be NULL (= 0).
+ *   mse_const: out = mean (x - target)^2   (GANLoss, LSGAN). */
+int v2v_l1_loss_forward(const float* a, const float* b, const float* mask, int N, int C, int H, int W, double* sum_ws, float* out,
+                        v2v_stream_t stream);
+int v2v_l1_loss_backward(const float* a, const float* b, const float* mask, int N, int C, int H, int W, const float* grad_out,
+                         float* grad_a, float* grad_b, v2v_stream_t stream);
+int v2v_mse_const_forward(const float* x, int64_t numel, float target, double* sum_ws, float* out, v2v_stream_t stream);
+int v2v_mse_const_backward(const float* x, int64_t numel, float target, const float* grad_out, float* grad_x, v2v_stream_t stream);
+/* Backward of v2v_avgpool3s2 (grad_in written) and of v2v_resample_forward (grad_image accumulated with atomics into a
+ * caller-zeroed tensor, grad_flow written; either may be NULL). */
+int v2v_avgpool3s2_backward(const float* grad_out, float* grad_in, int P, int H, int W, v2v_stream_t stream);
+int v2v_resample_backward(const float* image, const float* flow, const float* grad_out, float* grad_image, float* grad_flow, int N,
+                          int C, int H, int W, int align_corners, v2v_stream_t stream);
+
 /* FlowNet2 glue (models/flownet2_pytorch/models.py:97-160, models/flownet.py:43-58), fp32 NCHW.
  * flownet_prep: the image pair -> x (B,6,H,W) = (pair - mean over both frames and all pixels, per sample and colour) / rgb_max,
  *   frame 0 in channels 0-2, frame 1 in 3-5 (models.py:97-103); x1 (may be NULL) = the frame-1 half as its own contiguous
@@ -201,10 +218,26 @@ int v2v_g_export(v2v_plan* plan, int value, int slot);
 int v2v_g_composite(v2v_plan* plan, int s_raw, int s_flow, int s_weight, int s_prev, int prev_C, int s_fg, int s_mask,
                     int s_final, int N, int H, int W, int use_warp, int align_corners);
 
+/* As v2v_g_composite, with the composited raw image written to IO slot s_raw_out (>= 0) instead of over s_raw: training
+ * plans need the head output intact for the backward. */
+int v2v_g_composite_ex(v2v_plan* plan, int s_raw, int s_flow, int s_weight, int s_prev, int prev_C, int s_fg, int s_mask,
+                       int s_final, int s_raw_out, int N, int H, int W, int use_warp, int align_corners);
+
+/* Training plans (before finalize): keep the batch statistics and allocate dense fp32 gradient buffers. */
+int v2v_plan_set_training(v2v_plan* plan, int on);
+/* Backward of the LAST v2v_plan_run of this plan (whose intermediate buffers the plan still holds): autograd of
+ * netG.forward / netD.forward as train.py:50-93 drives it.  io_ptrs: the forward tensors, as passed to v2v_plan_run.
+ * grad_io_ptrs[slot]: for output slots the incoming gradient (fp32 NCHW, NULL = none); for input slots the destination of
+ * the input gradient (accumulated into; NULL = not wanted).  params / param_grads: n_params pairs (parameter device pointer as
+ * given in the conv / norm descriptors, gradient tensor of the same layout, accumulated into). */
+int v2v_plan_backward(v2v_plan* plan, void* const* io_ptrs, void* const* grad_io_ptrs, int n_io, const void* const* params,
+                      void* const* param_grads, int n_params, v2v_stream_t stream);
+
 int v2v_plan_finalize(v2v_plan* plan, v2v_stream_t stream);
 /* Re-read all weight pointers and repack (after an optimiser step / load_state_dict). */
 int v2v_plan_repack(v2v_plan* plan, v2v_stream_t stream);
-/* Run once.  io_ptrs[slot] = device pointer of the caller tensor bound to that slot. */
+/* Run once.  io_ptrs[slot] = device pointer of the caller tensor bound to that slot.  use_graph: 0 eager, 1 replay the
+ * captured CUDA graph, 2 eager without the running-statistics side effect (recomputation before a backward). */
 int v2v_plan_run(v2v_plan* plan, void* const* io_ptrs, int n_io, int use_graph, v2v_stream_t stream);
 
 /* Runs the plan once eagerly with a CUDA event after every kernel: kinds[i] (0 import, 1 conv, 2 raw-stats,

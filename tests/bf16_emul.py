@@ -11,6 +11,11 @@ from vid2vid_b200 import _lib as L
 
 
 ROUND = [True]      # False: no rounding anywhere and fp64 arithmetic -- the exact reference the precise mode is compared with
+GRAD = [False]      # True: keep the autograd graph to the module parameters (reference gradients for the backward kernels)
+
+
+def _param(t):
+    return t if GRAD[0] else t.detach()
 
 
 def r16(t):
@@ -32,8 +37,8 @@ def _act(x, act, slope):
 
 
 def _conv(x, conv, pmode, pad, with_bias):
-    w = r16(conv.weight.detach().float())
-    b = conv.bias.detach().to(w.dtype) if (with_bias and conv.bias is not None) else None
+    w = r16(_param(conv.weight).float())
+    b = _param(conv.bias).to(w.dtype) if (with_bias and conv.bias is not None) else None
     if isinstance(conv, nn.ConvTranspose2d):
         return F.conv_transpose2d(x, w, b, stride=conv.stride, padding=conv.padding, output_padding=conv.output_padding)
     if pmode == L.PAD_REFLECT and pad:
@@ -46,7 +51,7 @@ def _norm(raw, norm):
     if isinstance(norm, nn.BatchNorm2d):
         mean = raw.mean(dim=(0, 2, 3), keepdim=True)
         var = raw.var(dim=(0, 2, 3), unbiased=False, keepdim=True)
-        g, b = norm.weight.detach().view(1, -1, 1, 1).to(raw.dtype), norm.bias.detach().view(1, -1, 1, 1).to(raw.dtype)
+        g, b = _param(norm.weight).view(1, -1, 1, 1).to(raw.dtype), _param(norm.bias).view(1, -1, 1, 1).to(raw.dtype)
     else:
         mean = raw.mean(dim=(2, 3), keepdim=True)
         var = raw.var(dim=(2, 3), unbiased=False, keepdim=True)

@@ -20,6 +20,12 @@ cudaError_t launch_sub_channels(const float*, const float*, float*, int, int, in
 cudaError_t launch_flow_conf(const float*, const float*, float*, int, int, int, int, float, cudaStream_t);
 cudaError_t launch_ids_window_push(float*, const void*, int, int, int, int, cudaStream_t);
 cudaError_t launch_tensor2im_u8(const float*, uint8_t*, int, int, int, cudaStream_t);
+cudaError_t launch_l1_fwd(const float*, const float*, const float*, int, int, int, int, double*, float*, cudaStream_t);
+cudaError_t launch_l1_bwd(const float*, const float*, const float*, int, int, int, int, const float*, float*, float*, cudaStream_t);
+cudaError_t launch_mse_const_fwd(const float*, long long, float, double*, float*, cudaStream_t);
+cudaError_t launch_mse_const_bwd(const float*, long long, float, const float*, float*, cudaStream_t);
+cudaError_t launch_avgpool3s2_bwd(const float*, float*, int, int, int, cudaStream_t);
+cudaError_t launch_resample_bwd(const float*, const float*, const float*, float*, float*, int, int, int, int, int, cudaStream_t);
 struct FgLabels { int v[16]; };
 cudaError_t launch_fg_mask(const float*, float*, int, int, int, int, int, int, FgLabels, int, cudaStream_t);
 }  // namespace v2v
@@ -159,6 +165,41 @@ int v2v_flow_conf(const float* im1, const float* warped, float* conf, int N, int
                   v2v_stream_t stream) {
   API_REQUIRE(im1 && warped && conf && N > 0 && C > 0 && H > 0 && W > 0, "flow_conf: bad arguments");
   API_CUDA(launch_flow_conf(im1, warped, conf, N, C, H, W, threshold, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
+int v2v_l1_loss_forward(const float* a, const float* b, const float* mask, int N, int C, int H, int W, double* sum_ws, float* out,
+                        v2v_stream_t stream) {
+  API_REQUIRE(a && sum_ws && out && N > 0 && C > 0 && H > 0 && W > 0, "l1_loss: bad arguments");
+  API_CUDA(launch_l1_fwd(a, b, mask, N, C, H, W, sum_ws, out, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int v2v_l1_loss_backward(const float* a, const float* b, const float* mask, int N, int C, int H, int W, const float* grad_out,
+                         float* grad_a, float* grad_b, v2v_stream_t stream) {
+  API_REQUIRE(a && grad_out && (grad_a || grad_b), "l1_loss backward: bad arguments");
+  API_CUDA(launch_l1_bwd(a, b, mask, N, C, H, W, grad_out, grad_a, grad_b, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int v2v_mse_const_forward(const float* x, int64_t numel, float target, double* sum_ws, float* out, v2v_stream_t stream) {
+  API_REQUIRE(x && sum_ws && out && numel > 0, "mse_const: bad arguments");
+  API_CUDA(launch_mse_const_fwd(x, numel, target, sum_ws, out, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int v2v_mse_const_backward(const float* x, int64_t numel, float target, const float* grad_out, float* grad_x, v2v_stream_t stream) {
+  API_REQUIRE(x && grad_out && grad_x && numel > 0, "mse_const backward: bad arguments");
+  API_CUDA(launch_mse_const_bwd(x, numel, target, grad_out, grad_x, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int v2v_avgpool3s2_backward(const float* grad_out, float* grad_in, int P, int H, int W, v2v_stream_t stream) {
+  API_REQUIRE(grad_out && grad_in && P > 0 && H > 0 && W > 0, "avgpool3s2 backward: bad arguments");
+  API_CUDA(launch_avgpool3s2_bwd(grad_out, grad_in, P, H, W, reinterpret_cast<cudaStream_t>(stream)));
+  return 0;
+}
+int v2v_resample_backward(const float* image, const float* flow, const float* grad_out, float* grad_image, float* grad_flow, int N,
+                          int C, int H, int W, int align_corners, v2v_stream_t stream) {
+  API_REQUIRE(image && flow && grad_out && (grad_image || grad_flow), "resample backward: bad arguments");
+  API_CUDA(launch_resample_bwd(image, flow, grad_out, grad_image, grad_flow, N, C, H, W, align_corners,
+                               reinterpret_cast<cudaStream_t>(stream)));
   return 0;
 }
 

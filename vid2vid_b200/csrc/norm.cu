@@ -45,6 +45,10 @@ __global__ void __launch_bounds__(128) stats_finalize_kernel(FinalizeParams p) {
         const float sc = g * (float)(1.0 / sqrt(var + (double)p.eps));
         p.scale[(size_t)n * p.scale_stride + p.c_off + c] = sc;
         p.shift[(size_t)n * p.scale_stride + p.c_off + c] = b - (float)mean * sc;
+        if (p.mean_out) {
+          p.mean_out[(size_t)n * p.scale_stride + p.c_off + c] = (float)mean;
+          p.rstd_out[(size_t)n * p.scale_stride + p.c_off + c] = (float)(1.0 / sqrt(var + (double)p.eps));
+        }
       }
       rm_acc += mean;
       rv_acc += var * (p.count / (p.count > 1 ? p.count - 1 : 1));
@@ -66,6 +70,10 @@ __global__ void __launch_bounds__(128) stats_finalize_kernel(FinalizeParams p) {
     for (int n = 0; n < p.N; ++n) {
       p.scale[(size_t)n * p.scale_stride + p.c_off + c] = sc;
       p.shift[(size_t)n * p.scale_stride + p.c_off + c] = b - (float)mean * sc;
+      if (p.mean_out) {
+        p.mean_out[(size_t)n * p.scale_stride + p.c_off + c] = (float)mean;
+        p.rstd_out[(size_t)n * p.scale_stride + p.c_off + c] = (float)(1.0 / sqrt(var + (double)p.eps));
+      }
     }
     mean_run = mean; var_run = var * (cnt / (cnt > 1 ? cnt - 1 : 1));
   }

@@ -13,6 +13,8 @@
 
 #include "../../include/v2v_b200.h"
 #include "v2v_internal.h"
+#include "backward.h"
+#include <unordered_map>
 
 namespace v2v {
 
@@ -214,6 +216,8 @@ struct Value {
   std::vector<Req> reqs;
   std::vector<int> bufs;     // index into Plan::acts, one per req
   bool interior_use = false;
+  float* gval = nullptr;     // training plans: gradient of the value, dense NHWC fp32 [N][H][W][C]
+  int input_slot = -1;       // >= 0: the value is an import of that IO slot (data gradient only on request)
 };
 struct Raw {
   int N, H, W, C;
@@ -223,6 +227,8 @@ struct Raw {
   float* scale = nullptr; float* shift = nullptr;
   int tiles_per_img = 0, num_phases = 1;
   std::vector<int> running_done;   // channel offsets whose running stats already have an updating launch
+  float* mean = nullptr; float* rstd = nullptr;   // training plans: saved statistics [N][C]
+  float* graw = nullptr;           // training plans: gradient of the raw tensor, dense NHWC fp32 (channel stride desc.C)
 };
 
 enum GKind { G_INPUT, G_CONV, G_NORM_ACT, G_CONV_ACT, G_HEAD, G_EXPORT, G_COMPOSITE, G_CONCAT, G_CORR };
@@ -245,6 +251,7 @@ struct GOp {
   int corr[5] = {0, 0, 0, 0, 0};   // pad, kernel, max_disp, stride1, stride2
   // lowered
   bf16* wpacked = nullptr; int Ktotal = 0, Cp = 0;
+  float* gdz = nullptr;      // training plans: G_HEAD / G_CONV_ACT pre-activation gradient, dense NHWC fp32 [.][Cout]
   double macs = 0.0;
   CUtensorMap tmA{}, tmB{};
   ConvKernelParams kp{};
@@ -276,6 +283,11 @@ struct v2v_plan {
   int sp() const { return precise ? 2 : 1; }
   bool allow_reuse = true;
   bool lowered = false, finalized = false;
+  bool train = false;          // keep what the backward needs (batch statistics) and allocate gradient buffers
+  void* garena = nullptr; size_t garena_bytes = 0;
+  std::vector<float*> gslot;   // per IO slot: plan-internal gradient of a head output produced by the composite backward
+  float* gsums = nullptr;      // scratch of the norm backward [2][N][Cmax]
+  float* train_stats = nullptr;
   std::vector<Value> values;
   std::vector<Raw> raws;
   std::vector<GOp> gops;
@@ -597,6 +609,153 @@ static int run_xop(v2v_plan* P, const XOp& x, cudaStream_t s) {
   return 0;
 }
 
+// ------------------------------------------------------------------------------ training: gradient buffers
+static int alloc_training(v2v_plan* P, cudaStream_t stream) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = round_up_sz(off + bytes, 256); return o; };
+  std::vector<size_t> vo(P->values.size()), ro(P->raws.size()), go(P->gops.size(), 0), so(P->n_slots, (size_t)-1);
+  int cmax = 1, nmax = 1;
+  for (size_t i = 0; i < P->values.size(); ++i) { const Value& v = P->values[i]; vo[i] = take((size_t)v.N * v.H * v.W * v.C * 4); nmax = std::max(nmax, v.N); }
+  for (size_t i = 0; i < P->raws.size(); ++i) { const Raw& r = P->raws[i]; ro[i] = take(r.desc.elems() * 4); cmax = std::max(cmax, r.C); }
+  for (size_t i = 0; i < P->gops.size(); ++i) {
+    const GOp& op = P->gops[i];
+    if (op.kind == G_HEAD || op.kind == G_CONV_ACT) {
+      const Value& vin = P->values[op.value_in];
+      go[i] = take((size_t)vin.N * op.geom.out_h * op.geom.out_w * op.conv.Cout * 4);
+      cmax = std::max(cmax, op.conv.Cout);
+    } else if (op.kind == G_COMPOSITE) {
+      const CompositeParams& c = op.comp;
+      const size_t px = (size_t)c.N * c.H * c.W * 4;
+      so[c.s_raw] = take(3 * px);
+      if (c.s_flow >= 0) so[c.s_flow] = take(2 * px);
+      if (c.s_weight >= 0) so[c.s_weight] = take(px);
+      if (c.s_fg >= 0) so[c.s_fg] = take(3 * px);
+    }
+  }
+  const size_t sums_off = take((size_t)2 * nmax * cmax * 4);
+  P->garena_bytes = off;
+  V2V_CUDA(cudaMalloc(&P->garena, P->garena_bytes));
+  V2V_CUDA(cudaMemsetAsync(P->garena, 0, P->garena_bytes, stream));
+  uint8_t* b = reinterpret_cast<uint8_t*>(P->garena);
+  for (size_t i = 0; i < P->values.size(); ++i) P->values[i].gval = reinterpret_cast<float*>(b + vo[i]);
+  for (size_t i = 0; i < P->raws.size(); ++i) P->raws[i].graw = reinterpret_cast<float*>(b + ro[i]);
+  for (size_t i = 0; i < P->gops.size(); ++i) if (go[i] || P->gops[i].kind == G_HEAD || P->gops[i].kind == G_CONV_ACT) P->gops[i].gdz = reinterpret_cast<float*>(b + go[i]);
+  P->gslot.assign(P->n_slots, nullptr);
+  for (int sidx = 0; sidx < P->n_slots; ++sidx) if (so[sidx] != (size_t)-1) P->gslot[sidx] = reinterpret_cast<float*>(b + so[sidx]);
+  P->gsums = reinterpret_cast<float*>(b + sums_off);
+  return 0;
+}
+
+// Backward of one recorded forward (the plan's buffers still hold it).  Walks the graph ops in reverse.
+static int run_backward(v2v_plan* P, void* const* io, void* const* gio, const std::unordered_map<const void*, void*>& pg,
+                        cudaStream_t s) {
+  auto grad_of = [&](const void* param) -> float* {
+    if (!param) return nullptr;
+    auto it = pg.find(param);
+    return it == pg.end() ? nullptr : reinterpret_cast<float*>(it->second);
+  };
+  V2V_CUDA(cudaMemsetAsync(P->garena, 0, P->garena_bytes, s));
+  auto conv_bwd = [&](const GOp& op, const float* dy, int dy_C, bool bias_grad) -> int {
+    const Value& vin = P->values[op.value_in];
+    BwdConv b{};
+    b.N = vin.N; b.H = vin.H; b.W = vin.W; b.oh = op.geom.out_h; b.ow = op.geom.out_w;
+    b.Cin = op.conv.Cin; b.Cout = op.conv.Cout; b.kh = op.conv.kh; b.kw = op.conv.kw; b.stride = op.conv.stride;
+    b.pad = op.conv.pad; b.transposed = op.conv.transposed; b.pad_mode = op.conv.pad_mode;
+    b.x = P->acts[vin.bufs[op.req_index]];
+    b.dy = dy; b.dy_C = dy_C;
+    b.w = op.conv.weight; b.w2 = op.conv.Cout2 > 0 ? op.conv.weight2 : nullptr; b.Cout1 = op.conv.Cout - op.conv.Cout2;
+    const bool input_needs = vin.input_slot < 0 || (gio && gio[vin.input_slot] != nullptr);
+    b.dx = input_needs ? vin.gval : nullptr;
+    b.dw = grad_of(op.conv.weight); b.dw2 = b.w2 ? grad_of(op.conv.weight2) : nullptr;
+    if (bias_grad) { b.dbias = grad_of(op.conv.bias); b.dbias2 = b.w2 ? grad_of(op.conv.bias2) : nullptr; }
+    V2V_CUDA(launch_conv_bwd(b, s));
+    return 0;
+  };
+  for (int i = (int)P->gops.size() - 1; i >= 0; --i) {
+    const GOp& op = P->gops[i];
+    switch (op.kind) {
+      case G_EXPORT: {
+        const Value& v = P->values[op.value_in];
+        if (gio[op.slot]) V2V_CUDA(launch_grad_import(reinterpret_cast<const float*>(gio[op.slot]), v.gval, v.N, v.C, 0, v.C, v.H, v.W, s));
+        break;
+      }
+      case G_COMPOSITE: {
+        const CompositeParams& c = op.comp;
+        CompositeBwd b{};
+        b.N = c.N; b.H = c.H; b.W = c.W; b.prev_C = c.prev_C; b.use_warp = c.use_warp; b.align_corners = c.align_corners;
+        auto f = [&](int slot) { return slot >= 0 ? reinterpret_cast<const float*>(io[slot]) : nullptr; };
+        b.raw = f(c.s_raw); b.flow = f(c.s_flow); b.weight = f(c.s_weight); b.prev = f(c.s_prev); b.mask = f(c.s_mask);
+        V2V_REQUIRE(c.s_fg < 0 || c.s_raw_out >= 0, V2V_ERR_STATE, "training needs the composited raw image in its own slot");
+        b.g_final = reinterpret_cast<const float*>(gio[c.s_final]);
+        b.g_rawout = c.s_raw_out >= 0 ? reinterpret_cast<const float*>(gio[c.s_raw_out]) : nullptr;
+        b.d_raw = P->gslot[c.s_raw]; b.d_flow = c.s_flow >= 0 ? P->gslot[c.s_flow] : nullptr;
+        b.d_weight = c.s_weight >= 0 ? P->gslot[c.s_weight] : nullptr; b.d_fg = c.s_fg >= 0 ? P->gslot[c.s_fg] : nullptr;
+        V2V_CUDA(launch_composite_bwd(b, s));
+        break;
+      }
+      case G_HEAD: {
+        const Value& vin = P->values[op.value_in];
+        HeadBwd h{};
+        h.N = vin.N; h.H = op.geom.out_h; h.W = op.geom.out_w; h.Cout = op.conv.Cout; h.dz = op.gdz; h.dz_C = op.conv.Cout;
+        for (int j = 0; j < op.conv.Cout; ++j) {
+          const int slot = op.head[j].slot;
+          h.out[j] = reinterpret_cast<const float*>(io[slot]);
+          h.g_ext[j] = reinterpret_cast<const float*>(gio[slot]);
+          h.g_int[j] = slot < (int)P->gslot.size() ? P->gslot[slot] : nullptr;
+          h.off[j] = op.kp.head_off[j]; h.bstride[j] = op.kp.head_bstride[j];
+          h.act[j] = op.head[j].act; h.scale[j] = op.head[j].scale;
+        }
+        V2V_CUDA(launch_head_bwd(h, s));
+        int rc = conv_bwd(op, op.gdz, op.conv.Cout, true); if (rc) return rc;
+        break;
+      }
+      case G_NORM_ACT: {
+        const Raw& r = P->raws[op.raw];
+        const GOp& cop = P->gops[r.conv_op];
+        const Value& vo = P->values[op.value_out];
+        NormBwd n{};
+        n.N = vo.N; n.H = vo.H; n.W = vo.W; n.C = op.cC; n.raw = r.desc; n.c_off = op.n_off;
+        n.has_norm = op.norm.kind != V2V_NORM_NONE; n.batch_stats = op.norm.kind == V2V_NORM_BATCH;
+        V2V_REQUIRE(n.has_norm || cop.conv.bias || true, V2V_ERR_STATE, "unreachable");
+        n.scale = r.scale + op.n_off; n.shift = r.shift + op.n_off; n.stat_stride = r.C;
+        n.mean = n.has_norm ? r.mean + op.n_off : nullptr; n.rstd = n.has_norm ? r.rstd + op.n_off : nullptr;
+        if (!n.has_norm && !cop.conv.bias) {   // plain activation of a bias-less conv: scale / shift arrays are unset
+          v2v_plan::BiasAffine ba{r.scale, r.shift, nullptr, r.N, r.C, r.C};
+          V2V_CUDA(launch_bias_affine(ba.scale, ba.shift, nullptr, ba.N, ba.C, ba.stride, s));
+        }
+        n.act = op.act; n.slope = op.slope; n.dy = vo.gval; n.draw = r.graw; n.draw_C = r.desc.C;
+        n.dadd0 = op.add[0] >= 0 ? P->values[op.add[0]].gval : nullptr;
+        n.dadd1 = op.add[1] >= 0 ? P->values[op.add[1]].gval : nullptr;
+        n.sums = P->gsums;
+        if (n.has_norm) { n.dgamma = grad_of(op.norm.gamma); n.dbeta = grad_of(op.norm.beta); }
+        else { n.dgamma = nullptr; n.dbeta = grad_of(op.n_off == 0 ? cop.conv.bias : cop.conv.bias2); }
+        V2V_CUDA(launch_norm_bwd(n, s));
+        break;
+      }
+      case G_CONV: {
+        const Raw& r = P->raws[op.raw];
+        int rc = conv_bwd(op, r.graw, r.desc.C, false); if (rc) return rc;    // a bias in front of a norm has zero gradient
+        break;
+      }
+      case G_CONV_ACT: {
+        const Value& vo = P->values[op.value_out];
+        V2V_CUDA(launch_convact_bwd(vo.gval, P->acts[vo.bufs[0]], op.act, op.slope, op.gdz, op.conv.Cout, s));
+        int rc = conv_bwd(op, op.gdz, op.conv.Cout, true); if (rc) return rc;
+        break;
+      }
+      case G_INPUT: {
+        const Value& v = P->values[op.value_out];
+        if (gio[op.slot]) V2V_CUDA(launch_grad_export(v.gval, reinterpret_cast<float*>(gio[op.slot]), v.N, op.C_src, op.c_off, v.C, v.H, v.W, s));
+        break;
+      }
+      case G_CONCAT: case G_CORR:
+        set_error("backward through concat / correlation is not implemented (FlowNet2 runs under no_grad, models/flownet.py:26)");
+        return V2V_ERR_UNSUPPORTED;
+    }
+  }
+  return 0;
+}
+
 }  // namespace v2v
 
 // =============================================================================================== C ABI
@@ -625,11 +784,28 @@ int v2v_plan_set_precision(v2v_plan* p, int precision) {
   return 0;
 }
 
+int v2v_plan_set_training(v2v_plan* p, int on) {
+  V2V_REQUIRE(p && !p->finalized, V2V_ERR_STATE, "set the training flag before finalize");
+  p->train = on != 0;
+  return 0;
+}
+
+int v2v_plan_backward(v2v_plan* P, void* const* io_ptrs, void* const* grad_io_ptrs, int n_io, const void* const* params,
+                      void* const* param_grads, int n_params, v2v_stream_t stream_) {
+  V2V_REQUIRE(P && P->finalized && P->train, V2V_ERR_STATE, "plan not finalized in training mode");
+  V2V_REQUIRE(n_io >= P->n_slots && io_ptrs && grad_io_ptrs, V2V_ERR_INVALID, "need %d io / gradient pointers", P->n_slots);
+  std::unordered_map<const void*, void*> pg;
+  for (int i = 0; i < n_params; ++i) if (params[i] && param_grads[i]) pg[params[i]] = param_grads[i];
+  return run_backward(P, io_ptrs, grad_io_ptrs, pg, reinterpret_cast<cudaStream_t>(stream_));
+}
+
 int v2v_plan_destroy(v2v_plan* p) {
   if (!p) return 0;
   if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
   if (p->graph_stream) cudaStreamDestroy(p->graph_stream);
   if (p->arena) cudaFree(p->arena);
+  if (p->garena) cudaFree(p->garena);
+  if (p->train_stats) cudaFree(p->train_stats);
   if (p->io_dev) cudaFree(p->io_dev);
   delete p;
   return 0;
@@ -647,6 +823,7 @@ int v2v_g_input(v2v_plan* p, int slot, int N, int C_src, int c_off, int C, int H
               "bad input description");
   GOp op; op.kind = G_INPUT; op.slot = slot; op.C_src = C_src; op.c_off = c_off;
   op.value_out = new_value(p, N, H, W, C);
+  p->values[op.value_out].input_slot = slot;
   p->n_slots = std::max(p->n_slots, slot + 1);
   p->gops.push_back(op);
   *value_out = op.value_out;
@@ -774,6 +951,11 @@ int v2v_g_export(v2v_plan* p, int value, int slot) {
 
 int v2v_g_composite(v2v_plan* p, int s_raw, int s_flow, int s_weight, int s_prev, int prev_C, int s_fg, int s_mask,
                     int s_final, int N, int H, int W, int use_warp, int align_corners) {
+  return v2v_g_composite_ex(p, s_raw, s_flow, s_weight, s_prev, prev_C, s_fg, s_mask, s_final, -1, N, H, W, use_warp, align_corners);
+}
+
+int v2v_g_composite_ex(v2v_plan* p, int s_raw, int s_flow, int s_weight, int s_prev, int prev_C, int s_fg, int s_mask,
+                       int s_final, int s_raw_out, int N, int H, int W, int use_warp, int align_corners) {
   V2V_REQUIRE(p && !p->lowered, V2V_ERR_STATE, "plan already lowered or null");
   V2V_REQUIRE(s_raw >= 0 && s_final >= 0, V2V_ERR_INVALID, "composite needs raw and final slots");
   V2V_REQUIRE(!use_warp || (s_flow >= 0 && s_weight >= 0 && s_prev >= 0 && prev_C >= 3), V2V_ERR_INVALID,
@@ -782,6 +964,8 @@ int v2v_g_composite(v2v_plan* p, int s_raw, int s_flow, int s_weight, int s_prev
   GOp op; op.kind = G_COMPOSITE;
   CompositeParams& c = op.comp;
   c.s_raw = s_raw; c.s_flow = s_flow; c.s_weight = s_weight; c.s_prev = s_prev; c.s_fg = s_fg; c.s_mask = s_mask;
+  c.s_raw_out = s_raw_out;
+  p->n_slots = std::max(p->n_slots, s_raw_out + 1);
   c.s_final = s_final; c.prev_C = prev_C; c.N = N; c.H = H; c.W = W; c.align_corners = align_corners; c.use_warp = use_warp;
   int m = std::max({s_raw, s_flow, s_weight, s_prev, s_fg, s_mask, s_final});
   p->n_slots = std::max(p->n_slots, m + 1);
@@ -847,6 +1031,15 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
     r.shift = reinterpret_cast<float*>(base + raw_off[i].shift);
   }
 
+  if (P->train) {                       // saved batch statistics (the finalize launches below write them)
+    size_t tot = 0;
+    for (auto& r : P->raws) tot += 2 * (size_t)r.N * r.C;
+    float* st = nullptr;
+    V2V_CUDA(cudaMalloc(reinterpret_cast<void**>(&st), std::max<size_t>(tot, 1) * sizeof(float)));
+    V2V_CUDA(cudaMemsetAsync(st, 0, std::max<size_t>(tot, 1) * sizeof(float), stream));
+    P->train_stats = st;
+    for (auto& r : P->raws) { r.mean = st; st += (size_t)r.N * r.C; r.rstd = st; st += (size_t)r.N * r.C; }
+  }
   // ---- emit executable ops
   if (stats_end > stats_begin) {
     XOp m; m.kind = X_MEMSET; m.ms_ptr = base + stats_begin; m.ms_bytes = stats_end - stats_begin;
@@ -922,6 +1115,7 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
           fp.running_mean = op.norm.running_mean; fp.running_var = op.norm.running_var;
           fp.num_batches_tracked = reinterpret_cast<long long*>(op.norm.num_batches_tracked);
           fp.momentum = op.norm.momentum; fp.eps = op.norm.eps; fp.scale = r.scale; fp.shift = r.shift;
+          fp.mean_out = r.mean; fp.rstd_out = r.rstd;
           // fusing the finalize into the apply prologue measured slower than the separate launch: opt-in only
           { const char* ef = getenv("V2V_FUSE_FINALIZE"); fuse_fin = (ef && ef[0] == '1') && r.N <= 8; }
           fin_params = fp;
@@ -1004,6 +1198,7 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
       }
     }
   }
+  if (P->train) { rc = alloc_training(P, stream); if (rc) return rc; }
   V2V_CUDA(cudaStreamSynchronize(stream));
   P->finalized = true;
   return 0;
@@ -1023,6 +1218,15 @@ int v2v_plan_run(v2v_plan* P, void* const* io_ptrs, int n_io, int use_graph, v2v
   V2V_REQUIRE(n_io >= P->n_slots && io_ptrs, V2V_ERR_INVALID, "need %d io pointers, got %d", P->n_slots, n_io);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   V2V_CUDA(cudaMemcpyAsync(P->io_dev, io_ptrs, sizeof(void*) * P->n_slots, cudaMemcpyHostToDevice, stream));
+  if (use_graph & 2) {        // recomputation before a backward: same results, no running-statistics side effect
+    for (const XOp& x : P->xops) {
+      if (x.kind == X_FINALIZE) {
+        XOp y = x; y.fin.running_mean = nullptr; y.fin.running_var = nullptr; y.fin.num_batches_tracked = nullptr;
+        int rc = run_xop(P, y, stream); if (rc) return rc;
+      } else { int rc = run_xop(P, x, stream); if (rc) return rc; }
+    }
+    return 0;
+  }
   if (!use_graph) {
     for (const XOp& x : P->xops) { int rc = run_xop(P, x, stream); if (rc) return rc; }
     return 0;

@@ -143,6 +143,8 @@ struct FinalizeParams {
   float momentum, eps;
   float* scale;            // [N][scale_stride], written at column c_off + c
   float* shift;
+  float* mean_out;         // training plans: batch / instance mean and 1/sqrt(var + eps), same indexing; may be null
+  float* rstd_out;
   int c_off, scale_stride; // channel slice of the raw tensor this norm layer covers
 };
 
@@ -207,6 +209,7 @@ struct PackParams {
 struct CompositeParams {
   void* const* io;
   int s_raw, s_flow, s_weight, s_prev, s_fg, s_mask, s_final;   // IO slots; -1 = absent
+  int s_raw_out;           // >= 0: the composited raw image goes to this slot and s_raw keeps the head output (training plans)
   int prev_C;              // img_prev channel count (last 3 are warped)
   int N, H, W;
   int align_corners;

@@ -52,6 +52,7 @@ __global__ void composite_kernel(CompositeParams p) {
   const size_t total = (size_t)p.N * HW;
   float* raw = reinterpret_cast<float*>(p.io[p.s_raw]);          // in: tanh head output; out: composited
   float* fin = reinterpret_cast<float*>(p.io[p.s_final]);
+  float* raw_out = p.s_raw_out >= 0 ? reinterpret_cast<float*>(p.io[p.s_raw_out]) : raw;
   const float* flow = p.s_flow >= 0 ? reinterpret_cast<const float*>(p.io[p.s_flow]) : nullptr;
   const float* wgt = p.s_weight >= 0 ? reinterpret_cast<const float*>(p.io[p.s_weight]) : nullptr;
   const float* prev = p.s_prev >= 0 ? reinterpret_cast<const float*>(p.io[p.s_prev]) : nullptr;
@@ -90,7 +91,7 @@ __global__ void composite_kernel(CompositeParams p) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       fin[((size_t)n * 3 + c) * HW + pix] = f[c];
-      if (fg) raw[((size_t)n * 3 + c) * HW + pix] = r[c];
+      if (fg || raw_out != raw) raw_out[((size_t)n * 3 + c) * HW + pix] = r[c];
     }
   }
 }

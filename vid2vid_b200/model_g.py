@@ -30,15 +30,46 @@ class Vid2VidModelG(nn.Module):
         self.device_ = dev
         for s in range(self.n_scales):
             setattr(self, 'netG' + str(s), networks.build_netG(opt, s).to(dev))
+        # vid2vid_model_G.py:46-51: checkpoints are loaded whenever not training (or continuing / pre-training); a missing G0
+        # is an error there (base_model.py:63-72).  opt.synthetic_weights (benchmarks / tests, no checkpoints offline) skips it.
+        if (not self.isTrain or getattr(opt, 'continue_train', False) or getattr(opt, 'load_pretrain', '')) and \
+                not getattr(opt, 'synthetic_weights', False):
+            for s in range(self.n_scales):
+                self.load_network(getattr(self, 'netG' + str(s)), 'G' + str(s), opt.which_epoch, getattr(opt, 'load_pretrain', ''))
         self.netG_i = self.load_single_G() if self.use_single_G else None
         self.fake_B_prev = None
+        if self.isTrain:
+            self.init_train()
         return self
+
+    def load_network(self, network, network_label, epoch_label, save_dir=''):
+        """BaseModel.load_network (base_model.py:56-107): <checkpoints_dir>/<name>/<epoch>_net_<label>.pth; a missing G0
+        raises, other missing files are reported; on a key / shape mismatch the matching subset is loaded."""
+        save_filename = '%s_net_%s.pth' % (epoch_label, network_label)
+        save_dir = save_dir or os.path.join(self.opt.checkpoints_dir, self.opt.name)
+        save_path = os.path.join(save_dir, save_filename)
+        if not os.path.isfile(save_path):
+            print('%s not exists yet!' % save_path)
+            if 'G0' in network_label:
+                raise FileNotFoundError('Generator must exist! (%s)' % save_path)
+            return
+        sd = torch.load(save_path, map_location=self.device_)
+        try:
+            network.load_state_dict(sd)
+        except Exception:
+            own = network.state_dict()
+            kept = {k: v for k, v in sd.items() if k in own and v.size() == own[k].size()}
+            missing = sorted({k.split('.')[0] for k in own if k not in kept})
+            print('Pretrained network %s: loaded %d of %d tensors; not initialised from the file: %s' % (
+                network_label, len(kept), len(own), missing))
+            own.update(kept)
+            network.load_state_dict(own)
 
     # ------------------------------------------------------------------ first-frame generator
     def load_single_G(self):
         """vid2vid_model_G.py:261-288.  The architecture per loadSize is the reference's; weights are
-        loaded from checkpoints/label2city_single/ when that file exists, else left at their random
-        initialisation (synthetic benchmarking has no checkpoints)."""
+        loaded from checkpoints/label2city_single/ (a missing file raises, as torch.load does in the reference) unless
+        opt.synthetic_weights is set (synthetic benchmarking has no checkpoints)."""
         opt = self.opt
         if 'City' not in opt.dataroot:
             raise ValueError('Single image generator does not exist')
@@ -51,8 +82,9 @@ class Vid2VidModelG(nn.Module):
             load_path, netG = single_path + 'latest_net_G_2048.pth', networks.define_G(35, 3, 0, 32, 'local', 4, 'instance', 0, [], opt)
         else:
             raise ValueError('Single image generator does not exist')
-        if os.path.exists(load_path):
-            netG.load_state_dict(torch.load(load_path))
+        if getattr(opt, 'synthetic_weights', False) and not os.path.exists(load_path):
+            return netG.to(self.device_)            # benchmarks / tests: random initialisation, stated in `data`
+        netG.load_state_dict(torch.load(load_path, map_location=self.device_))      # missing file raises, as the reference does
         return netG.to(self.device_)
 
     # ------------------------------------------------------------------ tensor helpers (CUDA kernels)
@@ -178,5 +210,74 @@ class Vid2VidModelG(nn.Module):
             fake_B_prev = [B[0] for B in fake_B_prev]
         return fake_B_prev
 
+    # ------------------------------------------------------------------ training forward
+    def init_train(self):
+        """The training half of vid2vid_model_G.py:19-84: per-GPU frame budget and the generator optimizer."""
+        opt = self.opt
+        self.n_frames_load = min(getattr(opt, 'max_frames_per_gpu', 1), opt.n_frames_total - opt.n_frames_G + 1)
+        self.n_frames_bp = min(getattr(opt, 'max_frames_backpropagate', 1), self.n_frames_load)
+        self.finetune_all = True                                           # niter_fix_global == 0 (:66-68)
+        params = []
+        for s in range(self.n_scales):
+            params += list(getattr(self, 'netG' + str(s)).parameters())
+        beta1, beta2, lr = (0, 0.9, opt.lr / 2) if opt.TTUR else (opt.beta1, 0.999, opt.lr)       # :74-83
+        self.old_lr = opt.lr
+        self.optimizer_G = torch.optim.Adam(params, lr=lr, betas=(beta1, beta2))
+        return self
+
     def forward(self, input_A, input_B, inst_A, fake_B_prev, dummy_bs=0):
-        raise NotImplementedError('training forward needs the backward kernels (round 2); no PyTorch fallback')
+        """vid2vid_model_G.py:114-140 (one process per GPU: no dummy padding, no frame pipeline over GPUs)."""
+        tG = self.opt.n_frames_G
+        real_A_all, real_B_all, _ = self.encode_input(input_A, input_B, inst_A)
+        is_first_frame = fake_B_prev is None
+        if is_first_frame:
+            fake_B_prev = self.generate_first_frame(real_A_all, real_B_all)
+        fake_B, fake_B_raw, flow, weight = self.generate_frame_train(real_A_all, fake_B_prev, is_first_frame)
+        fake_B_prev = [B[:, -tG + 1:].detach() for B in fake_B]
+        fake_B = [B[:, tG - 1:] for B in fake_B]
+        return fake_B[0], fake_B_raw, flow, weight, real_A_all[:, tG - 1:], real_B_all[:, tG - 2:], fake_B_prev
+
+    def generate_frame_train(self, real_A_all, fake_B_pyr, is_first_frame):
+        """vid2vid_model_G.py:142-196."""
+        tG, n_scales = self.opt.n_frames_G, self.n_scales
+        if not hasattr(self, 'n_frames_load'):
+            self.init_train()
+        bs = real_A_all.shape[0]
+        real_A_pyr = self.build_pyr(real_A_all)
+        fake_B_pyr = list(fake_B_pyr)
+        fake_Bs_raw, flows, weights = None, None, None
+        cat = lambda a, b: b if a is None else torch.cat([a, b], dim=1)
+        for t in range(self.n_frames_load):
+            fake_B_feat = flow_feat = fake_B_fg_feat = None
+            for s in range(n_scales):
+                si = n_scales - 1 - s
+                real_As = real_A_pyr[si]
+                h, w = real_As.shape[-2:]
+                real_As_reshaped = real_As[:, t:t + tG].reshape(bs, -1, h, w)
+                fake_B_prevs = fake_B_pyr[si][:, t:t + tG - 1]
+                if (t % self.n_frames_bp) == 0:
+                    fake_B_prevs = fake_B_prevs.detach()
+                fake_B_prevs_reshaped = fake_B_prevs.reshape(bs, -1, h, w)
+                mask_F = self.compute_mask(real_As, t + tG - 1) if self.opt.fg else None
+                use_raw_only = self.opt.no_first_img and is_first_frame
+                fake_B, flow, weight, fake_B_raw, fake_B_feat, flow_feat, fake_B_fg_feat = getattr(self, 'netG' + str(s)).forward(
+                    real_As_reshaped, fake_B_prevs_reshaped, mask_F, fake_B_feat, flow_feat, fake_B_fg_feat, use_raw_only)
+                if s != n_scales - 1 and not self.finetune_all:
+                    fake_B, fake_B_feat = fake_B.detach(), fake_B_feat.detach()
+                    if flow is not None:
+                        flow, flow_feat = flow.detach(), flow_feat.detach()
+                    if fake_B_fg_feat is not None:
+                        fake_B_fg_feat = fake_B_fg_feat.detach()
+                fake_B_pyr[si] = cat(fake_B_pyr[si], fake_B.unsqueeze(1))
+                if s == n_scales - 1:
+                    fake_Bs_raw = cat(fake_Bs_raw, fake_B_raw.unsqueeze(1))
+                    if flow is not None:
+                        flows, weights = cat(flows, flow.unsqueeze(1)), cat(weights, weight.unsqueeze(1))
+        return fake_B_pyr, fake_Bs_raw, flows, weights
+
+    def compute_fake_B_prev(self, real_B_prev, fake_B_last, fake_B):
+        """vid2vid_model_G.py:332-336."""
+        fake_B_prev = real_B_prev[:, 0:1] if fake_B_last is None else fake_B_last[0][:, -1:]
+        if fake_B.size()[1] > 1:
+            fake_B_prev = torch.cat([fake_B_prev, fake_B[:, :-1].detach()], dim=1)
+        return fake_B_prev

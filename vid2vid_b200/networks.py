@@ -232,6 +232,49 @@ def _can_pair(mods_a, mods_b):
             ca.kernel_size == cb.kernel_size and ca.stride == cb.stride and ca.out_channels % 8 == 0)
 
 
+class _PlanFunction(torch.autograd.Function):
+    """Autograd node of one plan execution: forward = v2v_plan_run, backward = v2v_plan_backward (hand-written CUDA backward
+    kernels over the plan's own buffers).  A plan holds the intermediates of its LAST run only: when another forward of the
+    same plan happened in between (netD is called three times per loss, vid2vid_model_D.py:168-176), the backward first
+    re-executes this node's forward (without the running-statistics side effect)."""
+
+    @staticmethod
+    def forward(ctx, owner, plan, io, in_slots, out_slots, fixed_slots, *args):
+        # args = the input tensors that may need a gradient (slot order of in_slots) followed by the module parameters;
+        # fixed_slots = every slot the caller supplied (inputs incl. masks): all other slots are outputs / internal tensors
+        n_in = len(in_slots)
+        ctx.plan, ctx.io, ctx.in_slots, ctx.out_slots, ctx.n_in, ctx.fixed = plan, io, in_slots, out_slots, n_in, set(fixed_slots)
+        ctx.params = args[n_in:]
+        plan.run(io, owner.use_cuda_graph)
+        ctx.run_id = plan.run_id
+        return tuple(io[s] for s in out_slots)
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        plan, io = ctx.plan, ctx.io
+        if plan.run_id != ctx.run_id:
+            scratch = list(io)
+            for s_ in range(len(scratch)):      # outputs of the re-execution go to scratch tensors (the originals are the user's)
+                if s_ not in ctx.fixed and scratch[s_] is not None:
+                    scratch[s_] = torch.empty_like(scratch[s_])
+            plan.run(scratch, False, recompute=True)
+            io = scratch
+        gio = [None] * len(io)
+        for s_, g in zip(ctx.out_slots, gouts):
+            if g is not None:
+                gio[s_] = g.contiguous().float()
+        gin = []
+        for k, s_ in enumerate(ctx.in_slots):
+            if ctx.needs_input_grad[6 + k] and io[s_] is not None:
+                gio[s_] = torch.zeros_like(io[s_])
+                gin.append(gio[s_])
+            else:
+                gin.append(None)
+        pgrads = [torch.zeros_like(p) if ctx.needs_input_grad[6 + ctx.n_in + j] else None for j, p in enumerate(ctx.params)]
+        plan.backward(io, gio, ctx.params, pgrads)
+        return (None,) * 6 + tuple(gin) + tuple(pgrads)
+
+
 # Arithmetic of the conv stack (include/v2v_b200.h V2V_PREC_*): 'precise' = split-bf16 3-MMA, fp32-class -- the mode
 # the parity tests against the fp32 reference and the headline benchmark use; 'fast' = plain bf16 operands.
 DEFAULT_PRECISION = os.environ.get('V2V_PRECISION', 'precise')
@@ -266,15 +309,22 @@ class _Planned(nn.Module):
             ver += t._version
         return ptrs, ver
 
-    def _get_plan(self, key, device, build):
+    def _wants_grad(self, *tensors):
+        """Training plan (saved statistics, gradient buffers, autograd through the C-ABI backward) when autograd is
+        recording and a parameter or an input asks for a gradient; the inference plan otherwise."""
+        if not torch.is_grad_enabled():
+            return False
+        return any(p.requires_grad for p in self.parameters()) or any(t is not None and t.requires_grad for t in tensors)
+
+    def _get_plan(self, key, device, build, train=False):
         ptrs, ver = self._signature()
-        key = key + (self._precision(),)
+        key = key + (('train',) if train else ()) + (self._precision(),)
         ent = self._plans().get(key)
         if ent is not None and ent['ptrs'] != ptrs:
             ent = None
         if ent is None:
             plan = Plan(device.index if device.index is not None else torch.cuda.current_device(),
-                        precision=self._precision())
+                        precision=self._precision(), train=train)
             build(plan)
             plan.finalize()
             ent = {'plan': plan, 'ptrs': ptrs, 'ver': ver}
@@ -298,7 +348,7 @@ class _Planned(nn.Module):
 
 
 # IO slots of the composite generators
-S_IN, S_PREV, S_MASK, S_FINAL, S_FLOW, S_W, S_RAW, S_IMGF, S_FLOWF, S_FGF, S_FG, S_CI, S_CF, S_CG = range(14)
+S_IN, S_PREV, S_MASK, S_FINAL, S_FLOW, S_W, S_RAW, S_IMGF, S_FLOWF, S_FGF, S_FG, S_CI, S_CF, S_CG, S_RAWC = range(15)
 
 
 class CompositeGenerator(_Planned):
@@ -380,18 +430,27 @@ class CompositeGenerator(_Planned):
 
     def _emit_composite(self, plan, N, H, W, use_raw_only):
         warp = not (use_raw_only or self.no_flow)
+        # training plans keep the head output in S_RAW (the backward needs it) and write the composited raw image to S_RAWC
         plan.composite(S_RAW, S_FLOW if warp else -1, S_W if warp else -1, S_PREV if warp else -1, self.prev_output_nc,
                        S_FG if self.use_fg_model else -1, S_MASK if self.use_fg_model else -1, S_FINAL, N, H, W, warp,
-                       self.align_corners)                                                 # :216-230
+                       self.align_corners, s_raw_out=S_RAWC if (plan.train and self.use_fg_model) else -1)   # :216-230
 
     def _run(self, key, coarse, input, img_prev, mask, use_raw_only):
         self._require_cuda(input, img_prev, mask, *coarse)
         input, img_prev = input.contiguous(), img_prev.contiguous()
         N, _, H, W = input.shape
+        if input.shape[1] != self.input_nc or img_prev.shape[1] != self.prev_output_nc or tuple(img_prev.shape[2:]) != (H, W):
+            raise ValueError('netG input / img_prev shapes %s / %s do not match the module (%d / %d channels)' % (
+                tuple(input.shape), tuple(img_prev.shape), self.input_nc, self.prev_output_nc))
+        if self.use_fg_model and (mask is None or mask.numel() != N * H * W):
+            raise ValueError('fg model needs a (N,1,H,W) mask')
+        if self.output_nc != 3:
+            raise NotImplementedError('the fused composite kernel handles 3 output channels')
+        train = self._wants_grad(input, img_prev, *coarse)
         plan = self._get_plan(key + (N, H, W, bool(use_raw_only), bool(self.align_corners)), input.device,
-                              lambda p: self._describe(p, N, H, W, use_raw_only))
+                              lambda p: self._describe(p, N, H, W, use_raw_only), train=train)
         new = lambda c: torch.empty((N, c, H, W), device=input.device, dtype=torch.float32)
-        io = [None] * 14
+        io = [None] * 15
         io[S_IN], io[S_PREV] = input, img_prev
         io[S_FINAL], io[S_RAW], io[S_IMGF] = new(self.output_nc), new(self.output_nc), new(self._feat_c())
         if not self.no_flow:
@@ -401,8 +460,22 @@ class CompositeGenerator(_Planned):
             io[S_FGF], io[S_FG] = new(self._fg_feat_c()), new(self.output_nc)
         for s, t in zip((S_CI, S_CF, S_CG), coarse):
             io[s] = t.contiguous() if t is not None else None
-        plan.run(io, self.use_cuda_graph)
-        return io[S_FINAL], io[S_FLOW], io[S_W], io[S_RAW], io[S_IMGF], io[S_FLOWF], io[S_FGF]
+        if not train:
+            plan.run(io, self.use_cuda_graph)
+            return io[S_FINAL], io[S_FLOW], io[S_W], io[S_RAW], io[S_IMGF], io[S_FLOWF], io[S_FGF]
+        raw_slot = S_RAW
+        if self.use_fg_model:
+            io[S_RAWC] = new(self.output_nc)
+            raw_slot = S_RAWC
+        in_slots = [s for s in (S_IN, S_PREV, S_CI, S_CF, S_CG) if io[s] is not None]
+        out_slots = [s for s in (S_FINAL, S_FLOW, S_W, raw_slot, S_IMGF, S_FLOWF, S_FGF) if io[s] is not None]
+        fixed = [s for s in (S_IN, S_PREV, S_MASK, S_CI, S_CF, S_CG) if io[s] is not None]
+        params = [p for p in self.parameters()]
+        outs = _PlanFunction.apply(self, plan, io, tuple(in_slots), tuple(out_slots), tuple(fixed),
+                                   *([io[s] for s in in_slots] + params))
+        res = dict(zip(out_slots, outs))
+        return (res.get(S_FINAL), res.get(S_FLOW), res.get(S_W), res.get(raw_slot), res.get(S_IMGF), res.get(S_FLOWF),
+                res.get(S_FGF))
 
     def _feat_c(self):
         return self.model_final_img[1].in_channels
@@ -629,6 +702,9 @@ class MultiscaleDiscriminator(_Planned):
         layers.append(cur)
         return layers
 
+    def _tower_params(self, d):
+        return [p for mods in self._tower_layers(d) for m in mods for p in m.parameters()]
+
     def _describe(self, plan, d, N, H, W):
         layers = self._tower_layers(d)
         v = plan.input(0, N, self.input_nc, 0, self.input_nc, H, W)
@@ -655,12 +731,18 @@ class MultiscaleDiscriminator(_Planned):
 
         def build(p):
             shapes_box['s'] = self._describe(p, d, N, H, W)
-        plan = self._get_plan(key, x.device, build)
-        shapes = self._plans()[key + (self._precision(),)].setdefault('shapes', shapes_box.get('s'))
+        train = self._wants_grad(x)
+        plan = self._get_plan(key, x.device, build, train=train)
+        shapes = self._plans()[key + (('train',) if train else ()) + (self._precision(),)].setdefault('shapes', shapes_box.get('s'))
         outs = [torch.empty((N, c, h, w), device=x.device, dtype=torch.float32) for (c, h, w) in shapes]
         io = [x] + [o if (self.getIntermFeat or j == len(outs) - 1) else None for j, o in enumerate(outs)]
-        plan.run(io, self.use_cuda_graph)
-        return outs if self.getIntermFeat else [outs[-1]]
+        if not train:
+            plan.run(io, self.use_cuda_graph)
+            return outs if self.getIntermFeat else [outs[-1]]
+        out_slots = tuple(s for s in range(1, len(io)) if io[s] is not None)
+        params = [p for p in self._tower_params(d)]
+        res = _PlanFunction.apply(self, plan, io, (0,), out_slots, (0,), *([x] + params))
+        return list(res)
 
     def forward(self, input):
         from . import ops
@@ -670,7 +752,7 @@ class MultiscaleDiscriminator(_Planned):
         for i in range(self.num_D):
             result.append(self._tower_forward(self.num_D - 1 - i, x))
             if i != self.num_D - 1:
-                x = ops.avgpool3s2(x)
+                x = ops.avgpool3s2(x)            # autograd-aware (ops.AvgPool3s2Function) when x requires a gradient
         return result
 
 
@@ -720,5 +802,9 @@ class SequentialRunner(_Planned):
             last = plan.describe()['values'][-1]
             oc, oh, ow = last['C'], last['H'], last['W']
         out = torch.empty((N, oc, oh, ow), device=x.device, dtype=torch.float32)
-        plan.run([x, out], self.use_cuda_graph)
-        return out
+        if not self._wants_grad(x):
+            plan.run([x, out], self.use_cuda_graph)
+            return out
+        tplan = self._get_plan(key, x.device, lambda p: self._describe(p, N, C, H, W), train=True)
+        (res,) = _PlanFunction.apply(self, tplan, [x, out], (0,), (1,), (0,), *([x] + list(self.parameters())))
+        return res

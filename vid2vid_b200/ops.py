@@ -108,8 +108,7 @@ class ChannelNorm(nn.Module):
         return channelnorm(input1.contiguous(), self.norm_deg)
 
 
-def resample(image, flow, align_corners=False):
-    """BaseModel.resample / BaseNetwork.resample (base_model.py:189-196, networks.py:108-115)."""
+def _resample_fwd(image, flow, align_corners):
     image, flow = image.contiguous(), flow.contiguous()
     _chk(image, flow)
     b, c, h, w = image.shape
@@ -117,6 +116,34 @@ def resample(image, flow, align_corners=False):
     _ck(L.lib().v2v_resample_forward(_p(image), _p(flow), _p(out), b, c, h, w, int(align_corners),
                                          L.current_stream_ptr()))
     return out
+
+
+class ResampleFunction(torch.autograd.Function):
+    """resample with gradients wrt image and flow (the warp losses differentiate through it, vid2vid_model_D.py:123)."""
+
+    @staticmethod
+    def forward(ctx, image, flow, align_corners):
+        image, flow = image.detach().contiguous(), flow.detach().contiguous()
+        ctx.save_for_backward(image, flow)
+        ctx.ac = int(align_corners)
+        return _resample_fwd(image, flow, align_corners)
+
+    @staticmethod
+    def backward(ctx, g):
+        image, flow = ctx.saved_tensors
+        b, c, h, w = image.shape
+        g = g.contiguous()
+        gi = torch.zeros_like(image) if ctx.needs_input_grad[0] else None
+        gf = torch.empty_like(flow) if ctx.needs_input_grad[1] else None
+        _ck(L.lib().v2v_resample_backward(_p(image), _p(flow), _p(g), _p(gi), _p(gf), b, c, h, w, ctx.ac, L.current_stream_ptr()))
+        return gi, gf, None
+
+
+def resample(image, flow, align_corners=False):
+    """BaseModel.resample / BaseNetwork.resample (base_model.py:189-196, networks.py:108-115)."""
+    if torch.is_grad_enabled() and (image.requires_grad or flow.requires_grad):
+        return ResampleFunction.apply(image, flow, align_corners)
+    return _resample_fwd(image, flow, align_corners)
 
 
 def onehot_edges(label_map, inst_map, label_nc, use_instance):
@@ -132,8 +159,29 @@ def onehot_edges(label_map, inst_map, label_nc, use_instance):
     return out
 
 
+class AvgPool3s2Function(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = x.shape
+        return _avgpool3s2_fwd(x.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        h, w = ctx.shape[-2:]
+        g = g.contiguous()
+        gin = torch.empty(ctx.shape, device=g.device, dtype=torch.float32)
+        _ck(L.lib().v2v_avgpool3s2_backward(_p(g), _p(gin), gin.numel() // (h * w), h, w, L.current_stream_ptr()))
+        return gin
+
+
 def avgpool3s2(x):
-    """AvgPool2d(3, stride=2, padding=1, count_include_pad=False) over the last two dims."""
+    """AvgPool2d(3, stride=2, padding=1, count_include_pad=False) over the last two dims (autograd-aware)."""
+    if torch.is_grad_enabled() and x.requires_grad:
+        return AvgPool3s2Function.apply(x)
+    return _avgpool3s2_fwd(x)
+
+
+def _avgpool3s2_fwd(x):
     x = x.contiguous()
     _chk(x)
     h, w = x.shape[-2:]
@@ -152,3 +200,68 @@ def fg_mask(real_As, ts, fg_labels):
     arr = (C.c_int * len(fg_labels))(*fg_labels)
     _ck(L.lib().v2v_fg_mask(_p(real_As), _p(out), b, T, c, h, w, ts, arr, len(fg_labels), L.current_stream_ptr()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ training losses
+def _scalar_ws(dev):
+    return torch.zeros(1, device=dev, dtype=torch.float64), torch.empty(1, device=dev, dtype=torch.float32)
+
+
+class L1LossFunction(torch.autograd.Function):
+    """mean |a*m - b*m| (MaskedL1Loss, networks.py:804-812) / mean |a - b| (nn.L1Loss) with m = None; b may be None (= 0)."""
+
+    @staticmethod
+    def forward(ctx, a, b, mask):
+        a = a.detach().contiguous()
+        b = b.detach().contiguous() if b is not None else None
+        mask = mask.detach().contiguous() if mask is not None else None
+        _chk(a, b, mask)
+        a4 = a if a.dim() == 4 else a.reshape(-1, a.shape[-3], a.shape[-2], a.shape[-1])
+        ctx.dims = a4.shape
+        ws, out = _scalar_ws(a.device)
+        n, c, h, w = a4.shape
+        _ck(L.lib().v2v_l1_loss_forward(_p(a), _p(b), _p(mask), n, c, h, w, C.c_void_p(ws.data_ptr()), _p(out), L.current_stream_ptr()))
+        ctx.save_for_backward(a, b, mask)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b, mask = ctx.saved_tensors
+        n, c, h, w = ctx.dims
+        g = g.reshape(1).contiguous().float()
+        ga = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        gb = torch.empty_like(b) if (b is not None and ctx.needs_input_grad[1]) else None
+        if ga is None and gb is None:
+            return None, None, None
+        _ck(L.lib().v2v_l1_loss_backward(_p(a), _p(b), _p(mask), n, c, h, w, _p(g), _p(ga), _p(gb), L.current_stream_ptr()))
+        return ga, gb, None
+
+
+def l1_loss(a, b=None, mask=None):
+    return L1LossFunction.apply(a, b, mask)
+
+
+class MseConstFunction(torch.autograd.Function):
+    """mean (x - target)^2 against a constant label: GANLoss with use_lsgan (networks.py:764-774)."""
+
+    @staticmethod
+    def forward(ctx, x, target):
+        x = x.detach().contiguous()
+        _chk(x)
+        ctx.t = float(target)
+        ws, out = _scalar_ws(x.device)
+        _ck(L.lib().v2v_mse_const_forward(_p(x), x.numel(), ctx.t, C.c_void_p(ws.data_ptr()), _p(out), L.current_stream_ptr()))
+        ctx.save_for_backward(x)
+        return out.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (x,) = ctx.saved_tensors
+        g = g.reshape(1).contiguous().float()
+        gx = torch.empty_like(x)
+        _ck(L.lib().v2v_mse_const_backward(_p(x), x.numel(), ctx.t, _p(g), _p(gx), L.current_stream_ptr()))
+        return gx, None
+
+
+def mse_to_const(x, target):
+    return MseConstFunction.apply(x, target)

@@ -57,7 +57,7 @@ def norm_desc(m):
 
 
 class Plan:
-    def __init__(self, device=0, impl=None, precision='fast'):
+    def __init__(self, device=0, impl=None, precision='fast', train=False):
         if impl is None:
             impl = L.IMPL_SIMT if os.environ.get('V2V_CONV_IMPL') == 'simt' else L.IMPL_UMMA
         self._h = C.c_void_p()
@@ -65,6 +65,10 @@ class Plan:
         self.precision = precision
         L.check(L.lib().v2v_plan_create(device, impl, C.byref(self._h)))
         L.check(L.lib().v2v_plan_set_precision(self._h, {'fast': L.PREC_BF16, 'precise': L.PREC_BF16X3}[precision]))
+        self.train = bool(train)
+        if train:
+            L.check(L.lib().v2v_plan_set_training(self._h, 1))
+        self.run_id = 0
         self._keep = []
         self.finalized = False
         self.n_slots = 0
@@ -137,11 +141,11 @@ class Plan:
         self.n_slots = max(self.n_slots, slot + 1)
 
     def composite(self, s_raw, s_flow, s_weight, s_prev, prev_C, s_fg, s_mask, s_final, N, H, W, use_warp,
-                  align_corners):
-        L.check(L.lib().v2v_g_composite(self._h, s_raw, s_flow, s_weight, s_prev, prev_C, s_fg, s_mask, s_final, N, H,
-                                        W, int(use_warp), int(align_corners)))
+                  align_corners, s_raw_out=-1):
+        L.check(L.lib().v2v_g_composite_ex(self._h, s_raw, s_flow, s_weight, s_prev, prev_C, s_fg, s_mask, s_final, s_raw_out,
+                                           N, H, W, int(use_warp), int(align_corners)))
         self.n_slots = max(self.n_slots, s_raw + 1, s_flow + 1, s_weight + 1, s_prev + 1, s_fg + 1, s_mask + 1,
-                           s_final + 1)
+                           s_final + 1, s_raw_out + 1)
 
     # ---- execution
     def finalize(self):
@@ -151,18 +155,36 @@ class Plan:
     def repack(self):
         L.check(L.lib().v2v_plan_repack(self._h, L.current_stream_ptr()))
 
-    def run(self, io, use_graph=True):
-        """io: list indexed by slot of tensors (or None)."""
+    def _io_array(self, io):
         arr = (C.c_void_p * self.n_slots)()
         for i in range(self.n_slots):
             t = io[i] if i < len(io) else None
             arr[i] = t.data_ptr() if t is not None else None
+        return arr
+
+    def run(self, io, use_graph=True, recompute=False):
+        """io: list indexed by slot of tensors (or None).  recompute: eager re-execution before a backward, without the
+        running-statistics side effect."""
+        arr = self._io_array(io)
         # the first execution is eager (lazy module loading, attribute setup); graphs from the second on
-        g = int(use_graph and self._graph_ok)
+        g = 2 if recompute else int(use_graph and self._graph_ok)
         L.check(L.lib().v2v_plan_run(self._h, arr, self.n_slots, g, L.current_stream_ptr()))
         L.LAUNCHES[0] += self.num_kernels
-        self._graph_ok = True
+        if not recompute:
+            self._graph_ok = True
         self.last_io = io
+        self.run_id += 1
+
+    def backward(self, io, gio, params, grads):
+        """Backward of the last run: io = its forward tensors, gio[slot] = incoming gradient (outputs) / gradient destination
+        (inputs), params / grads = parameter tensors and the tensors their gradients are accumulated into."""
+        n = len(params)
+        pa, ga = (C.c_void_p * max(n, 1))(), (C.c_void_p * max(n, 1))()
+        for i, (p_, g_) in enumerate(zip(params, grads)):
+            pa[i], ga[i] = p_.data_ptr(), (g_.data_ptr() if g_ is not None else None)
+        L.check(L.lib().v2v_plan_backward(self._h, self._io_array(io), self._io_array(gio), self.n_slots, pa, ga, n,
+                                          L.current_stream_ptr()))
+        L.LAUNCHES[0] += 3 * self.num_kernels
 
     def profile(self, io=None):
         """Eager run with a CUDA event after every kernel -> list of (kind, ms, conv_macs)."""

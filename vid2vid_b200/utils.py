@@ -34,6 +34,8 @@ def make_opt(**kw):
         gan_mode='ls', continue_train=False, niter_fix_global=0, lr=0.0002,
         beta1=0.5, TTUR=False, max_frames_per_gpu=1, n_frames_total=30,
         max_frames_backpropagate=1,
+        # not a reference option: random-initialised networks (no checkpoints exist offline); False = the reference's behaviour
+        synthetic_weights=True,
     )
     for k, v in kw.items():
         setattr(opt, k, v)
