@@ -177,7 +177,7 @@ def test_generator_gradients_vs_oracle(name):
           enumerate((3, 2, 1, 3, c['ngf'], c['ngf'], c['ngf'] // 2 if c['nd'] > 2 else c['ngf']))]
     torch.set_default_dtype(torch.float64)
     try:
-        cd = [t.double().requires_grad_(True) if t is not None else None for t in coarse]
+        cd = [t.detach().clone().double().requires_grad_(True) if t is not None else None for t in coarse]
         if local:
             ref = GO.composite_local_generator(sd, inp.double(), img_prev.double(), mask.double(), *cd, False,
                                                n_blocks_local=c['n_blocks_local'], use_fg_model=c['fg'], scale=c['scale'])
@@ -189,7 +189,7 @@ def test_generator_gradients_vs_oracle(name):
         torch.set_default_dtype(torch.float32)
     # the fp32 noise floor of these gradients: the same oracle evaluated in fp32 against its fp64 evaluation
     sd32 = {k: v.detach().float().requires_grad_(v.requires_grad) for k, v in sd.items()}
-    c32 = [t.float().requires_grad_(True) if t is not None else None for t in coarse]
+    c32 = [t.detach().clone().float().requires_grad_(True) if t is not None else None for t in coarse]
     if local:
         r32 = GO.composite_local_generator(sd32, inp, img_prev, mask, *c32, False, n_blocks_local=c['n_blocks_local'],
                                            use_fg_model=c['fg'], scale=c['scale'])
@@ -202,7 +202,7 @@ def test_generator_gradients_vs_oracle(name):
     print('fp32-oracle vs fp64-oracle gradient rel L2: max %.2e median %.2e' % (max(floor.values()), sorted(floor.values())[len(floor) // 2]))
     net = net.cuda()
     net.precision = 'precise'
-    cg = [t.cuda().requires_grad_(True) if t is not None else None for t in coarse]
+    cg = [t.detach().clone().cuda().requires_grad_(True) if t is not None else None for t in coarse]
     out = net(inp.cuda(), img_prev.cuda(), mask.cuda(), *cg, False)
     sum(((o * g.cuda()).sum() for o, g in zip(out, gs) if o is not None)).backward()
     for key, o, r in zip(C.GEN_OUT_NAMES, out, ref):

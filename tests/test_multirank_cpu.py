@@ -65,5 +65,55 @@ def test_reference_arm_under_torchrun_rank0_only():
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
     assert d['impl'] == 'reference' and d['n_gpus'] == 2 and d['unit'] == 'frames/s' and d['higher_is_better'] is True
-    assert d['value'] > 0 and d['cpu_baseline']['kind'] == 'port' and d['cpu_baseline']['value'] == d['value']
+    assert d['value'] > 0 and d['cpu_baseline']['kind'] in ('reference', 'port') and d['cpu_baseline']['value'] == d['value']
     assert d['e2e'] == {'value': d['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}
+
+
+def _flat_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    import torch.nn as nn
+    from vid2vid_b200.trainer import FlatGrads
+    dist.init_process_group('gloo', init_method='tcp://127.0.0.1:%d' % port, rank=rank, world_size=world)
+    torch.manual_seed(0)
+    g = nn.Sequential(nn.Conv2d(3, 4, 3), nn.BatchNorm2d(4))
+    d = nn.Sequential(nn.Conv2d(4, 2, 3))
+    fg = FlatGrads([list(g.parameters()), list(d.parameters())])
+    x = torch.randn(2, 3, 8, 8, generator=torch.Generator().manual_seed(10 + rank))       # this rank's shard of the batch
+    loss = d(g(x)).pow(2).mean()
+    fg.zero()
+    loss.backward()
+    local = fg.flat.clone()
+    fg.all_reduce_mean(world)
+    q.put((rank, local, fg.flat.clone(), [p.grad.data_ptr() == fg.flat[o:].data_ptr() for p, o in
+                                          zip(list(g.parameters()) + list(d.parameters()), _offsets(list(g.parameters()) + list(d.parameters())))]))
+    dist.destroy_process_group()
+
+
+def _offsets(params):
+    off, out = 0, []
+    for p in params:
+        out.append(off)
+        off += p.numel()
+    return out
+
+
+def test_flat_gradient_all_reduce_world2_gloo():
+    """one flat [G | D | ...] gradient buffer, one all-reduce(SUM)/world per step: the result on every rank is the
+    mean of the per-rank gradients (= the gradient of the mean of the per-replica losses, train.py:65,78), and every
+    parameter's .grad stays a view into the flat buffer."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29731
+    procs = [ctx.Process(target=_flat_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+    (r0, l0, a0, v0), (r1, l1, a1, v1) = res
+    import torch
+    assert torch.allclose(a0, (l0 + l1) / 2, atol=1e-7) and torch.equal(a0, a1)
+    assert all(v0) and all(v1)
+    assert not torch.allclose(l0, l1)

@@ -270,6 +270,8 @@ class _PlanFunction(torch.autograd.Function):
                 gin.append(gio[s_])
             else:
                 gin.append(None)
+        if os.environ.get('V2V_DEBUG_AUTOGRAD'):
+            print('plan backward: in_slots', ctx.in_slots, 'needs', ctx.needs_input_grad[6:6 + ctx.n_in], 'gin', [g is not None for g in gin])
         pgrads = [torch.zeros_like(p) if ctx.needs_input_grad[6 + ctx.n_in + j] else None for j, p in enumerate(ctx.params)]
         plan.backward(io, gio, ctx.params, pgrads)
         return (None,) * 6 + tuple(gin) + tuple(pgrads)
