@@ -38,6 +38,11 @@ WORKLOADS = {
     'cfg4': dict(W=2048, H=1024, n_scales=3, ngf=128, desc='label2city 2048x1024 inference, n_scales_spatial=3 --fg --use_single_G'),
     'cfg2': dict(W=512, H=256, n_scales=1, ngf=128, desc='label2city 512x256 inference (use_single_G), n_scales_spatial=1 --fg'),
     'tiny': dict(W=256, H=128, n_scales=2, ngf=32, desc='plumbing: 256x128, 2 scales, ngf 32'),
+    # training steps (train.py:50-93): G + multiscale D + temporal D + FlowNet2 warp losses, one clip per GPU, one flat NCCL
+    # gradient all-reduce per step
+    'cfg3': dict(W=1024, H=512, n_scales=2, ngf=128, train=True,
+                 desc='label2city 1024x512 training step (G + multiscale D + FlowNet2 warp loss), batch-sharded, n_scales_spatial=2'),
+    'cfg3_small': dict(W=256, H=128, n_scales=2, ngf=32, train=True, desc='plumbing: 256x128 training step, ngf 32'),
 }
 
 
@@ -405,6 +410,10 @@ def cpu_frames_per_s(workload, steps, warm, budget_s=150.0):
 def run_reference(args, rank, world):
     if rank != 0:
         return
+    if WORKLOADS[args.workload].get('train'):
+        print(json.dumps({'impl': 'reference', 'unavailable': 'the CPU reference arm is defined for the headline inference workloads; '
+                          'the reference training step needs its CUDA-only FlowNet2 ops (see DESIGN.md)'}))
+        return
     K, Wm = args.steps, args.warmup
     r = cpu_frames_per_s(args.workload, steps=K, warm=min(Wm, 1), budget_s=180.0)
     wl = WORKLOADS[args.workload]
@@ -416,6 +425,111 @@ def run_reference(args, rank, world):
            'config': {'workload': wl['desc'], 'parallelism': 'host CPU, rank 0 only'},
            'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
            'e2e': {'value': r['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(out))
+
+
+# ----------------------------------------------------------------------------------------------- training step (cfg3)
+def run_train(args, rank, world, local_rank):
+    """BASELINE config 3: `python bench.py --workload cfg3 [--gpus N]`.  A step = one iteration of train.py's inner loop on one
+    clip per GPU (n_frames_load = 1 generated frame): generator forward (tcgen05, precise mode), FlowNet2 (no grad), image and
+    temporal discriminator losses, the three backward passes (hand-written fp32 SIMT backward kernels -- the first correct
+    CUDA path, not yet on tensor cores), ONE flat NCCL all-reduce over [G | D | D_T] and the Adam steps.  value = clips
+    (= generated frames) per second over all ranks; the all-reduce is timed separately with CUDA events."""
+    import torch
+    import torch.distributed as dist
+    from vid2vid_b200 import _lib as L
+    from vid2vid_b200 import flownet as FN
+    from vid2vid_b200.model_d import Vid2VidModelD
+    from vid2vid_b200.model_g import Vid2VidModelG
+    from vid2vid_b200.trainer import Trainer
+    from vid2vid_b200.utils import make_opt, synth_label_sequence
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    wl = WORKLOADS[args.workload]
+    H, Wd = wl['H'], wl['W']
+    opt = make_opt(label_nc=35, use_instance=True, fg=True, fg_labels=[26], n_scales_spatial=wl['n_scales'], ngf=wl['ngf'], num_D=3,
+                   n_scales_temporal=2, n_frames_D=3, isTrain=True, no_vgg=True, gpu_ids=[local_rank], n_frames_total=30,
+                   dataroot='datasets/Cityscapes/', loadSize=Wd)
+    torch.manual_seed(1234)                         # identical initial weights on every rank (DataParallel replicates rank 0's)
+    G = Vid2VidModelG().initialize(opt)
+    D = Vid2VidModelD().initialize(opt)
+    F = FN.FlowNet().initialize(opt)
+    tr = Trainer(opt, G, D, F, world=world)
+    K, Wm = args.steps, max(args.warmup, 3)
+    tG = opt.n_frames_G
+    T = K + Wm + tG + 2
+    A = synth_label_sequence(T, H, Wd, label_nc=35, block=64, seed=rank).pin_memory()
+    g = torch.Generator().manual_seed(77 + rank)
+    coarse = torch.rand(T, 3, H // 16, Wd // 16, generator=g) * 2 - 1
+    B = torch.nn.functional.interpolate(coarse, size=(H, Wd), mode='bilinear', align_corners=False).view(1, T, 3, H, Wd).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ar_ms = []
+    orig_ar = tr.grads.all_reduce_mean
+
+    def timed_ar(w):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig_ar(w)
+        e1.record()
+        ar_ms.append((e0, e1))
+    tr.grads.all_reduce_mean = timed_ar
+    t = 0
+    for _ in range(Wm):
+        a, b = A[:, t:t + tG].to(dev, non_blocking=True), B[:, t:t + tG].to(dev, non_blocking=True)
+        tr.step(a, b, a)
+        t += 1
+    barrier()
+    ar_ms.clear()
+    sampler.recording = True
+    l0 = L.LAUNCHES[0]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        a, b = A[:, t:t + tG].to(dev, non_blocking=True), B[:, t:t + tG].to(dev, non_blocking=True)     # H2D of the step's inputs
+        losses, _ = tr.step(a, b, a)                                                                  # float(loss) = D2H of the result
+        t += 1
+    e1.record()
+    barrier()
+    sampler.stop_flag = True
+    ms = e0.elapsed_time(e1)
+    launches = L.LAUNCHES[0] - l0
+    ar = sum(x.elapsed_time(y) for x, y in ar_ms) / max(len(ar_ms), 1)
+    ms, ar = reduce_times([ms, ar], world, dev)
+    if rank != 0:
+        return
+    gmacs = 0.0
+    for s in range(wl['n_scales']):
+        for key, ent in getattr(G, 'netG%d' % s)._plans().items():
+            if 'train' in key:
+                gmacs += ent['plan'].conv_macs
+    peak_burst, peak_sust, peak_gbs, peak_src = peaks()
+    step_ms = ms / K
+    fl = 3 * 2 * gmacs                    # forward + data gradient + weight gradient of every generator convolution
+    out = {'metric': 'training clips/sec (%s)' % args.workload, 'value': world * K / (ms * 1e-3), 'unit': 'clips/s', 'n_gpus': world, 'steps': K,
+           'warmup': Wm, 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+           'dtype': 'forward ' + DTYPE['precise'] + '; backward f32 (SIMT)',
+           'data': 'synthetic 35-label blocky clips + low-pass noise frames, random-init G / D / FlowNet2',
+           'config': {'workload': wl['desc'], 'parallelism': 'dp%d: one clip per GPU, per-rank BatchNorm statistics, ONE flat NCCL all-reduce '
+                      '(%.1f M fp32 gradients of [G | D | D_T0 | D_T1]) per step' % (world, tr.grads.numel / 1e6),
+                      'frames_per_step': 1, 'generator_conv_flops_fwd_bwd_per_step': fl},
+           'e2e': {'value': world * K / (ms * 1e-3), 'unit': 'clips/s', 'h2d_bytes_per_step': int(2 * tG * H * Wd * 4 + tG * 3 * H * Wd * 4),
+                   'd2h_bytes_per_step': 9 * 4, 'api': 'Trainer.step(host label / frame tensors) -> host loss values'},
+           'gpu_launches': launches, 'clocks': sampler.summary(),
+           'all_reduce': {'ms_per_step': ar, 'share_of_step': ar / step_ms, 'bytes': tr.grads.numel * 4,
+                          'algbw_gbs': tr.grads.numel * 4 / (ar * 1e-3) / 1e9 if ar > 0 else None, 'backend': 'nccl' if world > 1 else 'none (1 rank)'},
+           'roofline': {'bound': 'tensor', 'kernel': 'generator convolutions, forward (tcgen05) + backward (fp32 SIMT)', 'achieved': fl / (step_ms * 1e-3) / 1e12,
+                        'peak': peak_burst, 'unit': 'TFLOP/s', 'frac': fl / (step_ms * 1e-3) / 1e12 / peak_burst, 'peak_source': peak_src,
+                        'traffic': None, 'note': 'whole-step time as denominator (includes D, FlowNet2, losses, optimizer); the backward '
+                        'kernels are the first correct CUDA path and run on CUDA cores'},
+           'last_losses': losses}
     print(json.dumps(out))
 
 
@@ -440,7 +554,10 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-    run_ours(args, rank, world, local_rank)
+    if WORKLOADS[args.workload].get('train'):
+        run_train(args, rank, world, local_rank)
+    else:
+        run_ours(args, rank, world, local_rank)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

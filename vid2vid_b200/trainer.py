@@ -149,4 +149,4 @@ class Trainer:
         D.optimizer_D.step()
         for s in range(len(loss_D_T)):
             getattr(D, 'optimizer_D_T' + str(s)).step()
-        return {k: float(v) for k, v in loss_dict.items()}, [{k: float(v) for k, v in d.items()} for d in loss_dict_T]
+        return {k: float(v.detach()) for k, v in loss_dict.items()}, [{k: float(v.detach()) for k, v in d.items()} for d in loss_dict_T]
