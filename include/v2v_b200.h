@@ -190,6 +190,12 @@ int v2v_plan_set_precision(v2v_plan* plan, int precision);
 
 /* Channels [c_off, c_off + C) of the fp32 NCHW tensor (N, C_src, H, W) bound to IO slot `slot`. */
 int v2v_g_input(v2v_plan* plan, int slot, int N, int C_src, int c_off, int C, int H, int W, int* value_out);
+/* As v2v_g_input with flags.  V2V_INPUT_EXACT_BF16: the caller promises that every element of the window is exactly
+ * representable in bf16 (one-hot label maps, 0/1 edge maps -- what encode_input produces at full resolution,
+ * models/vid2vid_model_G.py:93-105): precise plans then skip the all-zero lo half of that operand (2 MMAs per K block, no
+ * change in results). */
+#define V2V_INPUT_EXACT_BF16 1
+int v2v_g_input_ex(v2v_plan* plan, int slot, int N, int C_src, int c_off, int C, int H, int W, int flags, int* value_out);
 /* Convolution of a value; result is a raw (pre-norm) tensor. */
 int v2v_g_conv(v2v_plan* plan, int value_in, const v2v_conv_desc* conv, int* raw_out);
 /* value = act(norm(raw)) + add0 + add1   (add ids may be -1).  Conv bias is folded into running_mean only.

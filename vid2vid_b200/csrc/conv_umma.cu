@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include "ptx.cuh"
 #include "v2v_internal.h"
+#include "finalize.cuh"
 
 namespace v2v {
 
@@ -143,7 +144,7 @@ __device__ __forceinline__ void mma_role(const ConvKernelParams& p, const MmaCtx
   const uint32_t a_step = (uint32_t)(p.row_bytes >> 4), b_step = (uint32_t)(cx.b_tx >> 4);
   const uint32_t a_wrap = (uint32_t)(((p.PW - p.RW) * p.row_bytes) >> 4);     // to the next patch row
   const uint32_t sBres_u32 = smem_u32(cx.sBres);
-  const int npass = p.split ? 3 : 1;
+  const int ps_step = p.split ? (p.a_exact ? 2 : 1) : 3;
   const uint32_t a_half16 = (uint32_t)(p.a_half_bytes >> 4), b_half16 = (uint32_t)(p.b_half_bytes >> 4);
   // descriptors differ only in the 14-bit (address >> 4) field of the low word
   const uint32_t a_hi = (uint32_t)(make_kmajor_desc(0, p.sbo_a_bytes, p.layout_type) >> 32);
@@ -188,7 +189,7 @@ __device__ __forceinline__ void mma_role(const ConvKernelParams& p, const MmaCtx
           // cycles per MMA for small-N layers, every instruction in the loop body counts.
           // precise plans: npass = 3 accumulates A_hi*B_hi + A_lo*B_hi + A_hi*B_lo (the lo halves sit a_half / b_half
           // bytes further in the same slots)
-          for (int ps = 0; ps < npass; ++ps) {
+          for (int ps = 0; ps < 3; ps += ps_step) {          // ps_step: 3 = one pass (fast), 1 = three passes, 2 = {hi*hi, hi*lo}
             const uint32_t alp = al + (ps == 1 ? a_half16 : 0u), blp = bl + (ps == 2 ? b_half16 : 0u);
             if (p.kmma == 4) issue_taps<kWarpWide, 4>(p, tmem_d, alp, blp, a_hi, b_hi, idesc, first, a_step, b_step, a_wrap);
             else if (p.kmma == 2) issue_taps<kWarpWide, 2>(p, tmem_d, alp, blp, a_hi, b_hi, idesc, first, a_step, b_step, a_wrap);
@@ -268,7 +269,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int gs = 0;
       uint32_t gpar = 0, gen = 0;
       int prev_key = -1;
-      const int nhalf = p.split ? 2 : 1;
+      const int nhalf = p.split ? 2 : 1;                       // weight halves
+      const int nhalfA = (p.split && !p.a_exact) ? 2 : 1;      // activation halves (an exact-in-bf16 input has no lo half)
       UnitIter un;
       un.init(p, t_first, t_step);
       for (int pit = 0; un.valid(p); un.next(p), ++pit) {
@@ -294,11 +296,11 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int n = min(p.CG, nsteps - s0);
           uint8_t* base = sG + (size_t)gs * group_bytes;
           mbar_wait(&g_empty[gs], gpar ^ 1);
-          mbar_expect_tx(&g_full[gs], (uint32_t)n * nhalf * (p.MG * a_tx + (p.b_resident ? 0 : p.R * b_tx)));
+          mbar_expect_tx(&g_full[gs], (uint32_t)n * (nhalfA * p.MG * a_tx + (p.b_resident ? 0 : nhalf * p.R * b_tx)));
           for (int i = 0; i < n; ++i) {
             const ConvGroup grp = p.groups[g];
             for (int j = 0; j < p.MG; ++j)
-              for (int hf = 0; hf < nhalf; ++hf)      // lo half: channels [Cp, 2 Cp) of the pixel
+              for (int hf = 0; hf < nhalfA; ++hf)     // lo half: channels [Cp, 2 Cp) of the pixel
                 tma_load_5d(base + (size_t)(i * p.MG + j) * p.a_slot_bytes + (size_t)hf * p.a_half_bytes, &tmA, &g_full[gs],
                             hf * p.Cp + cb * p.kc, x0 + j * p.TW + grp.dx, y0 + grp.dy, grp.plane, un.img);
             if (!p.b_resident) {
@@ -523,8 +525,24 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 
   tcgen05_fence_before();
+  __threadfence();                                  // this thread's statistics atomics are visible device-wide
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+  if (p.n_fin > 0) {
+    // Fused statistics finalisation.  All CTAs of this launch are co-resident (persistent grid <= SM count, one CTA per
+    // SM), so a grid-wide arrive-and-spin on a counter that the plan zeroes before every run is safe; afterwards CTA b
+    // finalises channels b, b + grid, ... (one warp per channel) of each attached norm slice.
+    if (threadIdx.x == 0) {
+      atomicAdd(p.fin_counter, 1u);
+      while (*reinterpret_cast<volatile unsigned int*>(p.fin_counter) < gridDim.x) __nanosleep(64);
+      __threadfence();
+    }
+    __syncthreads();
+    const int nwarps = blockDim.x >> 5;
+    for (int f = 0; f < p.n_fin; ++f)
+      for (int c = blockIdx.x + warp * gridDim.x; c < p.fin[f].C; c += nwarps * gridDim.x)
+        finalize_channel<true>(p.fin[f], c, lane);
+  }
   if ((p.dbg & 4) && blockIdx.x == 0 && threadIdx.x == 0) {
     const long long t0 = g_trace[0][0][0];
     for (int it = 0; it < 24; ++it)

@@ -10,79 +10,23 @@
 #include <cstdlib>
 #include "ptx.cuh"
 #include "v2v_internal.h"
+#include "finalize.cuh"
 
 namespace v2v {
 
-__device__ __forceinline__ double warp_sum_d(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// One warp per channel (4 channels per block): lanes stride the per-CTA partial rows, fp64 shuffle reduction.
+// One warp per channel (4 channels per block): see finalize.cuh.
 __global__ void __launch_bounds__(128) stats_finalize_kernel(FinalizeParams p) {
   pdl_prologue();
   const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (c >= p.C) return;
-  const int rows_img = p.num_phases * p.tiles_per_img;
-  double bs = 0.0, bq = 0.0, rm_acc = 0.0, rv_acc = 0.0;
-  for (int n = 0; n < p.N; ++n) {
-    double s = 0.0, q = 0.0;
-    for (int i = lane; i < rows_img; i += 32) {
-      const int ph = i / p.tiles_per_img, t = i - ph * p.tiles_per_img;
-      const size_t row = (size_t)ph * p.N * p.tiles_per_img + (size_t)n * p.tiles_per_img + t;
-      s += (double)p.stats[(row * 2 + 0) * p.Cs + p.c_off + c];
-      q += (double)p.stats[(row * 2 + 1) * p.Cs + p.c_off + c];
-    }
-    s = warp_sum_d(s); q = warp_sum_d(q);
-    if (p.instance) {
-      const double mean = s / p.count;
-      double var = q / p.count - mean * mean;
-      if (var < 0) var = 0;
-      if (lane == 0) {
-        const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
-        const float sc = g * (float)(1.0 / sqrt(var + (double)p.eps));
-        p.scale[(size_t)n * p.scale_stride + p.c_off + c] = sc;
-        p.shift[(size_t)n * p.scale_stride + p.c_off + c] = b - (float)mean * sc;
-        if (p.mean_out) {
-          p.mean_out[(size_t)n * p.scale_stride + p.c_off + c] = (float)mean;
-          p.rstd_out[(size_t)n * p.scale_stride + p.c_off + c] = (float)(1.0 / sqrt(var + (double)p.eps));
-        }
-      }
-      rm_acc += mean;
-      rv_acc += var * (p.count / (p.count > 1 ? p.count - 1 : 1));
-    } else {
-      bs += s; bq += q;
-    }
-  }
-  if (lane != 0) return;
-  double mean_run, var_run;
-  if (p.instance) {
-    mean_run = rm_acc / p.N; var_run = rv_acc / p.N;
-  } else {
-    const double cnt = p.count * p.N;
-    const double mean = bs / cnt;
-    double var = bq / cnt - mean * mean;
-    if (var < 0) var = 0;
-    const float g = p.gamma ? p.gamma[c] : 1.f, b = p.beta ? p.beta[c] : 0.f;
-    const float sc = g * (float)(1.0 / sqrt(var + (double)p.eps));
-    for (int n = 0; n < p.N; ++n) {
-      p.scale[(size_t)n * p.scale_stride + p.c_off + c] = sc;
-      p.shift[(size_t)n * p.scale_stride + p.c_off + c] = b - (float)mean * sc;
-      if (p.mean_out) {
-        p.mean_out[(size_t)n * p.scale_stride + p.c_off + c] = (float)mean;
-        p.rstd_out[(size_t)n * p.scale_stride + p.c_off + c] = (float)(1.0 / sqrt(var + (double)p.eps));
-      }
-    }
-    mean_run = mean; var_run = var * (cnt / (cnt > 1 ? cnt - 1 : 1));
-  }
-  if (p.running_mean) {   // train-mode side effect of nn.BatchNorm2d / InstanceNorm2d(track_running_stats)
-    const float bias = p.conv_bias ? p.conv_bias[c] : 0.f;
-    p.running_mean[c] = (1.f - p.momentum) * p.running_mean[c] + p.momentum * ((float)mean_run + bias);
-    p.running_var[c] = (1.f - p.momentum) * p.running_var[c] + p.momentum * (float)var_run;
-    if (c == 0 && p.num_batches_tracked) *p.num_batches_tracked += 1;
-  }
+  finalize_channel<false>(p, c, lane);
+}
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {   // nn.ReflectionPad2d index map
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
 }
 
 __device__ __forceinline__ void bf16x8_to_float(const uint4& r, float (&f)[8]) {
@@ -96,11 +40,6 @@ __device__ __forceinline__ void bf16x8_add(const uint4& r, float (&f)[8]) {
   for (int j = 0; j < 4; ++j) { float2 a = __bfloat1622float2(rp[j]); f[2 * j] += a.x; f[2 * j + 1] += a.y; }
 }
 
-__device__ __forceinline__ int reflect_idx(int i, int n) {   // nn.ReflectionPad2d index map
-  if (i < 0) i = -i;
-  if (i >= n) i = 2 * (n - 1) - i;
-  return i;
-}
 
 // Grid-stride over (padded pixel, 8-channel vector) items (2-D-grid and multi-item-per-thread variants measured slower).
 // 32-bit index arithmetic throughout: with 64-bit div/mod this kernel was instruction bound (~4 x 100-instruction

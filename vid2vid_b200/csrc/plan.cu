@@ -218,6 +218,7 @@ struct Value {
   bool interior_use = false;
   float* gval = nullptr;     // training plans: gradient of the value, dense NHWC fp32 [N][H][W][C]
   int input_slot = -1;       // >= 0: the value is an import of that IO slot (data gradient only on request)
+  bool exact_bf16 = false;   // caller promise: every element is exactly representable in bf16 (one-hot labels, edge maps)
 };
 struct Raw {
   int N, H, W, C;
@@ -438,6 +439,7 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   kp.MG = 1;
   const int sp = P->sp();
   kp.split = P->precise;
+  kp.a_exact = (P->precise && vin.exact_bf16) ? 1 : 0;
   const bool p2d = g.patch2d_kc > 0;
   if (p2d) { kp.kc = g.patch2d_kc; if (op.kind != G_HEAD) kp.BN = g.patch2d_bn; }
   const int m_tiles = kp.N * kp.tiles_x * kp.tiles_y;
@@ -539,7 +541,7 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
     const int avail = budget - (kp.b_resident ? nB * kp.b_slot_bytes : 0);
     const int nslots = std::max(2, avail / slot);
     const int steps = max_phase_groups * kp.cblocks;
-    const int est = (kp.split ? 3 : 1) * kp.MG * g.R * kp.kmma * std::max(40, kp.BN / 2);
+    const int est = (kp.split ? (kp.a_exact ? 2 : 3) : 1) * kp.MG * g.R * kp.kmma * std::max(40, kp.BN / 2);
     int cg;
     if (steps * est <= 6000 && 2 * steps <= nslots) cg = steps;           // one group per tile, double buffered
     else {
@@ -817,6 +819,13 @@ static int new_value(v2v_plan* p, int N, int H, int W, int C) {
   return (int)p->values.size() - 1;
 }
 
+int v2v_g_input_ex(v2v_plan* p, int slot, int N, int C_src, int c_off, int C, int H, int W, int flags, int* value_out) {
+  int rc = v2v_g_input(p, slot, N, C_src, c_off, C, H, W, value_out);
+  if (rc) return rc;
+  p->values[*value_out].exact_bf16 = (flags & V2V_INPUT_EXACT_BF16) != 0;
+  return 0;
+}
+
 int v2v_g_input(v2v_plan* p, int slot, int N, int C_src, int c_off, int C, int H, int W, int* value_out) {
   V2V_REQUIRE(p && !p->lowered && value_out, V2V_ERR_STATE, "plan already lowered or null");
   V2V_REQUIRE(slot >= 0 && N > 0 && C > 0 && c_off >= 0 && c_off + C <= C_src && H > 0 && W > 0, V2V_ERR_INVALID,
@@ -1015,7 +1024,7 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
   // (a CTA only writes the (phase, image) rows it actually worked on)
   const size_t stats_begin = off;
   for (size_t i = 0; i < P->raws.size(); ++i)
-    if (P->raws[i].conv_op >= 0) raw_off[i].stats = take((size_t)P->raws[i].stats_rows * 2 * P->raws[i].C * sizeof(float));
+    if (P->raws[i].conv_op >= 0) raw_off[i].stats = take((size_t)P->raws[i].stats_rows * 2 * P->raws[i].C * sizeof(float) + 64);   // + grid-barrier counter
   const size_t stats_end = off;
   P->arena_bytes = off;
   V2V_CUDA(cudaMalloc(&P->arena, P->arena_bytes));
@@ -1119,7 +1128,23 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
           // fusing the finalize into the apply prologue measured slower than the separate launch: opt-in only
           { const char* ef = getenv("V2V_FUSE_FINALIZE"); fuse_fin = (ef && ef[0] == '1') && r.N <= 8; }
           fin_params = fp;
-          if (!fuse_fin) P->xops.push_back(f);
+          // Default: the finalisation runs in the tail of the producing tcgen05 conv launch (grid barrier, see conv_umma.cu).
+          // A slice normalised more than once (defer_last emits two normalise passes of the same raw) is finalised -- and
+          // its running statistics updated -- once.  V2V_FUSED_FIN=0 restores one stats_finalize launch per normalise pass.
+          static const bool tail_ok = [] { const char* e = getenv("V2V_FUSED_FIN"); return !(e && e[0] == '0'); }();
+          GOp& prod = P->gops[r.conv_op];
+          bool in_tail = false;
+          if (tail_ok && !fuse_fin && P->impl == V2V_IMPL_UMMA) {
+            for (int q = 0; q < prod.kp.n_fin; ++q)
+              if (prod.kp.fin[q].c_off == fp.c_off && prod.kp.fin[q].gamma == fp.gamma && prod.kp.fin[q].running_mean == fp.running_mean) in_tail = true;
+            if (!in_tail && prod.kp.n_fin < 2) {
+              prod.kp.fin[prod.kp.n_fin++] = fp;
+              prod.kp.fin_counter = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(r.stats) +
+                                                                    (size_t)r.stats_rows * 2 * r.C * sizeof(float));
+              in_tail = true;
+            }
+          }
+          if (!fuse_fin && !in_tail) P->xops.push_back(f);
         } else if (cop.conv.bias != nullptr) {
           // norm-less biased conv (FlowNet2's conv / deconv / predict_flow units): the normalise pass runs with scale 1 and
           // shift = bias, written here and after every repack
@@ -1223,6 +1248,11 @@ int v2v_plan_run(v2v_plan* P, void* const* io_ptrs, int n_io, int use_graph, v2v
       if (x.kind == X_FINALIZE) {
         XOp y = x; y.fin.running_mean = nullptr; y.fin.running_var = nullptr; y.fin.num_batches_tracked = nullptr;
         int rc = run_xop(P, y, stream); if (rc) return rc;
+      } else if (x.kind == X_CONV && P->impl == V2V_IMPL_UMMA && P->gops[x.gop].kp.n_fin > 0) {
+        const GOp& op = P->gops[x.gop];
+        ConvKernelParams kp = op.kp;
+        for (int q = 0; q < kp.n_fin; ++q) { kp.fin[q].running_mean = nullptr; kp.fin[q].running_var = nullptr; kp.fin[q].num_batches_tracked = nullptr; }
+        V2V_CUDA(launch_conv_umma(op.tmA, op.tmB, kp, stream));
       } else { int rc = run_xop(P, x, stream); if (rc) return rc; }
     }
     return 0;

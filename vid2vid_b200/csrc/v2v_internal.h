@@ -72,6 +72,26 @@ struct ConvPhase {
   int oy_add, ox_add;           // output coordinate offset (transposed-conv sub-pixel phase)
 };
 
+struct FinalizeParams {
+  const float* stats;      // [rows][2][Cs]
+  int Cs, C;               // stats channel stride, channels
+  int N, tiles_per_img, num_phases;
+  double count;            // elements per channel per image
+  int instance;            // 0 = batch statistics over N, 1 = per-image statistics
+  const float* gamma;      // may be null (-> 1)
+  const float* beta;       // may be null (-> 0)
+  const float* conv_bias;  // folded into running_mean only (cancels in the normalised output)
+  float* running_mean;     // may be null
+  float* running_var;
+  long long* num_batches_tracked;
+  float momentum, eps;
+  float* scale;            // [N][scale_stride], written at column c_off + c
+  float* shift;
+  float* mean_out;         // training plans: batch / instance mean and 1/sqrt(var + eps), same indexing; may be null
+  float* rstd_out;
+  int c_off, scale_stride; // channel slice of the raw tensor this norm layer covers
+};
+
 struct ConvKernelParams {
   // problem
   int N, tiles_x, tiles_y, TH, TW;   // M tile = TH x TW output-grid pixels (TH*TW == 128)
@@ -93,6 +113,13 @@ struct ConvKernelParams {
   int a_half_bytes, b_half_bytes;    // byte offset of the lo half inside an A / B slot
   int Khalf;                         // taps * Cp: column offset of the lo half in the packed weight matrix
   int out_f32;                       // EPI_RAW_STATS: raw output element type (1 = fp32)
+  int a_exact;                       // precise plans: the input values are exact in bf16 (one-hot labels, edge maps): the lo
+                                     // half of A is all zero, so it is neither fetched nor multiplied (2 MMAs per K block)
+  // fused statistics finalisation: after its last tile every CTA arrives on a grid-wide counter; once all have, CTA b
+  // finalises channels b, b + grid, ... of up to two norm slices (no separate stats_finalize launches)
+  int n_fin;
+  FinalizeParams fin[2];
+  unsigned int* fin_counter;
   ConvPhase phases[V2V_MAX_PHASES];
   ConvGroup groups[V2V_MAX_TAPS];
   // epilogue
@@ -128,25 +155,6 @@ cudaError_t launch_conv_simt(const ActDesc& in, const bf16* wpacked, int Ktotal,
 
 
 // ---------------------------------------------------------------------------------------
-struct FinalizeParams {
-  const float* stats;      // [rows][2][Cs]
-  int Cs, C;               // stats channel stride, channels
-  int N, tiles_per_img, num_phases;
-  double count;            // elements per channel per image
-  int instance;            // 0 = batch statistics over N, 1 = per-image statistics
-  const float* gamma;      // may be null (-> 1)
-  const float* beta;       // may be null (-> 0)
-  const float* conv_bias;  // folded into running_mean only (cancels in the normalised output)
-  float* running_mean;     // may be null
-  float* running_var;
-  long long* num_batches_tracked;
-  float momentum, eps;
-  float* scale;            // [N][scale_stride], written at column c_off + c
-  float* shift;
-  float* mean_out;         // training plans: batch / instance mean and 1/sqrt(var + eps), same indexing; may be null
-  float* rstd_out;
-  int c_off, scale_stride; // channel slice of the raw tensor this norm layer covers
-};
 
 struct ApplyParams {
   RawDesc raw;

@@ -30,6 +30,9 @@ class Vid2VidModelG(nn.Module):
         self.device_ = dev
         for s in range(self.n_scales):
             setattr(self, 'netG' + str(s), networks.build_netG(opt, s).to(dev))
+        # the finest scale reads encode_input's one-hot + edge map at full resolution: exact in bf16 (coarser pyramid levels
+        # are avg-pooled, pose inputs are real-valued: not exact)
+        getattr(self, 'netG' + str(self.n_scales - 1)).input_exact_bf16 = bool(opt.label_nc != 0)
         # vid2vid_model_G.py:46-51: checkpoints are loaded whenever not training (or continuing / pre-training); a missing G0
         # is an error there (base_model.py:63-72).  opt.synthetic_weights (benchmarks / tests, no checkpoints offline) skips it.
         if (not self.isTrain or getattr(opt, 'continue_train', False) or getattr(opt, 'load_pretrain', '')) and \

@@ -404,9 +404,12 @@ class CompositeGenerator(_Planned):
 
     flow_multiplier = 20.0
     fuse_stems = True      # run model_down_seg.1 and indv_down.1 (same input, same 7x7 geometry) as one convolution
+    # Set by Vid2VidModelG for the finest scale: `input` is encode_input's full-resolution one-hot + edge map (exact in
+    # bf16), so precise plans need no lo half for it.  Leave False for arbitrary inputs (pose maps, pooled pyramid levels).
+    input_exact_bf16 = False
 
     def _describe(self, plan, N, H, W, use_raw_only=False):
-        v_in = plan.input(S_IN, N, self.input_nc, 0, self.input_nc, H, W)
+        v_in = plan.input(S_IN, N, self.input_nc, 0, self.input_nc, H, W, exact_bf16=self.input_exact_bf16)
         v_prev = plan.input(S_PREV, N, self.prev_output_nc, 0, self.prev_output_nc, H, W)
         fg0 = None
         if self.use_fg_model and self.fuse_stems and _can_pair(self.model_down_seg, self.indv_down):
@@ -449,7 +452,7 @@ class CompositeGenerator(_Planned):
         if self.output_nc != 3:
             raise NotImplementedError('the fused composite kernel handles 3 output channels')
         train = self._wants_grad(input, img_prev, *coarse)
-        plan = self._get_plan(key + (N, H, W, bool(use_raw_only), bool(self.align_corners)), input.device,
+        plan = self._get_plan(key + (N, H, W, bool(use_raw_only), bool(self.align_corners), bool(self.input_exact_bf16)), input.device,
                               lambda p: self._describe(p, N, H, W, use_raw_only), train=train)
         new = lambda c: torch.empty((N, c, H, W), device=input.device, dtype=torch.float32)
         io = [None] * 15
@@ -518,7 +521,7 @@ class CompositeLocalGenerator(CompositeGenerator):
     def _describe(self, plan, N, H, W, use_raw_only=False):
         h2, w2 = H // 2, W // 2
         c2 = self.model_down_seg[4].out_channels
-        v_in = plan.input(S_IN, N, self.input_nc, 0, self.input_nc, H, W)
+        v_in = plan.input(S_IN, N, self.input_nc, 0, self.input_nc, H, W, exact_bf16=self.input_exact_bf16)
         v_prev = plan.input(S_PREV, N, self.prev_output_nc, 0, self.prev_output_nc, H, W)
         ci = plan.input(S_CI, N, c2, 0, c2, h2, w2)
         fg0 = None

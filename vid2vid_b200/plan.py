@@ -83,9 +83,9 @@ class Plan:
             pass
 
     # ---- description
-    def input(self, slot, N, C_src, c_off, Cn, H, W):
+    def input(self, slot, N, C_src, c_off, Cn, H, W, exact_bf16=False):
         v = C.c_int()
-        L.check(L.lib().v2v_g_input(self._h, slot, N, C_src, c_off, Cn, H, W, C.byref(v)))
+        L.check(L.lib().v2v_g_input_ex(self._h, slot, N, C_src, c_off, Cn, H, W, 1 if exact_bf16 else 0, C.byref(v)))
         self.n_slots = max(self.n_slots, slot + 1)
         return v.value
 
