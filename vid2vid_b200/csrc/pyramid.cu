@@ -61,6 +61,34 @@ __global__ void __launch_bounds__(256) avgpool3s2_kernel(const float* __restrict
   }
 }
 
+// W % 4 == 0: a thread produces two adjacent outputs from one 16-byte load (+ one scalar) per input row: 3x fewer load
+// instructions and twice the bytes in flight per thread (the scalar kernel above ran at 47 % of the copy rate, latency bound:
+// profiles/r02_hbm_ops_ncu.txt).  Same summation order -> same results.
+__global__ void __launch_bounds__(128) avgpool3s2_vec_kernel(const float* __restrict__ in, float* __restrict__ out, int P, int H, int W,
+                                                             int Ho, int Wo) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;      // output pair index: outputs 2k, 2k + 1 read input columns 4k-1 .. 4k+3
+  if (4 * k >= W) return;
+  const int yo = blockIdx.y;
+  for (int pl = blockIdx.z; pl < P; pl += gridDim.z) {
+    const float* ip = in + (size_t)pl * H * W;
+    float s0 = 0.f, s1 = 0.f;
+    int rows = 0;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy) {
+      const int y = 2 * yo + dy;
+      if (y < 0 || y >= H) continue;
+      ++rows;
+      const float* rp = ip + (size_t)y * W + 4 * k;
+      const float4 v = *reinterpret_cast<const float4*>(rp);
+      if (k > 0) s0 += __ldg(rp - 1);
+      s0 += v.x; s0 += v.y;
+      s1 += v.y; s1 += v.z; s1 += v.w;
+    }
+    const int c0 = (k > 0 ? 3 : 2), c1 = 3;                  // 4k + 3 <= W - 1 always when W % 4 == 0
+    *reinterpret_cast<float2*>(out + ((size_t)pl * Ho + yo) * Wo + 2 * k) = make_float2(s0 / (float)(rows * c0), s1 / (float)(rows * c1));
+  }
+}
+
 // real_A (B, T, C, H, W) -> mask (B, 1, H, W) for frame index t
 struct FgLabels { int v[16]; };
 __global__ void fg_mask_kernel(const float* __restrict__ real_A, float* __restrict__ mask, int B, int T, int C, int H,
@@ -114,6 +142,11 @@ cudaError_t launch_onehot_edges(const float* labels, const float* inst, float* o
 }
 cudaError_t launch_avgpool3s2(const float* in, float* out, int P, int H, int W, cudaStream_t s) {
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  if (W % 4 == 0 && W >= 4) {
+    dim3 grid((W / 4 + 127) / 128, Ho, P < 64 ? P : 64);
+    avgpool3s2_vec_kernel<<<grid, 128, 0, s>>>(in, out, P, H, W, Ho, Wo);
+    return cudaGetLastError();
+  }
   dim3 grid((Wo + 255) / 256, Ho, P < 64 ? P : 64);
   avgpool3s2_kernel<<<grid, 256, 0, s>>>(in, out, P, H, W, Ho, Wo);
   return cudaGetLastError();

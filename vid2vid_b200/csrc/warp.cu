@@ -7,6 +7,7 @@
 // The reference omits align_corners (PyTorch 0.4 == True, installed torch == False):
 // the flag is explicit.  Coordinate arithmetic mirrors get_grid (networks.py:79-93: torch.linspace)
 // and ATen's grid_sampler unnormalise / clip so results agree with the oracle to ~1e-6.
+#include <cstdlib>
 #include "ptx.cuh"
 #include "v2v_internal.h"
 
@@ -96,6 +97,63 @@ __global__ void composite_kernel(CompositeParams p) {
   }
 }
 
+// Vectorised form (W % 4 == 0): a thread owns 4 consecutive pixels of one row, so every streamed tensor moves as 16-byte
+// loads / stores with no per-pixel index division (grid = x blocks, rows, images); the warp gathers stay scalar (they hit
+// L2: neighbouring pixels sample neighbouring texels).  Same per-pixel arithmetic as composite_kernel -> identical results.
+__global__ void __launch_bounds__(128) composite_vec4_kernel(CompositeParams p) {
+  pdl_prologue();
+  const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y, n = blockIdx.z;
+  if (x0 >= p.W) return;
+  const size_t HW = (size_t)p.H * p.W, pix = (size_t)y * p.W + x0;
+  float* raw = reinterpret_cast<float*>(p.io[p.s_raw]);
+  float* fin = reinterpret_cast<float*>(p.io[p.s_final]);
+  float* raw_out = p.s_raw_out >= 0 ? reinterpret_cast<float*>(p.io[p.s_raw_out]) : raw;
+  const float* fg = p.s_fg >= 0 ? reinterpret_cast<const float*>(p.io[p.s_fg]) : nullptr;
+  auto ld4 = [&](const float* base, int c, int C) { return *reinterpret_cast<const float4*>(base + ((size_t)n * C + c) * HW + pix); };
+  float4 r[3], f[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) r[c] = ld4(raw, c, 3);
+  if (p.use_warp) {
+    const float* flow = reinterpret_cast<const float*>(p.io[p.s_flow]);
+    const float* prev = reinterpret_cast<const float*>(p.io[p.s_prev]);
+    const float4 fx = ld4(flow, 0, 2), fy = ld4(flow, 1, 2);
+    const float4 w = ld4(reinterpret_cast<const float*>(p.io[p.s_weight]), 0, 1);
+    const float fxs[4] = {fx.x, fx.y, fx.z, fx.w}, fys[4] = {fy.x, fy.y, fy.z, fy.w}, ws[4] = {w.x, w.y, w.z, w.w};
+    float o[3][4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const Bilerp b = warp_coords(x0 + j, y, fxs[j], fys[j], p.W, p.H, p.align_corners);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float wv = bilerp(prev + ((size_t)n * p.prev_C + (p.prev_C - 3) + c) * HW, b, p.W);
+        const float rc = reinterpret_cast<const float*>(&r[c])[j];
+        o[c][j] = rc * ws[j] + wv * (1.f - ws[j]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) f[c] = make_float4(o[c][0], o[c][1], o[c][2], o[c][3]);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) f[c] = r[c];
+  }
+  if (fg) {
+    const float4 m = ld4(reinterpret_cast<const float*>(p.io[p.s_mask]), 0, 1);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float4 g = ld4(fg, c, 3);
+      f[c] = make_float4(g.x * m.x + f[c].x * (1.f - m.x), g.y * m.y + f[c].y * (1.f - m.y), g.z * m.z + f[c].z * (1.f - m.z),
+                         g.w * m.w + f[c].w * (1.f - m.w));
+      r[c] = make_float4(g.x * m.x + r[c].x * (1.f - m.x), g.y * m.y + r[c].y * (1.f - m.y), g.z * m.z + r[c].z * (1.f - m.z),
+                         g.w * m.w + r[c].w * (1.f - m.w));
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    *reinterpret_cast<float4*>(fin + ((size_t)n * 3 + c) * HW + pix) = f[c];
+    if (fg || raw_out != raw) *reinterpret_cast<float4*>(raw_out + ((size_t)n * 3 + c) * HW + pix) = r[c];
+  }
+}
+
 // stand-alone resample(image, flow): image (N,C,H,W), flow (N,2,H,W) in pixels -> (N,C,H,W)
 __global__ void resample_kernel(const float* __restrict__ img, const float* __restrict__ flow, float* __restrict__ out,
                                 int N, int C, int H, int W, int align_corners) {
@@ -118,6 +176,9 @@ static inline int grid1d(size_t total) {
 }
 
 cudaError_t launch_composite(const CompositeParams& p, cudaStream_t stream) {
+  static const bool vec_ok = [] { const char* e = getenv("V2V_COMPOSITE_VEC"); return !(e && e[0] == '0'); }();
+  if (vec_ok && p.W % 4 == 0 && p.H <= 65535 && p.N <= 65535)
+    return launch_pdl(composite_vec4_kernel, dim3((p.W / 4 + 127) / 128, p.H, p.N), dim3(128), 0, stream, p);
   return launch_pdl(composite_kernel, dim3(grid1d((size_t)p.N * p.H * p.W)), dim3(256), 0, stream, p);
   return cudaGetLastError();
 }
