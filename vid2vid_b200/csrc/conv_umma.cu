@@ -98,7 +98,7 @@ struct UnitIter {
     while (img >= p.N) { img -= p.N; ++key; if (++nt == p.n_tiles) { nt = 0; ++phase; } }
   }
   __device__ __forceinline__ int n0(const ConvKernelParams& p) const { return nt * p.BN; }
-  __device__ __forceinline__ int x0(const ConvKernelParams& p) const { return txi * p.MG * p.TW; }   // first tile of the unit
+  __device__ __forceinline__ int x0(const ConvKernelParams& p) const { return txi * p.MG * p.tile_dx; }   // first tile of the unit
   __device__ __forceinline__ int y0(const ConvKernelParams& p) const { return ty * p.TH; }
 };
 
@@ -392,6 +392,34 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
 
+        if (p.epi == EPI_HEAD_F32 && p.headkx) {
+          // kx-GEMM head: accumulator row = INPUT pixel x0 + row of this output row, column kx * Cout + c.
+          // out(x)[c] = sum_kx D[x + kx][kx * Cout + c]: stage the 128 x (kw * Cout) block in shared memory (stride 25: conflict
+          // free), then thread `row` gathers its kw shifted rows.  Rows 128 - (kw - 1) .. 127 only feed their left neighbours.
+          float* S = red + eg * kRedFloatsPerGroup;
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr, r);
+          tmem_ld_wait();
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[my_as]);
+          const int ncol = p.headkx * p.Cout;
+#pragma unroll
+          for (int j = 0; j < 25; ++j) if (j < ncol) S[row * 25 + j] = __uint_as_float(r[j]);
+          named_bar_sync(1 + eg, kEpiThreads);
+          if (valid && row < p.tile_dx) {
+            const size_t pix = (size_t)oy * p.out_W + ox;
+            for (int j = 0; j < p.Cout; ++j) {
+              float v = 0.f;
+              for (int kx = 0; kx < p.headkx; ++kx) v += S[(row + kx) * 25 + kx * p.Cout + j];
+              if (p.bias) v += (p.bias2 && j >= p.Cout1) ? __ldg(p.bias2 + j - p.Cout1) : __ldg(p.bias + j);
+              v = apply_act(v, p.head_act[j], p.lrelu_slope) * p.head_scale[j];
+              reinterpret_cast<float*>(p.io[p.head_slot[j]])[p.head_off[j] + (size_t)n_img * p.head_bstride[j] + pix] = v;
+            }
+          }
+          named_bar_sync(1 + eg, kEpiThreads);        // S is rewritten by the group's next tile
+          continue;
+        }
         if (p.epi == EPI_HEAD_F32) {
           uint32_t r[16];
           tmem_ld_32x32b_x16(taddr, r);

@@ -133,14 +133,17 @@ __global__ void __launch_bounds__(256) export_nchw_kernel(ExportParams p) {
 
 __global__ void pack_weights_kernel(PackParams p) {
   const int K = p.ntaps * p.Cp;
-  const long long total = (long long)p.Cout * K;
+  const int rows = p.headkx ? p.headkx * p.Cout : p.Cout;
+  const long long total = (long long)rows * K;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(idx % K), co = (int)(idx / K);
+    const int k = (int)(idx % K), row = (int)(idx / K);
     const int t = k / p.Cp, c = k - t * p.Cp;
+    int co = row, ky, kx;
+    if (p.headkx) { kx = row / p.Cout; co = row - kx * p.Cout; ky = t; }        // kx-GEMM head: one tap per filter ROW
+    else { ky = p.tap_ky[t]; kx = p.tap_kx[t]; }
     float v = 0.f;
     if (c < p.Cin) {
-      const int ky = p.tap_ky[t], kx = p.tap_kx[t];
       if (p.w2 && co >= p.Cout1) {
         v = p.w2[((((size_t)(co - p.Cout1)) * p.Cin + c) * p.kh + ky) * p.kw + kx];
       } else {
@@ -150,7 +153,7 @@ __global__ void pack_weights_kernel(PackParams p) {
         v = p.w[wi];
       }
     }
-    if (p.split) split_bf16(v, p.out[(size_t)co * 2 * K + k], p.out[(size_t)co * 2 * K + K + k]);
+    if (p.split) split_bf16(v, p.out[(size_t)row * 2 * K + k], p.out[(size_t)row * 2 * K + K + k]);
     else p.out[idx] = __float2bfloat16_rn(v);
   }
 }
@@ -225,7 +228,7 @@ cudaError_t launch_export_nchw(const ExportParams& p, cudaStream_t stream) {
 }
 
 cudaError_t launch_pack_weights(const PackParams& p, cudaStream_t stream) {
-  const long long total = (long long)p.Cout * p.ntaps * p.Cp;
+  const long long total = (long long)(p.headkx ? p.headkx * p.Cout : p.Cout) * p.ntaps * p.Cp;
   long long b = (total + 255) / 256;
   if (b > 148 * 16) b = 148 * 16;
   pack_weights_kernel<<<(int)b, 256, 0, stream>>>(p);

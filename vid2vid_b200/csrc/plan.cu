@@ -65,6 +65,7 @@ struct ConvGeom {
   int patch2d_kc;         // > 0: 16x8 pixel tiles, ONE activation patch of (16+kh-1) x (8+kw-1) pixels serves all kh*kw taps;
   int patch2d_bn;         //      K block / N tile / weight residency chosen together with the geometry (they decide the fit)
   int patch2d_resident;
+  int headkx;             // > 0 (= kw): small-Cout head evaluated as a GEMM over (kx, channel) columns (taps over ky only)
   int n_groups, n_phases;
   ConvGroup groups[V2V_MAX_TAPS];
   ConvPhase phases[V2V_MAX_PHASES];
@@ -127,7 +128,8 @@ static bool choose_patch2d(const v2v_conv_desc& c, bool head, int N, int grid_h,
   return false;
 }
 
-static int conv_geometry(const v2v_conv_desc& c, bool head, int N, int H, int W, bool allow_reuse, int sp, ConvGeom* g) {
+// head: 0 = no, 1 = small-Cout head, 2 = head that may use the kx-GEMM form (tcgen05 implementation only)
+static int conv_geometry(const v2v_conv_desc& c, int head, int N, int H, int W, bool allow_reuse, int sp, ConvGeom* g) {
   memset(g, 0, sizeof(*g));
   V2V_REQUIRE(c.kh >= 1 && c.kw >= 1 && c.kh * c.kw <= V2V_MAX_TAPS, V2V_ERR_UNSUPPORTED, "kernel %dx%d unsupported",
               c.kh, c.kw);
@@ -152,7 +154,17 @@ static int conv_geometry(const v2v_conv_desc& c, bool head, int N, int H, int W,
   g->TH = 128 / g->TW;
   g->R = 1;
   int ng = 0;
-  if (allow_reuse && choose_patch2d(c, head, N, g->grid_h, g->grid_w, sp, &g->patch2d_kc, &g->patch2d_bn, &g->patch2d_resident)) {
+  static const bool headkx_ok = [] { const char* e = getenv("V2V_HEADKX"); return !(e && e[0] == '0'); }();
+  if (head == 2 && headkx_ok && !c.transposed && c.stride == 1 && c.kw >= 3 && c.kw * c.Cout <= 25 && g->grid_w >= 32) {
+    // Small-Cout heads (7x7, 2-3 channels) are MMA-issue bound as N = 16 convolutions: 49 taps x K blocks of ~40-cycle MMAs per
+    // 128 pixels.  As a GEMM with N = kw * Cout columns per INPUT pixel and taps over the kh filter rows only, a tile issues
+    // kh x K-block MMAs (7x fewer) and the epilogue sums the kw horizontally shifted columns; tiles overlap by kw - 1 pixels.
+    g->n_phases = 1;
+    g->TW = 128; g->TH = 1; g->R = 1; g->RW = 1;
+    g->headkx = c.kw;
+    for (int ky = 0; ky < c.kh; ++ky) g->groups[ng++] = ConvGroup{0, (int8_t)ky, 0, 0, (int16_t)ky, 0};
+    g->phases[0] = ConvPhase{0, ng, 0, 0};
+  } else if (allow_reuse && choose_patch2d(c, head != 0, N, g->grid_h, g->grid_w, sp, &g->patch2d_kc, &g->patch2d_bn, &g->patch2d_resident)) {
     g->n_phases = 1;
     g->TH = 16; g->TW = 8;
     g->R = c.kh * c.kw; g->RW = c.kw;
@@ -393,7 +405,8 @@ static int lower(v2v_plan* P) {
   for (auto& op : P->gops) {
     if (op.kind == G_CONV || op.kind == G_CONV_ACT || op.kind == G_HEAD) {
       Value& vin = P->values[op.value_in];
-      int rc = conv_geometry(op.conv, op.kind == G_HEAD, vin.N, vin.H, vin.W, P->allow_reuse, P->sp(), &op.geom);
+      int rc = conv_geometry(op.conv, op.kind == G_HEAD ? (P->impl == V2V_IMPL_UMMA ? 2 : 1) : 0, vin.N, vin.H, vin.W, P->allow_reuse,
+                             P->sp(), &op.geom);
       if (rc) return rc;
       op.req_index = add_req(vin, conv_req(op.conv, op.geom));
       const v2v_conv_desc& c = op.conv;
@@ -430,10 +443,12 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   ConvKernelParams& kp = op.kp;
   memset(&kp, 0, sizeof(kp));
   kp.N = vin.N; kp.TH = g.TH; kp.TW = g.TW;
-  kp.tiles_x = (g.grid_w + g.TW - 1) / g.TW; kp.tiles_y = (g.grid_h + g.TH - 1) / g.TH;
+  kp.headkx = g.headkx;
+  kp.tile_dx = g.headkx ? g.TW - (g.headkx - 1) : g.TW;
+  kp.tiles_x = (g.grid_w + kp.tile_dx - 1) / kp.tile_dx; kp.tiles_y = (g.grid_h + g.TH - 1) / g.TH;
   kp.grid_h = g.grid_h; kp.grid_w = g.grid_w;
   kp.Cout = op.conv.Cout;
-  kp.BN = op.kind == G_HEAD ? 16 : std::min(128, round_up(op.conv.Cout, 32));
+  kp.BN = op.kind == G_HEAD ? (g.headkx ? 32 : 16) : std::min(128, round_up(op.conv.Cout, 32));
   kp.Cp = pad_channels(op.conv.Cin);
   kp.kc = std::min(kp.Cp, 64);
   kp.MG = 1;
@@ -566,7 +581,7 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   kp.bias = op.conv.bias;
   kp.lrelu_slope = op.slope;
   kp.act = op.act;
-  op.Cp = kp.Cp; op.Ktotal = op.conv.kh * op.conv.kw * kp.Cp;
+  op.Cp = kp.Cp; op.Ktotal = (g.headkx ? op.conv.kh : op.conv.kh * op.conv.kw) * kp.Cp;
   kp.Khalf = op.Ktotal;
 }
 
@@ -575,7 +590,7 @@ static int pack_one(const GOp& op, cudaStream_t stream) {
   pp.w = op.conv.weight; pp.transposed = op.conv.transposed;
   pp.w2 = op.conv.Cout2 > 0 ? op.conv.weight2 : nullptr; pp.Cout1 = op.conv.Cout - op.conv.Cout2;
   pp.Cout = op.conv.Cout; pp.Cin = op.conv.Cin; pp.kh = op.conv.kh; pp.kw = op.conv.kw;
-  pp.Cp = op.Cp; pp.ntaps = op.conv.kh * op.conv.kw; pp.split = op.kp.split;
+  pp.Cp = op.Cp; pp.ntaps = op.geom.headkx ? op.conv.kh : op.conv.kh * op.conv.kw; pp.split = op.kp.split; pp.headkx = op.geom.headkx;
   for (int ky = 0; ky < op.conv.kh; ++ky)
     for (int kx = 0; kx < op.conv.kw; ++kx) { pp.tap_ky[ky * op.conv.kw + kx] = (int8_t)ky; pp.tap_kx[ky * op.conv.kw + kx] = (int8_t)kx; }
   pp.out = op.wpacked;
@@ -851,7 +866,7 @@ static int check_conv(v2v_plan* p, int value_in, const v2v_conv_desc* c) {
 int v2v_g_conv(v2v_plan* p, int value_in, const v2v_conv_desc* c, int* raw_out) {
   int rc = check_conv(p, value_in, c); if (rc) return rc;
   V2V_REQUIRE(raw_out, V2V_ERR_INVALID, "null raw_out");
-  ConvGeom g; rc = conv_geometry(*c, false, p->values[value_in].N, p->values[value_in].H, p->values[value_in].W, p->allow_reuse, p->sp(), &g); if (rc) return rc;
+  ConvGeom g; rc = conv_geometry(*c, 0, p->values[value_in].N, p->values[value_in].H, p->values[value_in].W, p->allow_reuse, p->sp(), &g); if (rc) return rc;
   GOp op; op.kind = G_CONV; op.value_in = value_in; op.conv = *c;
   Raw r{}; r.N = p->values[value_in].N; r.H = g.out_h; r.W = g.out_w; r.C = c->Cout; r.conv_op = (int)p->gops.size();
   p->raws.push_back(r);
@@ -892,7 +907,7 @@ int v2v_g_norm_act(v2v_plan* p, int raw_in, const v2v_norm_desc* norm, int act, 
 int v2v_g_conv_act(v2v_plan* p, int value_in, const v2v_conv_desc* c, int act, float slope, int* value_out) {
   int rc = check_conv(p, value_in, c); if (rc) return rc;
   V2V_REQUIRE(value_out, V2V_ERR_INVALID, "null value_out");
-  ConvGeom g; rc = conv_geometry(*c, false, p->values[value_in].N, p->values[value_in].H, p->values[value_in].W, p->allow_reuse, p->sp(), &g); if (rc) return rc;
+  ConvGeom g; rc = conv_geometry(*c, 0, p->values[value_in].N, p->values[value_in].H, p->values[value_in].W, p->allow_reuse, p->sp(), &g); if (rc) return rc;
   GOp op; op.kind = G_CONV_ACT; op.value_in = value_in; op.conv = *c; op.act = act; op.slope = slope;
   op.value_out = new_value(p, p->values[value_in].N, g.out_h, g.out_w, c->Cout);
   p->gops.push_back(op);
@@ -1000,7 +1015,7 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
     GOp& op = P->gops[i];
     if (op.kind == G_CONV || op.kind == G_CONV_ACT || op.kind == G_HEAD) {
       fill_conv_params(P, op);
-      w_off[i] = take((size_t)P->sp() * op.conv.Cout * op.Ktotal * sizeof(bf16));
+      w_off[i] = take((size_t)P->sp() * (op.geom.headkx ? op.geom.headkx * op.conv.Cout : op.conv.Cout) * op.Ktotal * sizeof(bf16));
       if (op.kind == G_CONV) {
         Raw& r = P->raws[op.raw];
         r.desc.N = r.N; r.desc.H = r.H; r.desc.W = r.W; r.desc.Cvalid = r.C; r.desc.C = round_up(r.C, 8);
@@ -1095,7 +1110,8 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
         }
         if (P->impl == V2V_IMPL_UMMA) {
           rc = make_tmap_act(&op.tmA, ain, kp.PW, kp.PH, kp.kc); if (rc) return rc;
-          rc = make_tmap_w(&op.tmB, op.wpacked, P->sp() * op.Ktotal, op.conv.Cout, kp.BN, kp.kc); if (rc) return rc;
+          rc = make_tmap_w(&op.tmB, op.wpacked, P->sp() * op.Ktotal, op.geom.headkx ? op.geom.headkx * op.conv.Cout : op.conv.Cout, kp.BN,
+                           kp.kc); if (rc) return rc;
         }
         rc = pack_one(op, stream); if (rc) return rc;
         XOp x; x.kind = X_CONV; x.gop = (int)i;
@@ -1364,7 +1380,7 @@ int v2v_conv_tap_table(const v2v_conv_desc* conv, int H, int W, int allow_reuse,
                        int* pads, int* parity, int* grid_hw, int* out_hw, int* mul) {
   V2V_REQUIRE(conv, V2V_ERR_INVALID, "null conv");
   ConvGeom g;
-  int rc = conv_geometry(*conv, false, 1, H, W, allow_reuse != 0, 1, &g);
+  int rc = conv_geometry(*conv, 0, 1, H, W, allow_reuse != 0, 1, &g);
   if (rc) return rc;
   *n_groups = g.n_groups; R[0] = g.R; R[1] = g.RW; *n_phases = g.n_phases; *parity = g.parity; *mul = g.mul;
   for (int i = 0; i < g.n_groups; ++i) { plane[i] = g.groups[i].plane; dy[i] = g.groups[i].dy; dx[i] = g.groups[i].dx; tap0[i] = g.groups[i].tap0; }

@@ -113,6 +113,9 @@ struct ConvKernelParams {
   int a_half_bytes, b_half_bytes;    // byte offset of the lo half inside an A / B slot
   int Khalf;                         // taps * Cp: column offset of the lo half in the packed weight matrix
   int out_f32;                       // EPI_RAW_STATS: raw output element type (1 = fp32)
+  int tile_dx;                       // x distance between consecutive M tiles (TW, or TW - (kw - 1) for kx-GEMM heads)
+  int headkx;                        // > 0: small-Cout head as a GEMM over (kx, channel) columns: N = kw * Cout accumulator
+                                     // columns per INPUT pixel, taps over ky only; the epilogue sums the kw shifted columns
   int a_exact;                       // precise plans: the input values are exact in bf16 (one-hot labels, edge maps): the lo
                                      // half of A is all zero, so it is neither fetched nor multiplied (2 MMAs per K block)
   // fused statistics finalisation: after its last tile every CTA arrives on a grid-wide counter; once all have, CTA b
@@ -210,6 +213,7 @@ struct PackParams {
   int Cp, ntaps;
   int8_t tap_ky[V2V_MAX_TAPS], tap_kx[V2V_MAX_TAPS];   // filter coordinates of packed tap t
   int split;               // 1: [Cout][2][ntaps * Cp] (hi row half, then lo row half)
+  int headkx;              // > 0 (= kw): rows are (kx * Cout + co), taps are the kh filter rows: out[kx * Cout + co][ky * Cp + c]
   bf16* out;               // [Cout][ntaps * Cp]
 };
 
