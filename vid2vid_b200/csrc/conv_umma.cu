@@ -66,6 +66,23 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
   return v[0];
 }
 
+// kx-GEMM heads: acc[j] = sum_kx (value of accumulator column kx * COUT + j held by lane + kx)
+template <int COUT>
+__device__ __forceinline__ void head_shift_sum(const uint32_t (&r)[32], int kw, float (&acc)[4]) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j) acc[j] = 0.f;
+#pragma unroll
+  for (int kx = 0; kx < 8; ++kx) {
+    if (kx * COUT + COUT <= 32) {
+#pragma unroll
+      for (int j = 0; j < COUT; ++j) {
+        const float v = __shfl_down_sync(0xffffffffu, __uint_as_float(r[kx * COUT + j]), kx);
+        if (kx < kw) acc[j] += v;
+      }
+    }
+  }
+}
+
 // Work units (MG consecutive M tiles of one tile row, of one (phase, N tile) "key"; M fastest) are walked by every role as u = first, first + step, ...
 // Integer division is ~150 cycles of dependent SASS on one thread, and the single MMA-issuing thread used to spend
 // ~1000 cycles per tile decoding u (measured with the V2V_DBG traces: a 1000-cycle bubble between tiles of 2100 cycles
@@ -141,7 +158,8 @@ __device__ __forceinline__ void mma_role(const ConvKernelParams& p, const MmaCtx
   int gs = 0, it = 0, as = 0;
   uint32_t gpar = 0, gen = 0, aphase = 0;
   int prev_key = -1;
-  const uint32_t a_step = (uint32_t)(p.row_bytes >> 4), b_step = (uint32_t)(cx.b_tx >> 4);
+  // tap r of a patch: next pixel (horizontal reuse) or, for kx-GEMM heads, next patch ROW (TW pixels further)
+  const uint32_t a_step = (uint32_t)(((p.headkx ? p.TW : 1) * p.row_bytes) >> 4), b_step = (uint32_t)(cx.b_tx >> 4);
   const uint32_t a_wrap = (uint32_t)(((p.PW - p.RW) * p.row_bytes) >> 4);     // to the next patch row
   const uint32_t sBres_u32 = smem_u32(cx.sBres);
   const int ps_step = p.split ? (p.a_exact ? 2 : 1) : 3;
@@ -393,31 +411,35 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
 
         if (p.epi == EPI_HEAD_F32 && p.headkx) {
-          // kx-GEMM head: accumulator row = INPUT pixel x0 + row of this output row, column kx * Cout + c.
-          // out(x)[c] = sum_kx D[x + kx][kx * Cout + c]: stage the 128 x (kw * Cout) block in shared memory (stride 25: conflict
-          // free), then thread `row` gathers its kw shifted rows.  Rows 128 - (kw - 1) .. 127 only feed their left neighbours.
-          float* S = red + eg * kRedFloatsPerGroup;
+          // kx-GEMM head.  Tile = 4 rows x 32 INPUT pixels: TMEM lane quarter q = tile row, lane = pixel, accumulator
+          // column kx * Cout + c.  out(x)[c] = sum_kx D[x + kx][kx * Cout + c] is a sum over the NEXT kw - 1 lanes of the
+          // same warp: warp shuffles, no shared memory.  Lanes 32 - (kw - 1) .. 31 only feed their left neighbours
+          // (tiles advance by tile_dx = 32 - (kw - 1) pixels).
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr, r);
           tmem_ld_wait();
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[my_as]);
-          const int ncol = p.headkx * p.Cout;
-#pragma unroll
-          for (int j = 0; j < 25; ++j) if (j < ncol) S[row * 25 + j] = __uint_as_float(r[j]);
-          named_bar_sync(1 + eg, kEpiThreads);
-          if (valid && row < p.tile_dx) {
+          float acc[4];
+          switch (p.Cout) {
+            case 1: head_shift_sum<1>(r, p.headkx, acc); break;
+            case 2: head_shift_sum<2>(r, p.headkx, acc); break;
+            case 3: head_shift_sum<3>(r, p.headkx, acc); break;
+            default: head_shift_sum<4>(r, p.headkx, acc); break;
+          }
+          if (valid && rx < p.tile_dx) {
             const size_t pix = (size_t)oy * p.out_W + ox;
-            for (int j = 0; j < p.Cout; ++j) {
-              float v = 0.f;
-              for (int kx = 0; kx < p.headkx; ++kx) v += S[(row + kx) * 25 + kx * p.Cout + j];
-              if (p.bias) v += (p.bias2 && j >= p.Cout1) ? __ldg(p.bias2 + j - p.Cout1) : __ldg(p.bias + j);
-              v = apply_act(v, p.head_act[j], p.lrelu_slope) * p.head_scale[j];
-              reinterpret_cast<float*>(p.io[p.head_slot[j]])[p.head_off[j] + (size_t)n_img * p.head_bstride[j] + pix] = v;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (j < p.Cout) {
+                float v = acc[j];
+                if (p.bias) v += (p.bias2 && j >= p.Cout1) ? __ldg(p.bias2 + j - p.Cout1) : __ldg(p.bias + j);
+                v = apply_act(v, p.head_act[j], p.lrelu_slope) * p.head_scale[j];
+                reinterpret_cast<float*>(p.io[p.head_slot[j]])[p.head_off[j] + (size_t)n_img * p.head_bstride[j] + pix] = v;
+              }
             }
           }
-          named_bar_sync(1 + eg, kEpiThreads);        // S is rewritten by the group's next tile
           continue;
         }
         if (p.epi == EPI_HEAD_F32) {

@@ -155,14 +155,19 @@ static int conv_geometry(const v2v_conv_desc& c, int head, int N, int H, int W, 
   g->R = 1;
   int ng = 0;
   static const bool headkx_ok = [] { const char* e = getenv("V2V_HEADKX"); return !(e && e[0] == '0'); }();
-  if (head == 2 && headkx_ok && !c.transposed && c.stride == 1 && c.kw >= 3 && c.kw * c.Cout <= 25 && g->grid_w >= 32) {
+  if (head == 2 && headkx_ok && !c.transposed && c.stride == 1 && c.kw >= 3 && c.kw <= 8 && c.Cout <= 4 && c.kw * c.Cout <= 32 &&
+      c.kh <= 8 && g->grid_w >= 32) {
     // Small-Cout heads (7x7, 2-3 channels) are MMA-issue bound as N = 16 convolutions: 49 taps x K blocks of ~40-cycle MMAs per
     // 128 pixels.  As a GEMM with N = kw * Cout columns per INPUT pixel and taps over the kh filter rows only, a tile issues
-    // kh x K-block MMAs (7x fewer) and the epilogue sums the kw horizontally shifted columns; tiles overlap by kw - 1 pixels.
+    // kh x K-block MMAs (7x fewer) and the epilogue sums the kw horizontally shifted columns (warp shuffles).  Tile = 4 rows x
+    // 32 input pixels; ONE patch of (4 + kh - 1) rows x 32 pixels serves all kh taps (operand of tap ky = the patch advanced
+    // by ky rows: contiguous in shared memory, so the canonical 8-row group stride applies); tiles advance by 32 - (kw - 1)
+    // pixels.  (One box per filter row on 1x128 tiles was TMA-request bound: 1792 smem rows per 122 outputs against 640 per
+    // 104 here.)
     g->n_phases = 1;
-    g->TW = 128; g->TH = 1; g->R = 1; g->RW = 1;
+    g->TW = 32; g->TH = 4; g->R = c.kh; g->RW = c.kh;
     g->headkx = c.kw;
-    for (int ky = 0; ky < c.kh; ++ky) g->groups[ng++] = ConvGroup{0, (int8_t)ky, 0, 0, (int16_t)ky, 0};
+    g->groups[ng++] = ConvGroup{0, 0, 0, 0, 0, 0};
     g->phases[0] = ConvPhase{0, ng, 0, 0};
   } else if (allow_reuse && choose_patch2d(c, head != 0, N, g->grid_h, g->grid_w, sp, &g->patch2d_kc, &g->patch2d_bn, &g->patch2d_resident)) {
     g->n_phases = 1;
@@ -457,6 +462,17 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   kp.a_exact = (P->precise && vin.exact_bf16) ? 1 : 0;
   const bool p2d = g.patch2d_kc > 0;
   if (p2d) { kp.kc = g.patch2d_kc; if (op.kind != G_HEAD) kp.BN = g.patch2d_bn; }
+  if (g.headkx) {
+    // K block of a kx-GEMM head: the largest whose patch ring (2 stages) fits next to the resident weight set, or, failing
+    // that, whose two streamed stages fit
+    for (int kc = std::min(kp.Cp, 64); kc >= 16; kc >>= 1) {
+      if (kp.Cp % kc) continue;
+      const int a_sl = sp * round_up(g.TW * (g.TH + op.conv.kh - 1) * kc * 2, 1024), b_sl = sp * round_up(g.R * kp.BN * kc * 2, 1024);
+      const long long res = (long long)(kp.Cp / kc) * b_sl;
+      kp.kc = kc;
+      if ((res <= kResidentMax && kSmemBudget - res >= 2 * a_sl) || 2 * (a_sl + b_sl) <= kSmemBudget) break;
+    }
+  }
   const int m_tiles = kp.N * kp.tiles_x * kp.tiles_y;
   // M blocking for row-tile filters whose weights must be streamed (the 7x7 stems over the 108-channel label input):
   // per M tile such a layer pulls taps*Cp*BN*2 bytes of weights through L2 -> SM (802 KB for 108->48, 13 GB per launch at
@@ -483,7 +499,7 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
     for (int ci = 0; ci < (sp == 2 ? 4 : 1) && !mblock; ++ci) {
       const int t_kc = cand[ci][0], t_bn = cand[ci][1], t_mg = cand[ci][2];
       if (t_mg < 1 || kp.Cp % t_kc || t_bn % 32 || t_bn > 128 || kp.tiles_x % t_mg || 2 * t_mg * std::max(32, t_bn) > 512) continue;
-      const int a_slot = sp * round_up((g.TW + g.R - 1) * g.TH * t_kc * 2, 1024), b_slot = sp * round_up(g.R * t_bn * t_kc * 2, 1024);
+      const int a_slot = sp * round_up((g.TW + g.R - 1) * g.TH * t_kc * 2, 1024), b_slot = sp * round_up(g.R * t_bn * t_kc * 2, 1024);   // (never a head)
       if (2 * (t_mg * a_slot + b_slot) <= kSmemBudget) { kp.kc = t_kc; kp.BN = t_bn; kp.MG = t_mg; mblock = true; }
     }
   }
@@ -493,8 +509,8 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   kp.R = g.R; kp.RW = g.RW;
   // patch extent in pixels; 8-row core-matrix groups of the A operand are SBO bytes apart: the canonical 8 rows for
   // row tiles, one patch row (PW pixels) in 2-D patch mode
-  kp.PW = p2d ? g.TW + op.conv.kw - 1 : g.TW + g.R - 1;
-  kp.PH = p2d ? g.TH + op.conv.kh - 1 : g.TH;
+  kp.PW = p2d ? g.TW + op.conv.kw - 1 : (g.headkx ? g.TW : g.TW + g.R - 1);
+  kp.PH = p2d ? g.TH + op.conv.kh - 1 : (g.headkx ? g.TH + op.conv.kh - 1 : g.TH);
   kp.sbo_bytes = 8 * kp.row_bytes;
   kp.sbo_a_bytes = p2d ? kp.PW * kp.row_bytes : 8 * kp.row_bytes;
   kp.a_half_bytes = round_up(kp.PW * kp.PH * kp.row_bytes, 1024);
@@ -508,7 +524,7 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
   // shared-memory budget: 227 KB - epilogue scratch (12.5 KB per group) - alignment slack - barriers
   const int budget = kSmemBudget;
   // a weight slot holds the R taps served by one activation patch; keep >= 2 slots + 3 patches in the budget
-  if (sp == 2 && !p2d && !mblock && g.R > 1) {
+  if (sp == 2 && !p2d && !mblock && g.R > 1 && !g.headkx) {
     // precise plans: every slot doubles.  N tiles below 64 make the (3x) MMAs issue bound, so try (K block, N tile) in the
     // order (kc, BN), (kc, BN/2 >= 64), (32, BN), (32, BN/2 >= 64) before falling through to the generic halving
     const int bn0 = kp.BN, kc0 = kp.kc;
