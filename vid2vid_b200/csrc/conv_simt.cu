@@ -72,7 +72,7 @@ __global__ void conv_simt_kernel(ActDesc in, const bf16* __restrict__ w, int Kto
 
 // Per-channel (sum, sumsq) of a raw NHWC bf16 tensor, one partial row per image:
 // stats[(n*2 + {0,1}) * C + c].  Used with the SIMT conv (the tcgen05 epilogue produces these itself).
-__global__ void raw_stats_kernel(const void* __restrict__ raw_, int f32, int HW, int C, int Cs, float* __restrict__ stats) {
+__global__ void raw_stats_kernel(const void* __restrict__ raw_, int f32, int HW, int C, int Cs, stat_t* __restrict__ stats) {
   const int n = blockIdx.y, c = blockIdx.x;
   float s = 0.f, q = 0.f;
   for (int i = threadIdx.x; i < HW; i += blockDim.x) {
@@ -88,8 +88,8 @@ __global__ void raw_stats_kernel(const void* __restrict__ raw_, int f32, int HW,
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    stats[((size_t)n * 2 + 0) * Cs + c] = ss[0];
-    stats[((size_t)n * 2 + 1) * Cs + c] = sq[0];
+    stats[((size_t)n * 2 + 0) * Cs + c] = (stat_t)__float2ll_rn(ss[0] * V2V_STAT_SUM_SCALE);
+    stats[((size_t)n * 2 + 1) * Cs + c] = (stat_t)__float2ll_rn(sq[0] * V2V_STAT_SQ_SCALE);
   }
 }
 
@@ -102,7 +102,7 @@ cudaError_t launch_conv_simt(const ActDesc& in, const bf16* wpacked, int Ktotal,
   return cudaGetLastError();
 }
 
-cudaError_t launch_raw_stats(const RawDesc& raw, float* stats, int stats_C, cudaStream_t stream) {
+cudaError_t launch_raw_stats(const RawDesc& raw, stat_t* stats, int stats_C, cudaStream_t stream) {
   dim3 grid(raw.Cvalid, raw.N);
   raw_stats_kernel<<<grid, 256, 0, stream>>>(raw.base, raw.f32, raw.H * raw.W, raw.C, stats_C, stats);
   return cudaGetLastError();

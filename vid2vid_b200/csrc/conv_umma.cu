@@ -367,9 +367,9 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           s += racc[(w * 2 + 0) * 128 + etid];
           qq += racc[(w * 2 + 1) * 128 + etid];
         }
-        const size_t rowi = ((size_t)acc_phase * p.N + acc_img) * gridDim.x + blockIdx.x;
-        atomicAdd(&p.stats[(rowi * 2 + 0) * p.stats_C + acc_n0 + etid], s);
-        atomicAdd(&p.stats[(rowi * 2 + 1) * p.stats_C + acc_n0 + etid], qq);
+        // 64-bit fixed-point integer atomics onto the image's single statistics row: order independent (deterministic)
+        atomicAdd(&p.stats[((size_t)acc_img * 2 + 0) * p.stats_C + acc_n0 + etid], (stat_t)__float2ll_rn(s * V2V_STAT_SUM_SCALE));
+        atomicAdd(&p.stats[((size_t)acc_img * 2 + 1) * p.stats_C + acc_n0 + etid], (stat_t)__float2ll_rn(qq * V2V_STAT_SQ_SCALE));
       }
       named_bar_sync(1 + eg, kEpiThreads);                // racc may be cleared again
     };
@@ -579,19 +579,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
   if (p.n_fin > 0) {
-    // Fused statistics finalisation.  All CTAs of this launch are co-resident (persistent grid <= SM count, one CTA per
-    // SM), so a grid-wide arrive-and-spin on a counter that the plan zeroes before every run is safe; afterwards CTA b
-    // finalises channels b, b + grid, ... (one warp per channel) of each attached norm slice.
-    if (threadIdx.x == 0) {
-      atomicAdd(p.fin_counter, 1u);
-      while (*reinterpret_cast<volatile unsigned int*>(p.fin_counter) < gridDim.x) __nanosleep(64);
-      __threadfence();
-    }
+    // Statistics finalisation by the LAST CTA to get here (ticket counter, zeroed with the statistics rows before every run):
+    // all rows are complete then; every other CTA has exited, nobody waits.
+    if (threadIdx.x == 0) *tmem_slot = atomicAdd(p.fin_counter, 1u);
     __syncthreads();
-    const int nwarps = blockDim.x >> 5;
-    for (int f = 0; f < p.n_fin; ++f)
-      for (int c = blockIdx.x + warp * gridDim.x; c < p.fin[f].C; c += nwarps * gridDim.x)
-        finalize_channel<true>(p.fin[f], c, lane);
+    if (*tmem_slot == gridDim.x - 1) {
+      __threadfence();
+      for (int f = 0; f < p.n_fin; ++f)
+        for (int c = threadIdx.x; c < p.fin[f].C; c += blockDim.x) channel_side_effects(p.fin[f], c);
+    }
   }
   if ((p.dbg & 4) && blockIdx.x == 0 && threadIdx.x == 0) {
     const long long t0 = g_trace[0][0][0];

@@ -14,13 +14,13 @@
 
 namespace v2v {
 
-// One warp per channel (4 channels per block): see finalize.cuh.
+// Stand-alone finalisation (one thread per channel): only the grid-stride fallback of the normalise pass needs the scale /
+// shift arrays ahead of time; the row-segment kernel computes them in its block prologue (see finalize.cuh).
 __global__ void __launch_bounds__(128) stats_finalize_kernel(FinalizeParams p) {
   pdl_prologue();
-  const int c = blockIdx.x * 4 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= p.C) return;
-  finalize_channel<false>(p, c, lane);
+  channel_side_effects(p, c);
 }
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {   // nn.ReflectionPad2d index map
@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(256) norm_apply_rows_kernel(ApplyParams p, int
   pdl_prologue();
   const int vecs = p.out.C >> 3;
   const int t = threadIdx.x;
-  if (t >= ppb * vecs) return;
-  const int pl = t / vecs, v = t - pl * vecs;
+  const bool idle = t >= ppb * vecs;                 // (idle threads still take part in the prologue barrier)
+  const int pl = idle ? 0 : t / vecs, v = idle ? 0 : t - pl * vecs;
   const int Hpad = p.out.H + p.out.pad_t + p.out.pad_b, Wpad = p.out.W + p.out.pad_l + p.out.pad_r;
   const int n = blockIdx.y / Hpad, yp = blockIdx.y - n * Hpad;
   const int c0 = v * 8;
@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(256) norm_apply_rows_kernel(ApplyParams p, int
     sc[j] = cv ? (p.scale ? __ldg(p.scale + (size_t)n * p.scale_stride + c0 + j) : 1.f) : 0.f;
     sh[j] = (cv && p.scale) ? __ldg(p.shift + (size_t)n * p.scale_stride + c0 + j) : 0.f;
   }
+  if (idle) return;
   const size_t eb = PREC ? 4 : 2;
   const char* raw_row = reinterpret_cast<const char*>(p.raw.base) +
                         (((size_t)n * p.raw.H + (zero_row ? 0 : y)) * p.raw.W * (size_t)p.raw.C + c0) * eb;
@@ -260,119 +261,6 @@ __global__ void __launch_bounds__(256) norm_apply_rows_kernel(ApplyParams p, int
   }
 }
 
-// Fused variant: block (x, g) owns channel group g (64 channels = 128 bytes per pixel, coalesced) and a grid-stride share
-// of the pixels.  Its prologue reduces the conv kernel's per-CTA (sum, sumsq) partial rows for those 64 channels into
-// scale / shift in shared memory (what stats_finalize_kernel does in a separate launch), block x == 0 also applies the
-// running-stat side effect.  Removes one launch per normalised layer (131 per cfg4 frame).
-static constexpr int kFusedMaxN = 8;
-__global__ void __launch_bounds__(256) norm_apply_fused_kernel(ApplyParams p) {
-  __shared__ float s_scale[kFusedMaxN][64], s_shift[kFusedMaxN][64];
-  const FinalizeParams& f = p.fin;
-  const int cg0 = blockIdx.y * 64;                       // first channel (slice-local) of this block's group
-  const int rows_img = f.num_phases * f.tiles_per_img;
-  // ---- prologue: one thread per (image or batch, channel) item
-  const int items = (f.instance ? f.N : 1) * 64;
-  for (int it = threadIdx.x; it < items; it += blockDim.x) {
-    const int c = cg0 + (it & 63), ni = it >> 6;
-    if (c >= f.C) { for (int n = 0; n < f.N; ++n) if (f.instance ? n == ni : true) { s_scale[n][it & 63] = 0.f; s_shift[n][it & 63] = 0.f; } continue; }
-    double s = 0.0, q = 0.0;
-    const int n_lo = f.instance ? ni : 0, n_hi = f.instance ? ni + 1 : f.N;
-    for (int n = n_lo; n < n_hi; ++n)
-      for (int ph = 0; ph < f.num_phases; ++ph) {
-        const float* row = f.stats + ((size_t)(ph * f.N + n) * f.tiles_per_img * 2) * f.Cs + f.c_off + c;
-        for (int t = 0; t < f.tiles_per_img; ++t, row += 2 * (size_t)f.Cs) { s += (double)row[0]; q += (double)row[f.Cs]; }
-      }
-    const double cnt = f.count * (n_hi - n_lo);
-    const double mean = s / cnt;
-    double var = q / cnt - mean * mean;
-    if (var < 0) var = 0;
-    const float g = f.gamma ? f.gamma[c] : 1.f, b = f.beta ? f.beta[c] : 0.f;
-    const float sc = g * (float)(1.0 / sqrt(var + (double)f.eps));
-    const float sh = b - (float)mean * sc;
-    for (int n = n_lo; n < n_hi; ++n) { s_scale[n][it & 63] = sc; s_shift[n][it & 63] = sh; }
-    if (p.update_running && blockIdx.x == 0 && f.running_mean) {
-      // instance norm averages the per-image statistics over the batch (one thread per image would race): only the
-      // thread of image 0 updates, using this block's batch view
-      if (!f.instance) {
-        const float bias = f.conv_bias ? f.conv_bias[c] : 0.f;
-        f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * ((float)mean + bias);
-        f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)(var * (cnt / (cnt > 1 ? cnt - 1 : 1)));
-      } else if (ni == 0) {
-        double ms = 0.0, vs = 0.0;
-        for (int n = 0; n < f.N; ++n) {
-          double s2 = 0.0, q2 = 0.0;
-          for (int ph = 0; ph < f.num_phases; ++ph) {
-            const float* row = f.stats + ((size_t)(ph * f.N + n) * f.tiles_per_img * 2) * f.Cs + f.c_off + c;
-            for (int t = 0; t < f.tiles_per_img; ++t, row += 2 * (size_t)f.Cs) { s2 += (double)row[0]; q2 += (double)row[f.Cs]; }
-          }
-          const double m2 = s2 / f.count;
-          double v2 = q2 / f.count - m2 * m2;
-          if (v2 < 0) v2 = 0;
-          ms += m2; vs += v2 * (f.count / (f.count > 1 ? f.count - 1 : 1));
-        }
-        const float bias = f.conv_bias ? f.conv_bias[c] : 0.f;
-        f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * ((float)(ms / f.N) + bias);
-        f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * (float)(vs / f.N);
-      }
-      if (c == 0 && f.num_batches_tracked) *f.num_batches_tracked += 1;
-    }
-  }
-  (void)rows_img;
-  __syncthreads();
-  // ---- main: grid-stride over (padded pixel, vector within the 64-channel group)
-  const int vecs_all = p.out.C / 8;
-  const int gv = min(8, vecs_all - blockIdx.y * 8);
-  const int Hpad = p.out.H + p.out.pad_t + p.out.pad_b, Wpad = p.out.W + p.out.pad_l + p.out.pad_r;
-  const long long total = (long long)p.out.N * Hpad * Wpad * gv;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += stride) {
-    const int vl = (int)(idx % gv);
-    long long t = idx / gv;
-    const int xp = (int)(t % Wpad); t /= Wpad;
-    const int yp = (int)(t % Hpad);
-    const int n = (int)(t / Hpad);
-    int y = yp - p.out.pad_t, x = xp - p.out.pad_l;
-    const bool halo = (y < 0 || y >= p.out.H || x < 0 || x >= p.out.W);
-    uint4 o = make_uint4(0, 0, 0, 0);
-    const int c0 = cg0 + vl * 8;
-    bool zero = (c0 >= p.raw.Cvalid);
-    if (halo) {
-      if (p.pad_mode == PAD_REFLECT) { y = reflect_idx(y, p.out.H); x = reflect_idx(x, p.out.W); }
-      else zero = true;
-    }
-    if (!zero) {
-      const uint4 r = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(p.raw.base) + (((size_t)n * p.raw.H + y) * p.raw.W + x) * p.raw.C + c0);
-      float fv[8];
-      const __nv_bfloat162* rp = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { float2 a = __bfloat1622float2(rp[j]); fv[2 * j] = a.x; fv[2 * j + 1] = a.y; }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) fv[j] = (c0 + j < p.raw.Cvalid) ? fmaf(fv[j], s_scale[n][vl * 8 + j], s_shift[n][vl * 8 + j]) : 0.f;
-      if (p.act == ACT_RELU) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) fv[j] = fmaxf(fv[j], 0.f);
-      } else if (p.act == ACT_LRELU) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) fv[j] = fv[j] > 0.f ? fv[j] : fv[j] * p.slope;
-      }
-      for (int a = 0; a < p.n_add; ++a) {
-        const ActDesc& ad = p.add[a];
-        if (c0 < ad.C) {
-          const uint4 qd = *reinterpret_cast<const uint4*>(ad.base + ad.offset(n, y, x) + c0);
-          const __nv_bfloat162* qp = reinterpret_cast<const __nv_bfloat162*>(&qd);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) { float2 b2 = __bfloat1622float2(qp[j]); fv[2 * j] += b2.x; fv[2 * j + 1] += b2.y; }
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) if (c0 + j >= p.raw.Cvalid) fv[j] = 0.f;
-      o.x = pack_bf16x2(fv[0], fv[1]); o.y = pack_bf16x2(fv[2], fv[3]);
-      o.z = pack_bf16x2(fv[4], fv[5]); o.w = pack_bf16x2(fv[6], fv[7]);
-    }
-    *reinterpret_cast<uint4*>(p.out.base + p.out.offset(n, yp - p.out.pad_t, xp - p.out.pad_l) + c0) = o;
-  }
-}
-
 static inline int grid_for(long long total, int block) {
   long long b = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -380,7 +268,15 @@ static inline int grid_for(long long total, int block) {
 }
 
 cudaError_t launch_stats_finalize(const FinalizeParams& p, cudaStream_t stream) {
-  return launch_pdl(stats_finalize_kernel, dim3((p.C + 3) / 4), dim3(128), 0, stream, p);
+  return launch_pdl(stats_finalize_kernel, dim3((p.C + 127) / 128), dim3(128), 0, stream, p);
+}
+
+// true: the row-segment kernel (which derives scale / shift in its prologue) handles this launch; false: grid-stride fallback
+bool norm_apply_uses_rows(const ApplyParams& p) {
+  static const int variant = [] { const char* e = getenv("V2V_APPLY"); return e ? atoi(e) : 1; }();
+  const int vecs = p.out.C / 8;
+  const int Hpad = p.out.H + p.out.pad_t + p.out.pad_b;
+  return variant == 1 && vecs <= 256 && (long long)p.out.N * Hpad <= 65535;
 }
 
 cudaError_t launch_norm_apply(const ApplyParams& p, cudaStream_t stream) {
@@ -389,33 +285,22 @@ cudaError_t launch_norm_apply(const ApplyParams& p, cudaStream_t stream) {
   if (total >= (1LL << 31)) return cudaErrorInvalidValue;
   const bool prec = p.raw.f32 != 0;
   if (prec != (p.out.split != 0)) return cudaErrorInvalidValue;      // precise plans: fp32 raw <-> split activations
-  if (p.fused && !prec) {
-    const int groups = (p.out.C + 63) / 64;
-    int gx = grid_for(total / groups + 1, 256);
-    gx = std::max(1, std::min(gx, (148 * 8) / groups + 1));      // few, long-lived blocks: the prologue runs once per block
-    dim3 grid(gx, groups);
-    norm_apply_fused_kernel<<<grid, 256, 0, stream>>>(p);
-  } else {
-    static const int variant = [] { const char* e = getenv("V2V_APPLY"); return e ? atoi(e) : 1; }();
-    const int vecs = p.out.C / 8;
-    const int Hpad = p.out.H + p.out.pad_t + p.out.pad_b, Wpad = p.out.W + p.out.pad_l + p.out.pad_r;
-    if (variant == 1 && vecs <= 256 && (long long)p.out.N * Hpad <= 65535) {
-      const int ppb = 256 / vecs;                     // pixels per block pass
-      const int xt = ppb * 8;                         // 8 items per thread
-      dim3 grid((Wpad + xt - 1) / xt, p.out.N * Hpad);
-      if (prec) {
-        if (p.n_add == 0) return launch_pdl(norm_apply_rows_kernel<0, true>, grid, dim3(256), 0, stream, p, xt, ppb);
-        if (p.n_add == 1) return launch_pdl(norm_apply_rows_kernel<1, true>, grid, dim3(256), 0, stream, p, xt, ppb);
-        return launch_pdl(norm_apply_rows_kernel<2, true>, grid, dim3(256), 0, stream, p, xt, ppb);
-      }
-      if (p.n_add == 0) return launch_pdl(norm_apply_rows_kernel<0, false>, grid, dim3(256), 0, stream, p, xt, ppb);
-      if (p.n_add == 1) return launch_pdl(norm_apply_rows_kernel<1, false>, grid, dim3(256), 0, stream, p, xt, ppb);
-      return launch_pdl(norm_apply_rows_kernel<2, false>, grid, dim3(256), 0, stream, p, xt, ppb);
-    } else {
-      return launch_pdl(norm_apply_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, p);
+  const int vecs = p.out.C / 8;
+  const int Wpad = p.out.W + p.out.pad_l + p.out.pad_r, Hpad = p.out.H + p.out.pad_t + p.out.pad_b;
+  if (norm_apply_uses_rows(p)) {
+    const int ppb = 256 / vecs;                     // pixels per block pass
+    const int xt = ppb * 8;                         // 8 items per thread
+    dim3 grid((Wpad + xt - 1) / xt, p.out.N * Hpad);
+    if (prec) {
+      if (p.n_add == 0) return launch_pdl(norm_apply_rows_kernel<0, true>, grid, dim3(256), 0, stream, p, xt, ppb);
+      if (p.n_add == 1) return launch_pdl(norm_apply_rows_kernel<1, true>, grid, dim3(256), 0, stream, p, xt, ppb);
+      return launch_pdl(norm_apply_rows_kernel<2, true>, grid, dim3(256), 0, stream, p, xt, ppb);
     }
+    if (p.n_add == 0) return launch_pdl(norm_apply_rows_kernel<0, false>, grid, dim3(256), 0, stream, p, xt, ppb);
+    if (p.n_add == 1) return launch_pdl(norm_apply_rows_kernel<1, false>, grid, dim3(256), 0, stream, p, xt, ppb);
+    return launch_pdl(norm_apply_rows_kernel<2, false>, grid, dim3(256), 0, stream, p, xt, ppb);
   }
-  return cudaGetLastError();
+  return launch_pdl(norm_apply_kernel, dim3(grid_for(total, 256)), dim3(256), 0, stream, p);
 }
 
 }  // namespace v2v

@@ -241,7 +241,7 @@ struct Raw {
   int N, H, W, C;
   int conv_op = -1;          // index of producing graph op
   RawDesc desc{};
-  float* stats = nullptr; int stats_rows = 0;
+  stat_t* stats = nullptr;           // [N][2][C] fixed-point statistics rows (zeroed at the start of every run)
   float* scale = nullptr; float* shift = nullptr;
   int tiles_per_img = 0, num_phases = 1;
   std::vector<int> running_done;   // channel offsets whose running stats already have an updating launch
@@ -286,7 +286,7 @@ struct XOp {
   CompositeParams comp{};
   CopyParams copy{};
   CorrParams corr{};
-  RawDesc rawd{}; float* stats = nullptr; int stats_C = 0;
+  RawDesc rawd{}; stat_t* stats = nullptr; int stats_C = 0;
   void* ms_ptr = nullptr; size_t ms_bytes = 0;
 };
 
@@ -1038,7 +1038,6 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
         r.desc.f32 = P->precise;
         if (P->impl == V2V_IMPL_UMMA) { r.tiles_per_img = op.kp.grid; r.num_phases = op.kp.num_phases; }
         else { r.tiles_per_img = 1; r.num_phases = 1; }
-        r.stats_rows = r.num_phases * r.N * r.tiles_per_img;
         raw_off[op.raw].raw = take(r.desc.elems() * r.desc.elem_bytes());
         raw_off[op.raw].scale = take((size_t)r.N * r.C * sizeof(float));
         raw_off[op.raw].shift = take((size_t)r.N * r.C * sizeof(float));
@@ -1055,7 +1054,7 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
   // (a CTA only writes the (phase, image) rows it actually worked on)
   const size_t stats_begin = off;
   for (size_t i = 0; i < P->raws.size(); ++i)
-    if (P->raws[i].conv_op >= 0) raw_off[i].stats = take((size_t)P->raws[i].stats_rows * 2 * P->raws[i].C * sizeof(float) + 64);   // + grid-barrier counter
+    if (P->raws[i].conv_op >= 0) raw_off[i].stats = take((size_t)P->raws[i].N * 2 * P->raws[i].C * sizeof(stat_t) + 64);   // + ticket counter
   const size_t stats_end = off;
   P->arena_bytes = off;
   V2V_CUDA(cudaMalloc(&P->arena, P->arena_bytes));
@@ -1066,7 +1065,7 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
   for (size_t i = 0; i < P->raws.size(); ++i) {
     Raw& r = P->raws[i];
     r.desc.base = base + raw_off[i].raw;
-    r.stats = reinterpret_cast<float*>(base + raw_off[i].stats);
+    r.stats = reinterpret_cast<stat_t*>(base + raw_off[i].stats);
     r.scale = reinterpret_cast<float*>(base + raw_off[i].scale);
     r.shift = reinterpret_cast<float*>(base + raw_off[i].shift);
   }
@@ -1141,42 +1140,17 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
       case G_NORM_ACT: {
         Raw& r = P->raws[op.raw];
         const GOp& cop = P->gops[r.conv_op];
-        bool fuse_fin = false;
-        FinalizeParams fin_params{};
-        if (op.norm.kind != V2V_NORM_NONE) {
-          XOp f; f.kind = X_FINALIZE;
-          FinalizeParams& fp = f.fin;
+        FinalizeParams fp{};
+        const bool has_norm = op.norm.kind != V2V_NORM_NONE;
+        if (has_norm) {
           fp.stats = r.stats; fp.Cs = r.C; fp.C = op.cC; fp.c_off = op.n_off; fp.scale_stride = r.C;
-          fp.N = r.N; fp.tiles_per_img = r.tiles_per_img; fp.num_phases = r.num_phases;
+          fp.N = r.N; fp.tiles_per_img = 1; fp.num_phases = 1;
           fp.count = (double)r.H * r.W; fp.instance = (op.norm.kind == V2V_NORM_INSTANCE);
           const int cout1 = cop.conv.Cout - cop.conv.Cout2;
           V2V_REQUIRE(op.n_off == 0 || (cop.conv.Cout2 > 0 && op.n_off == cout1), V2V_ERR_UNSUPPORTED,
                       "a raw slice must start at channel 0 or at the second weight set");
           fp.gamma = op.norm.gamma; fp.beta = op.norm.beta; fp.conv_bias = op.n_off == 0 ? cop.conv.bias : cop.conv.bias2;
-          fp.running_mean = op.norm.running_mean; fp.running_var = op.norm.running_var;
-          fp.num_batches_tracked = reinterpret_cast<long long*>(op.norm.num_batches_tracked);
-          fp.momentum = op.norm.momentum; fp.eps = op.norm.eps; fp.scale = r.scale; fp.shift = r.shift;
-          fp.mean_out = r.mean; fp.rstd_out = r.rstd;
-          // fusing the finalize into the apply prologue measured slower than the separate launch: opt-in only
-          { const char* ef = getenv("V2V_FUSE_FINALIZE"); fuse_fin = (ef && ef[0] == '1') && r.N <= 8; }
-          fin_params = fp;
-          // Default: the finalisation runs in the tail of the producing tcgen05 conv launch (grid barrier, see conv_umma.cu).
-          // A slice normalised more than once (defer_last emits two normalise passes of the same raw) is finalised -- and
-          // its running statistics updated -- once.  V2V_FUSED_FIN=0 restores one stats_finalize launch per normalise pass.
-          static const bool tail_ok = [] { const char* e = getenv("V2V_FUSED_FIN"); return !(e && e[0] == '0'); }();
-          GOp& prod = P->gops[r.conv_op];
-          bool in_tail = false;
-          if (tail_ok && !fuse_fin && P->impl == V2V_IMPL_UMMA) {
-            for (int q = 0; q < prod.kp.n_fin; ++q)
-              if (prod.kp.fin[q].c_off == fp.c_off && prod.kp.fin[q].gamma == fp.gamma && prod.kp.fin[q].running_mean == fp.running_mean) in_tail = true;
-            if (!in_tail && prod.kp.n_fin < 2) {
-              prod.kp.fin[prod.kp.n_fin++] = fp;
-              prod.kp.fin_counter = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(r.stats) +
-                                                                    (size_t)r.stats_rows * 2 * r.C * sizeof(float));
-              in_tail = true;
-            }
-          }
-          if (!fuse_fin && !in_tail) P->xops.push_back(f);
+          fp.momentum = op.norm.momentum; fp.eps = op.norm.eps;
         } else if (cop.conv.bias != nullptr) {
           // norm-less biased conv (FlowNet2's conv / deconv / predict_flow units): the normalise pass runs with scale 1 and
           // shift = bias, written here and after every repack
@@ -1192,17 +1166,36 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
           ap.raw = r.desc;
           ap.raw.base = reinterpret_cast<uint8_t*>(r.desc.base) + (size_t)op.n_off * r.desc.elem_bytes();
           ap.raw.Cvalid = op.cC;                                               // channel slice, full row stride
-          ap.scale = (op.norm.kind != V2V_NORM_NONE || cop.conv.bias != nullptr) ? r.scale + op.n_off : nullptr;
+          ap.scale = (has_norm || cop.conv.bias != nullptr) ? r.scale + op.n_off : nullptr;
           ap.shift = r.shift + op.n_off;
           ap.scale_stride = r.C;
           ap.act = op.act; ap.slope = op.slope;
           ap.n_add = 0;
           for (int k = 0; k < 2; ++k) if (op.add[k] >= 0) ap.add[ap.n_add++] = P->acts[P->values[op.add[k]].bufs[0]];
           ap.out = P->acts[vo.bufs[m]]; ap.pad_mode = P->act_pad_mode[vo.bufs[m]];
-          ap.fused = fuse_fin ? 1 : 0; ap.fin = fin_params;
-          ap.update_running = 0;
-          if (fuse_fin && std::find(r.running_done.begin(), r.running_done.end(), op.n_off) == r.running_done.end()) {
-            ap.update_running = 1; r.running_done.push_back(op.n_off);
+          ap.fused = 0; ap.update_running = 0; ap.fin = fp;
+          if (has_norm) {
+            // Train-mode side effects (running statistics; the scale / shift / mean / rstd arrays the backward and the
+            // grid-stride fallback read) happen ONCE per (raw, slice), however many normalise passes read it (two output
+            // layouts; defer_last emits the same slice twice).
+            const bool first = std::find(r.running_done.begin(), r.running_done.end(), op.n_off) == r.running_done.end();
+            FinalizeParams side = fp;
+            side.running_mean = op.norm.running_mean; side.running_var = op.norm.running_var;
+            side.num_batches_tracked = reinterpret_cast<long long*>(op.norm.num_batches_tracked);
+            side.scale = r.scale; side.shift = r.shift; side.mean_out = r.mean; side.rstd_out = r.rstd;
+            if (first) {
+              // scale / shift come from the tail of the producing tcgen05 launch (last-CTA finalisation, conv_umma.cu); the
+              // SIMT cross-check implementation and a third slice of one raw use a stats_finalize launch instead
+              static const bool tail_ok = [] { const char* e = getenv("V2V_FUSED_FIN"); return !(e && e[0] == '0'); }();
+              GOp& prod = P->gops[r.conv_op];
+              if (tail_ok && P->impl == V2V_IMPL_UMMA && prod.kp.n_fin < 2) {
+                prod.kp.fin[prod.kp.n_fin++] = side;
+                prod.kp.fin_counter = reinterpret_cast<unsigned int*>(reinterpret_cast<uint8_t*>(r.stats) + (size_t)r.N * 2 * r.C * sizeof(stat_t));
+              } else {
+                XOp f; f.kind = X_FINALIZE; f.fin = side; P->xops.push_back(f);
+              }
+              r.running_done.push_back(op.n_off);
+            }
           }
           P->xops.push_back(a);
         }

@@ -72,8 +72,15 @@ struct ConvPhase {
   int oy_add, ox_add;           // output coordinate offset (transposed-conv sub-pixel phase)
 };
 
+// Norm statistics of a raw conv output: ONE row per image, stats[n][0][c] = sum, stats[n][1][c] = sum of squares, as 64-bit
+// fixed point (sum * 2^20, sumsq * 2^16) accumulated with integer atomics by the conv epilogue: integer addition is
+// associative, so the result does not depend on the CTA order (deterministic) and needs no second reduction pass.
+typedef unsigned long long stat_t;
+#define V2V_STAT_SUM_SCALE 1048576.0f
+#define V2V_STAT_SQ_SCALE 65536.0f
+
 struct FinalizeParams {
-  const float* stats;      // [rows][2][Cs]
+  const stat_t* stats;     // [N][2][Cs]
   int Cs, C;               // stats channel stride, channels
   int N, tiles_per_img, num_phases;
   double count;            // elements per channel per image
@@ -116,13 +123,15 @@ struct ConvKernelParams {
   int tile_dx;                       // x distance between consecutive M tiles (TW, or TW - (kw - 1) for kx-GEMM heads)
   int headkx;                        // > 0: small-Cout head as a GEMM over (kx, channel) columns: N = kw * Cout accumulator
                                      // columns per INPUT pixel, taps over ky only; the epilogue sums the kw shifted columns
-  int a_exact;                       // precise plans: the input values are exact in bf16 (one-hot labels, edge maps): the lo
-                                     // half of A is all zero, so it is neither fetched nor multiplied (2 MMAs per K block)
-  // fused statistics finalisation: after its last tile every CTA arrives on a grid-wide counter; once all have, CTA b
-  // finalises channels b, b + grid, ... of up to two norm slices (no separate stats_finalize launches)
+  // Statistics finalisation in the tail of the launch: the CTA that takes the last ticket of a counter (zeroed with the
+  // statistics rows before every run) turns the completed rows of up to two norm slices into scale / shift (and the
+  // train-mode side effects).  No grid barrier: every other CTA has already exited.
   int n_fin;
   FinalizeParams fin[2];
   unsigned int* fin_counter;
+  int a_exact;                       // precise plans: the input values are exact in bf16 (one-hot labels, edge maps): the lo
+                                     // half of A is all zero, so it is neither fetched nor multiplied (2 MMAs per K block)
+
   ConvPhase phases[V2V_MAX_PHASES];
   ConvGroup groups[V2V_MAX_TAPS];
   // epilogue
@@ -131,7 +140,7 @@ struct ConvKernelParams {
   int out_H, out_W, out_C;           // destination extent / channel stride
   void* out;                         // EPI_RAW_STATS: bf16 NHWC raw; EPI_ACT_BF16: ActDesc base (see out_act)
   ActDesc out_act;                   // EPI_ACT_BF16 destination
-  float* stats;                      // [tile rows][2][stats_C] partial (sum, sumsq); may be null
+  stat_t* stats;                     // [N][2][stats_C] fixed-point (sum, sumsq), see FinalizeParams; may be null
   int stats_C;
   const float* bias;                 // may be null
   const float* bias2; int Cout1;     // fused heads: channels >= Cout1 take bias2[j - Cout1]
@@ -169,8 +178,8 @@ struct ApplyParams {
   ActDesc add[2];          // interior is read (any padding / parity)
   ActDesc out;
   int pad_mode;            // PadMode of out's halo
-  int fused;               // 1: compute scale/shift in the prologue from `fin` (no separate finalize launch)
-  int update_running;      // 1: this launch also applies the train-mode running-stat side effect
+  int fused;               // (unused: the block-prologue variant measured 2x slower than reading the arrays, profiles/README.md)
+  int update_running;
   FinalizeParams fin;
 };
 
@@ -228,7 +237,7 @@ struct CompositeParams {
   int use_warp;            // 0: img_final = img_raw (use_raw_only / no_flow)
 };
 
-cudaError_t launch_raw_stats(const RawDesc& raw, float* stats, int stats_C, cudaStream_t stream);
+cudaError_t launch_raw_stats(const RawDesc& raw, stat_t* stats, int stats_C, cudaStream_t stream);
 
 // x = hi + lo with hi = bf16(x), lo = bf16(x - hi)
 __device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& lo) {
@@ -237,6 +246,7 @@ __device__ __forceinline__ void split_bf16(float x, bf16& hi, bf16& lo) {
 }
 cudaError_t launch_stats_finalize(const FinalizeParams& p, cudaStream_t stream);
 cudaError_t launch_norm_apply(const ApplyParams& p, cudaStream_t stream);
+bool norm_apply_uses_rows(const ApplyParams& p);
 cudaError_t launch_import_nchw(const ImportParams& p, cudaStream_t stream);
 cudaError_t launch_export_nchw(const ExportParams& p, cudaStream_t stream);
 cudaError_t launch_pack_weights(const PackParams& p, cudaStream_t stream);
