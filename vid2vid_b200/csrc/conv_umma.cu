@@ -121,7 +121,7 @@ struct UnitIter {
 
 struct MmaCtx {
   uint8_t* sG; uint8_t* sBres;
-  uint64_t *g_full, *g_empty, *bres_full, *bres_empty, *tmem_full, *tmem_empty;
+  uint64_t *g_full, *g_empty, *bres_full, *bres_empty, *tmem_full, *tmem_empty, *b_full, *b_empty;
   uint32_t tmem_base, acc_cols;
   int group_bytes, b_tx, NS, t_first, t_step;
 };
@@ -145,6 +145,86 @@ __device__ __forceinline__ void issue_taps(const ConvKernelParams& p, uint32_t t
       }
       first = 1u;
     }
+  }
+}
+
+// One (tap, K block) of MMAs for one accumulator: KMMA K=16 steps x the operand passes of the arithmetic mode.
+template <int KMMA>
+__device__ __forceinline__ void issue_tap(uint32_t tmem_d, uint32_t al, uint32_t bl, uint32_t a_hi, uint32_t b_hi, uint32_t idesc,
+                                          uint32_t& first, int ps_step, uint32_t a_half16, uint32_t b_half16) {
+  for (int ps = 0; ps < 3; ps += ps_step) {
+    const uint64_t ad = ((uint64_t)a_hi << 32) | (al + (ps == 1 ? a_half16 : 0u)), bd = ((uint64_t)b_hi << 32) | (bl + (ps == 2 ? b_half16 : 0u));
+    umma_bf16(tmem_d, ad, bd, idesc, first);
+    if (KMMA >= 2) umma_bf16(tmem_d, ad + 2, bd + 2, idesc, 1u);
+    if (KMMA >= 4) {
+      umma_bf16(tmem_d, ad + 4, bd + 4, idesc, 1u);
+      umma_bf16(tmem_d, ad + 6, bd + 6, idesc, 1u);
+    }
+    first = 1u;
+  }
+}
+
+// ring2 issue loop (one elected lane).  K loop of a unit: steps (tap group, K block); per step ONE patch slot (MG tiles) from
+// the A ring and ceil(R / TB) weight chunks from the B ring; tap r of the step reads the patch advanced by
+// (r / RW) * PW + (r % RW) rows.
+template <int KMMA>
+__device__ __forceinline__ void mma_role_ring2(const ConvKernelParams& p, const MmaCtx& cx) {
+  const uint32_t idesc = make_idesc_bf16(128, p.BN);
+  const int ps_step = p.split ? (p.a_exact ? 2 : 1) : 3;
+  const uint32_t a_half16 = (uint32_t)(p.a_half_bytes >> 4), b_half16 = (uint32_t)(p.b_half_bytes >> 4);
+  const uint32_t a_hi = (uint32_t)(make_kmajor_desc(0, p.sbo_a_bytes, p.layout_type) >> 32);
+  const uint32_t b_hi = (uint32_t)(make_kmajor_desc(0, p.sbo_bytes, p.layout_type) >> 32);
+  const uint32_t a_lo0 = (uint32_t)make_kmajor_desc(0, p.sbo_a_bytes, p.layout_type);
+  const uint32_t b_lo0 = (uint32_t)make_kmajor_desc(0, p.sbo_bytes, p.layout_type);
+  const uint32_t row16 = (uint32_t)(p.row_bytes >> 4), prow16 = (uint32_t)((p.PW * p.row_bytes) >> 4), btap16 = (uint32_t)(cx.b_tx >> 4);
+  const uint32_t sB_u32 = smem_u32(cx.sBres);
+  int as = 0, bs = 0, acc = 0, it = 0;
+  uint32_t apar = 0, bpar = 0, accpar = 0;
+  const int RH = p.R / p.RW;                              // patch rows of taps
+  UnitIter un;
+  un.init(p, cx.t_first, cx.t_step);
+  for (; un.valid(p); ++it) {
+    const ConvPhase ph = p.phases[un.phase];
+    un.next(p);
+    const int nsteps = (ph.group_end - ph.group_begin) * p.cblocks;
+    mbar_wait(&cx.tmem_empty[acc], accpar ^ 1);
+    tcgen05_fence_after();
+    const uint32_t tmem_d0 = cx.tmem_base + acc * p.MG * cx.acc_cols;
+    uint32_t first = 0;
+    for (int st = 0; st < nsteps; ++st) {
+      mbar_wait(&cx.g_full[as], apar);
+      tcgen05_fence_after();
+      const uint32_t a_base16 = a_lo0 + ((smem_u32(cx.sG + (size_t)as * p.MG * p.a_slot_bytes) & 0x3FFFF) >> 4);
+      uint32_t first_step = first;
+      uint32_t bchunk16 = 0;
+      int tin = 0, r = 0;                                       // tap index inside the current weight chunk / inside the step
+      for (int ky = 0; ky < RH; ++ky) {
+        for (int kx = 0; kx < p.RW; ++kx, ++r) {
+          if (tin == 0) {
+            mbar_wait(&cx.b_full[bs], bpar);
+            tcgen05_fence_after();
+            bchunk16 = b_lo0 + (((sB_u32 + (uint32_t)bs * (uint32_t)p.b_slot_bytes) & 0x3FFFF) >> 4);
+          }
+          const uint32_t al0 = a_base16 + (uint32_t)ky * prow16 + (uint32_t)kx * row16, bl = bchunk16 + (uint32_t)tin * btap16;
+          for (int j = 0; j < p.MG; ++j) {
+            uint32_t f = first_step;
+            issue_tap<KMMA>(tmem_d0 + j * cx.acc_cols, al0 + (uint32_t)j * (uint32_t)(p.a_slot_bytes >> 4), bl, a_hi, b_hi, idesc, f, ps_step,
+                            a_half16, b_half16);
+          }
+          first_step = 1u;
+          if (++tin == p.TB || r == p.R - 1) {                      // chunks hold TB taps; the last one of a step may be short
+            tin = 0;
+            umma_commit(&cx.b_empty[bs]);                          // this weight chunk is free when the MMAs above retire
+            if (++bs == p.SBr) { bs = 0; bpar ^= 1; }
+          }
+        }
+      }
+      first = 1u;
+      umma_commit(&cx.g_empty[as]);                                // ... and so is the patch slot
+      if (++as == p.SG) { as = 0; apar ^= 1; }
+    }
+    umma_commit(&cx.tmem_full[acc]);                               // accumulator(s) complete
+    if (++acc == cx.NS) { acc = 0; accpar ^= 1; }
   }
 }
 
@@ -236,11 +316,12 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // group slots: [SG][ CG activation patches | CG streamed weight slots ], then the resident weight set (if any)
-  const int slot_b = p.b_resident ? 0 : p.b_slot_bytes;
+  // ring2: [SG patch slots of MG tiles][SBr weight slots]
+  const int slot_b = (p.b_resident || p.ring2) ? 0 : p.b_slot_bytes;
   const int group_bytes = p.CG * (p.MG * p.a_slot_bytes + slot_b);
   uint8_t* sG = smem;
   uint8_t* sBres = sG + (size_t)p.SG * group_bytes;
-  float* red = reinterpret_cast<float*>(sBres + (p.b_resident ? (size_t)p.SB * p.b_slot_bytes : 0));
+  float* red = reinterpret_cast<float*>(sBres + (p.ring2 ? (size_t)p.SBr * p.b_slot_bytes : (p.b_resident ? (size_t)p.SB * p.b_slot_bytes : 0)));
   uint64_t* bars = reinterpret_cast<uint64_t*>(red + p.EG * kRedFloatsPerGroup);
   uint64_t* g_full = bars;
   uint64_t* g_empty = g_full + p.SG;
@@ -249,6 +330,8 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = bres_empty + 1;     // [kMaxGroups]
   uint64_t* tmem_empty = tmem_full + kMaxGroups;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + kMaxGroups);
+  uint64_t* b_full = reinterpret_cast<uint64_t*>(tmem_slot + 2);       // ring2: weight ring barriers [8] + [8]
+  uint64_t* b_empty = b_full + 8;
   const int NS = p.EG > 1 ? p.EG : 2;       // accumulator stages in TMEM
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -261,6 +344,7 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
     for (int i = 0; i < p.SG; ++i) { mbar_init(&g_full[i], 1); mbar_init(&g_empty[i], 1); }
     mbar_init(bres_full, 1); mbar_init(bres_empty, 1);
+    if (p.ring2) for (int i = 0; i < p.SBr; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < NS; ++i) { mbar_init(&tmem_full[i], 1); mbar_init(&tmem_empty[i], 4); }
     fence_barrier_init();
   }
@@ -291,6 +375,38 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int nhalfA = (p.split && !p.a_exact) ? 2 : 1;      // activation halves (an exact-in-bf16 input has no lo half)
       UnitIter un;
       un.init(p, t_first, t_step);
+      if (p.ring2) {
+        int as = 0, bs = 0;
+        uint32_t apar = 0, bpar = 0;
+        for (; un.valid(p); un.next(p)) {
+          const ConvPhase ph = p.phases[un.phase];
+          const int x0 = un.x0(p), y0 = un.y0(p), n0 = un.n0(p);
+          for (int g = ph.group_begin; g < ph.group_end; ++g) {
+            const ConvGroup grp = p.groups[g];
+            for (int cb = 0; cb < p.cblocks; ++cb) {
+              uint8_t* abase = sG + (size_t)as * p.MG * p.a_slot_bytes;
+              mbar_wait(&g_empty[as], apar ^ 1);
+              mbar_expect_tx(&g_full[as], (uint32_t)(nhalfA * p.MG * a_tx));
+              for (int j = 0; j < p.MG; ++j)
+                for (int hf = 0; hf < nhalfA; ++hf)
+                  tma_load_5d(abase + (size_t)j * p.a_slot_bytes + (size_t)hf * p.a_half_bytes, &tmA, &g_full[as], hf * p.Cp + cb * p.kc,
+                              x0 + j * p.TW + grp.dx, y0 + grp.dy, grp.plane, un.img);
+              if (++as == p.SG) { as = 0; apar ^= 1; }
+              for (int t0 = 0; t0 < p.R; t0 += p.TB) {
+                uint8_t* bbase = sBres + (size_t)bs * p.b_slot_bytes;
+                const int nt = min(p.TB, p.R - t0);
+                mbar_wait(&b_empty[bs], bpar ^ 1);
+                mbar_expect_tx(&b_full[bs], (uint32_t)(nhalf * nt * b_tx));
+                for (int hf = 0; hf < nhalf; ++hf)
+                  for (int t = 0; t < nt; ++t)
+                    tma_load_2d(bbase + (size_t)hf * p.b_half_bytes + (size_t)t * b_tx, &tmB, &b_full[bs],
+                                hf * p.Khalf + (grp.tap0 + t0 + t) * p.Cp + cb * p.kc, n0);
+                if (++bs == p.SBr) { bs = 0; bpar ^= 1; }
+              }
+            }
+          }
+        }
+      } else
       for (int pit = 0; un.valid(p); un.next(p), ++pit) {
         TRACE(0, pit, 0);
         const ConvPhase ph = p.phases[un.phase];
@@ -337,9 +453,15 @@ conv_umma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    MmaCtx cx{sG, sBres, g_full, g_empty, bres_full, bres_empty, tmem_full, tmem_empty, tmem_base, acc_cols,
+    MmaCtx cx{sG, sBres, g_full, g_empty, bres_full, bres_empty, tmem_full, tmem_empty, b_full, b_empty, tmem_base, acc_cols,
               group_bytes, b_tx, NS, t_first, t_step};
-    if (p.dbg & 8) {
+    if (p.ring2) {
+      if (elect_one_sync()) {
+        if (p.kmma == 4) mma_role_ring2<4>(p, cx);
+        else if (p.kmma == 2) mma_role_ring2<2>(p, cx);
+        else mma_role_ring2<1>(p, cx);
+      }
+    } else if (p.dbg & 8) {
       mma_role<true>(p, cx);                   // whole warp walks the loop (uniform datapath), elect.sync per MMA group
     } else if (elect_one_sync()) {
       mma_role<false>(p, cx);                  // one elected lane runs the whole loop
@@ -620,9 +742,11 @@ int device_sm_count() {
 
 cudaError_t launch_conv_umma(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvKernelParams& p,
                              cudaStream_t stream) {
-  const size_t smem = (size_t)p.SG * p.CG * ((size_t)p.MG * p.a_slot_bytes + (p.b_resident ? 0 : p.b_slot_bytes)) +
-                      (p.b_resident ? (size_t)p.SB * p.b_slot_bytes : 0) + 1024 /*align*/ + (size_t)p.EG * kRedFloatsPerGroup * sizeof(float) +
-                      (2 * p.SG + 2 + 2 * kMaxGroups + 2) * sizeof(uint64_t);
+  const size_t operands = p.ring2 ? (size_t)p.SG * p.MG * p.a_slot_bytes + (size_t)p.SBr * p.b_slot_bytes
+                                  : (size_t)p.SG * p.CG * ((size_t)p.MG * p.a_slot_bytes + (p.b_resident ? 0 : p.b_slot_bytes)) +
+                                        (p.b_resident ? (size_t)p.SB * p.b_slot_bytes : 0);
+  const size_t smem = operands + 1024 /*align*/ + (size_t)p.EG * kRedFloatsPerGroup * sizeof(float) +
+                      (2 * p.SG + 2 + 2 * kMaxGroups + 2 + 16) * sizeof(uint64_t);
   static size_t configured = 0;
   if (smem > configured) {
     cudaError_t e = cudaFuncSetAttribute(conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

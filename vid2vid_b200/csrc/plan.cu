@@ -564,10 +564,59 @@ static void fill_conv_params(v2v_plan* P, GOp& op) {
     set_error("internal: 2-D patch conv does not fit (a %d b %d)", kp.a_slot_bytes, kp.b_slot_bytes);
   }
   kp.SB = kp.b_resident ? nB : 0;
+  // Decoupled operand rings for streamed-weight layers whose coupled stages forced a narrow K block or N tile (see
+  // ConvKernelParams::ring2): 64-byte rows halve the TMA request efficiency (measured ~0.3 smem rows per clock whatever the row
+  // size) and N < 128 MMAs waste issue slots, which is what bounded 1024->1024 (kc 32) and every streamed precise layer.
+  kp.ring2 = 0;
+  {
+    static const bool ring2_ok = [] { const char* e = getenv("V2V_RING2"); return !(e && e[0] == '0'); }();
+    const int kc_nat = std::min(kp.Cp, 64), bn_nat = std::min(128, round_up(op.conv.Cout, 32));
+    // Measured (profiles/r02c_*): a gain for precise plans (108->96 2.20 -> 1.58 ms, 128->128 1.68 -> 1.26, 1024->1024 4.92 ->
+    // 4.18); bf16 plans and the exact-input finest stem were faster with the coupled stages (fewer barrier round trips per
+    // MMA), so they keep them.
+    if (ring2_ok && sp == 2 && !kp.a_exact && P->impl == V2V_IMPL_UMMA && !kp.b_resident && g.R >= 3 && !g.headkx && g.n_phases == 1 &&
+        op.kind != G_HEAD && (kp.kc < kc_nat || kp.BN < bn_nat)) {
+      const int nhA = 2;
+      const int a_half = round_up(kp.PW * kp.PH * kc_nat * 2, 1024);
+      bool found = false;
+      int f_bn = 0, f_mg = 0, f_tb = 0, f_sbr = 0;
+      // N tile: the natural one unless that leaves SMs idle (512->512 @32x64: 64 tiles of 128 columns on 148 SMs)
+      const long long units_nat = (long long)kp.N * kp.tiles_x * kp.tiles_y * ((op.conv.Cout + bn_nat - 1) / bn_nat);
+      const int bns[2] = {bn_nat, bn_nat / 2}, mgs[2] = {kp.MG, 1};
+      const bool too_few = units_nat * 5 < (long long)sms * 3;      // 512->512 @32x64: 64 tiles on 148 SMs -- the coupled BN 64 path wins (0.89 vs 1.00 ms)
+      for (int bi = 0; bi < 2 && !found && !too_few; ++bi) {
+        const int bn = bns[bi];
+        if (bn < 32 || bn % 32 || (bi == 1 && bn < 64)) continue;
+        for (int mi = 0; mi < 2 && !found; ++mi) {
+          const int mg = mgs[mi];
+          if (mg < 1 || kp.tiles_x % mg || 2 * mg * std::max(32, bn) > 512 || (mi == 1 && mgs[0] == 1)) continue;
+          // taps per weight chunk: as many as leave >= 3 chunks in flight (a commit + barrier round trip per chunk costs the
+          // issuing thread ~500 cycles: fewer, longer chunks)
+          for (int tb = std::min(g.R, 4); tb >= 1 && !found; --tb) {
+            const int chunk = sp * round_up(tb * bn * kc_nat * 2, 1024);
+            const int sbr = (budget - 2 * mg * nhA * a_half) / chunk;
+            if (sbr >= 3) { found = true; f_bn = bn; f_mg = mg; f_tb = tb; f_sbr = std::min(8, sbr); }
+          }
+        }
+      }
+      if (found) {
+        kp.ring2 = 1; kp.kc = kc_nat; kp.BN = f_bn; kp.MG = f_mg; kp.TB = f_tb; kp.SBr = f_sbr;
+        kp.cblocks = kp.Cp / kp.kc; kp.row_bytes = kp.kc * 2; kp.kmma = kp.kc / 16;
+        kp.layout_type = kp.kc == 64 ? 2 : (kp.kc == 32 ? 4 : 6);
+        kp.sbo_bytes = 8 * kp.row_bytes; kp.sbo_a_bytes = p2d ? kp.PW * kp.row_bytes : 8 * kp.row_bytes;
+        kp.a_half_bytes = a_half; kp.a_slot_bytes = nhA * a_half;
+        kp.b_half_bytes = round_up(kp.TB * kp.BN * kp.row_bytes, 1024); kp.b_slot_bytes = sp * kp.b_half_bytes;
+        kp.n_tiles = (kp.Cout + kp.BN - 1) / kp.BN;
+        kp.m_total = kp.N * (kp.tiles_x / kp.MG) * kp.tiles_y;
+        kp.total_tiles = kp.m_total * kp.n_tiles * g.n_phases;
+        kp.b_resident = 0; kp.SB = 0; kp.CG = 1; kp.SG = 2; kp.SA = 2;
+      }
+    }
+  }
   // Commit groups.  Measured on B200: every tcgen05.commit / barrier round trip costs the issuing warp ~500 cycles
   // during which the tensor pipe idles (its queue is shallow), so CG consecutive K-loop steps share one barrier pair;
   // a step issues R * kmma MMAs of max(40, BN/2) cycles each (smem operand fetch floors small-N MMAs at ~40 cycles).
-  {
+  if (!kp.ring2) {
     const int slot = kp.MG * kp.a_slot_bytes + (kp.b_resident ? 0 : kp.b_slot_bytes);
     const int avail = budget - (kp.b_resident ? nB * kp.b_slot_bytes : 0);
     const int nslots = std::max(2, avail / slot);
@@ -1367,10 +1416,10 @@ int64_t v2v_plan_describe(const v2v_plan* P_, char* buf, int64_t cap) {
     snprintf(t, sizeof(t),
              "%s{\"kind\":%d,\"Cin\":%d,\"Cout\":%d,\"k\":[%d,%d],\"stride\":%d,\"transposed\":%d,\"in\":%d,\"TH\":%d,\"TW\":%d,"
              "\"R\":%d,\"groups\":%d,\"phases\":%d,\"grid\":[%d,%d],\"out\":[%d,%d],"
-             "\"BN\":%d,\"kc\":%d,\"MG\":%d,\"CG\":%d,\"SG\":%d,\"resident\":%d,\"EG\":%d,\"units\":%d,\"split\":%d}",
+             "\"BN\":%d,\"kc\":%d,\"MG\":%d,\"CG\":%d,\"SG\":%d,\"resident\":%d,\"EG\":%d,\"units\":%d,\"split\":%d,\"ring2\":%d,\"TB\":%d,\"SBr\":%d}",
              first ? "" : ",", (int)op.kind, op.conv.Cin, op.conv.Cout, op.conv.kh, op.conv.kw, op.conv.stride, op.conv.transposed,
              op.value_in, g.TH, g.TW, g.R, g.n_groups, g.n_phases, g.grid_h, g.grid_w, g.out_h, g.out_w,
-             kp.BN, kp.kc, kp.MG, kp.CG, kp.SG, kp.b_resident, kp.EG, kp.total_units, kp.split);
+             kp.BN, kp.kc, kp.MG, kp.CG, kp.SG, kp.b_resident, kp.EG, kp.total_units, kp.split, kp.ring2, kp.TB, kp.SBr);
     s += t;
     first = false;
   }

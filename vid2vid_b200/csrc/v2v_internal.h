@@ -120,6 +120,11 @@ struct ConvKernelParams {
   int a_half_bytes, b_half_bytes;    // byte offset of the lo half inside an A / B slot
   int Khalf;                         // taps * Cp: column offset of the lo half in the packed weight matrix
   int out_f32;                       // EPI_RAW_STATS: raw output element type (1 = fp32)
+  // Decoupled operand rings (ring2): the activation patch of a K-loop step (MG tiles) and its weights travel through separate
+  // rings -- SG patch slots, SBr weight slots of TB taps each (b_slot_bytes per slot) -- so a step's R taps need not fit in
+  // shared memory next to the patch: 64-channel K blocks (128-byte rows, the efficient TMA / MMA operand) and 128-wide N
+  // tiles stay available to streamed-weight layers and to precise (hi/lo) plans.
+  int ring2, TB, SBr;
   int tile_dx;                       // x distance between consecutive M tiles (TW, or TW - (kw - 1) for kx-GEMM heads)
   int headkx;                        // > 0: small-Cout head as a GEMM over (kx, channel) columns: N = kw * Cout accumulator
                                      // columns per INPUT pixel, taps over ky only; the epilogue sums the kw shifted columns
