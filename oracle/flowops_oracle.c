@@ -5,9 +5,11 @@
  *                        (+ output shape arithmetic correlation_cuda.cc:25-38)
  *   resample2d_forward   .../resample2d_package/resample2d_kernel.cu:15-64
  *   channelnorm_forward  .../channelnorm_package/channelnorm_kernel.cu:18-60
- * Parity pin: the reference holds no tests or vectors for these ops ("parity unpinned" by reference
- * tests); tests/test_flowops_oracle.py cross-checks this file against independent PyTorch formulations
- * (grid_sample(align_corners=True, border), an unfold/einsum correlation, torch.norm).
+ * Parity pin: the reference holds no tests or vectors for these ops and the CUDA sources cannot be built or run in the build
+ * container ("parity unpinned" by reference tests).  tests/test_flowops_oracle.py pins this file (i) against independent
+ * PyTorch formulations (grid_sample(align_corners=True, border), shifted dot products, torch.norm) and (ii) against
+ * known-answer vectors computed by hand from the CUDA sources (floor / clamp rules, displacement-to-channel order, the
+ * 1 / (C k k) normalisation and the per-lane + shuffle-tree fp32 summation order).
  * Build: see oracle/Makefile -> oracle/_build/libflowops_oracle.so
  */
 #include <math.h>
