@@ -207,3 +207,26 @@ def test_cfg4_finest_scale_properties():
     recon = img_raw * weight + warp * (1 - weight)
     d = (recon - img_final).abs()[sel]
     assert d.max().item() < 1e-5, d.max().item()
+
+
+def test_running_statistics_update_once_per_forward():
+    """nn.BatchNorm2d's train-mode side effect happens exactly once per layer per forward -- also for the layer whose raw
+    output feeds two normalise passes (CompositeLocalGenerator: model_down_img's last norm is applied with the img and the
+    flow coarse features, networks.py:298-305) -- and moves running_mean towards the batch mean."""
+    import torch.nn as nn
+    c = C.CASES['gl_small_s1']
+    net = det_fill_(C.build_module(c), seed=c['seed']).cuda()
+    inp, img_prev, mask = (t.cuda() for t in C.gen_inputs(c['label_nc'], c['h'], c['w'], c['seed']))
+    coarse = tuple(t.cuda() for t in coarse_feats(c))
+    with torch.no_grad():
+        net(inp, img_prev, mask, *coarse, False)
+        torch.cuda.synchronize()
+        bns = [(n, m) for n, m in net.named_modules() if isinstance(m, nn.BatchNorm2d)]
+        assert len(bns) > 10
+        for n, m in bns:
+            assert int(m.num_batches_tracked.item()) == 1, (n, int(m.num_batches_tracked.item()))
+            assert m.running_mean.abs().max().item() > 0 and torch.isfinite(m.running_var).all(), n
+        net(inp, img_prev, mask, *coarse, False)
+        torch.cuda.synchronize()
+        for n, m in bns:
+            assert int(m.num_batches_tracked.item()) == 2, n

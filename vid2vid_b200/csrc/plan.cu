@@ -44,6 +44,17 @@ void set_error(const char* fmt, ...) {
     }                                \
   } while (0)
 
+// Makes the plan's device current for the duration of an entry point and restores the caller's device afterwards (the
+// reference supports several GPUs per process: models/vid2vid_model_G.py:126-133; PyTorch's current device must not change
+// behind the caller's back).
+struct DeviceGuard {
+  int prev = -1; bool changed = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) changed = (cudaSetDevice(dev) == cudaSuccess);
+  }
+  ~DeviceGuard() { if (changed) cudaSetDevice(prev); }
+};
+
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline size_t round_up_sz(size_t a, size_t b) { return (a + b - 1) / b * b; }
 // padded channel count of an activation buffer: one K block of min(C,64) channels per shared-memory row
@@ -876,6 +887,7 @@ int v2v_plan_backward(v2v_plan* P, void* const* io_ptrs, void* const* grad_io_pt
                       void* const* param_grads, int n_params, v2v_stream_t stream_) {
   V2V_REQUIRE(P && P->finalized && P->train, V2V_ERR_STATE, "plan not finalized in training mode");
   V2V_REQUIRE(n_io >= P->n_slots && io_ptrs && grad_io_ptrs, V2V_ERR_INVALID, "need %d io / gradient pointers", P->n_slots);
+  DeviceGuard guard(P->device);
   std::unordered_map<const void*, void*> pg;
   for (int i = 0; i < n_params; ++i) if (params[i] && param_grads[i]) pg[params[i]] = param_grads[i];
   return run_backward(P, io_ptrs, grad_io_ptrs, pg, reinterpret_cast<cudaStream_t>(stream_));
@@ -1066,7 +1078,7 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   V2V_REQUIRE(P && !P->finalized, V2V_ERR_STATE, "plan null or already finalized");
   int rc = lower(P); if (rc) return rc;
-  V2V_CUDA(cudaSetDevice(P->device));
+  DeviceGuard guard(P->device);
 
   // ---- size the arena
   size_t off = 0;
@@ -1305,6 +1317,7 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
 
 int v2v_plan_repack(v2v_plan* P, v2v_stream_t stream_) {
   V2V_REQUIRE(P && P->finalized, V2V_ERR_STATE, "plan not finalized");
+  DeviceGuard guard(P->device);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   for (auto& op : P->gops)
     if (op.kind == G_CONV || op.kind == G_CONV_ACT || op.kind == G_HEAD) { int rc = pack_one(op, stream); if (rc) return rc; }
@@ -1315,6 +1328,7 @@ int v2v_plan_repack(v2v_plan* P, v2v_stream_t stream_) {
 int v2v_plan_run(v2v_plan* P, void* const* io_ptrs, int n_io, int use_graph, v2v_stream_t stream_) {
   V2V_REQUIRE(P && P->finalized, V2V_ERR_STATE, "plan not finalized");
   V2V_REQUIRE(n_io >= P->n_slots && io_ptrs, V2V_ERR_INVALID, "need %d io pointers, got %d", P->n_slots, n_io);
+  DeviceGuard guard(P->device);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   V2V_CUDA(cudaMemcpyAsync(P->io_dev, io_ptrs, sizeof(void*) * P->n_slots, cudaMemcpyHostToDevice, stream));
   if (use_graph & 2) {        // recomputation before a backward: same results, no running-statistics side effect
@@ -1357,6 +1371,7 @@ int v2v_plan_profile(v2v_plan* P, void* const* io_ptrs, int n_io, v2v_stream_t s
                      float* ms, double* macs, int* n_ops) {
   V2V_REQUIRE(P && P->finalized, V2V_ERR_STATE, "plan not finalized");
   V2V_REQUIRE(n_io >= P->n_slots && io_ptrs && kinds && ms && macs && n_ops, V2V_ERR_INVALID, "bad profile arguments");
+  DeviceGuard guard(P->device);
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
   V2V_CUDA(cudaMemcpyAsync(P->io_dev, io_ptrs, sizeof(void*) * P->n_slots, cudaMemcpyHostToDevice, stream));
   const int n = std::min<int>(max_ops, (int)P->xops.size());

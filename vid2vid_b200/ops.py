@@ -31,6 +31,16 @@ def _ck(rc):
     L.LAUNCHES[0] += 1
 
 
+def _on(t):
+    """Context for a launch on tensor t's device (correlation.py:21 `with torch.cuda.device_of(input1)`); pair it with
+    _st(t), the caller's current stream on THAT device."""
+    return torch.cuda.device_of(t)
+
+
+def _st(t):
+    return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
 def _p(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
 
@@ -46,8 +56,7 @@ def correlation(input1, input2, pad_size=20, kernel_size=1, max_displacement=20,
     out = torch.empty((n, oc.value, oh.value, ow.value), device=input1.device, dtype=torch.float32)
     with torch.cuda.device_of(input1):
         _ck(L.lib().v2v_correlation_forward(_p(input1), _p(input2), _p(out), n, c, h, w, pad_size, kernel_size,
-                                                max_displacement, stride1, stride2, corr_multiply,
-                                                L.current_stream_ptr()))
+                                                max_displacement, stride1, stride2, corr_multiply, _st(input1)))
     return out
 
 
@@ -71,8 +80,7 @@ def resample2d(input1, input2, kernel_size=1):
     b, _, h, w = input2.shape
     out = torch.empty((b, d, h, w), device=input1.device, dtype=torch.float32)
     with torch.cuda.device_of(input1):
-        _ck(L.lib().v2v_resample2d_forward(_p(input1), _p(input2), _p(out), b, d, h, w, ih, iw, kernel_size,
-                                               L.current_stream_ptr()))
+        _ck(L.lib().v2v_resample2d_forward(_p(input1), _p(input2), _p(out), b, d, h, w, ih, iw, kernel_size, _st(input1)))
     return out
 
 
@@ -93,7 +101,7 @@ def channelnorm(input1, norm_deg=2):
     b, c, h, w = input1.shape
     out = torch.empty((b, 1, h, w), device=input1.device, dtype=torch.float32)
     with torch.cuda.device_of(input1):
-        _ck(L.lib().v2v_channelnorm_forward(_p(input1), _p(out), b, c, h, w, norm_deg, L.current_stream_ptr()))
+        _ck(L.lib().v2v_channelnorm_forward(_p(input1), _p(out), b, c, h, w, norm_deg, _st(input1)))
     return out
 
 
@@ -113,8 +121,8 @@ def _resample_fwd(image, flow, align_corners):
     _chk(image, flow)
     b, c, h, w = image.shape
     out = torch.empty_like(image)
-    _ck(L.lib().v2v_resample_forward(_p(image), _p(flow), _p(out), b, c, h, w, int(align_corners),
-                                         L.current_stream_ptr()))
+    with _on(image):
+        _ck(L.lib().v2v_resample_forward(_p(image), _p(flow), _p(out), b, c, h, w, int(align_corners), _st(image)))
     return out
 
 
@@ -154,8 +162,8 @@ def onehot_edges(label_map, inst_map, label_nc, use_instance):
     _chk(label_map, inst)
     b, t, _, h, w = label_map.shape
     out = torch.empty((b, t, label_nc + int(bool(use_instance)), h, w), device=label_map.device, dtype=torch.float32)
-    _ck(L.lib().v2v_onehot_edges(_p(label_map), _p(inst), _p(out), b * t, label_nc, int(bool(use_instance)), h, w,
-                                     L.current_stream_ptr()))
+    with _on(label_map):
+        _ck(L.lib().v2v_onehot_edges(_p(label_map), _p(inst), _p(out), b * t, label_nc, int(bool(use_instance)), h, w, _st(label_map)))
     return out
 
 
@@ -187,7 +195,8 @@ def _avgpool3s2_fwd(x):
     h, w = x.shape[-2:]
     planes = x.numel() // (h * w)
     out = torch.empty(tuple(x.shape[:-2]) + ((h - 1) // 2 + 1, (w - 1) // 2 + 1), device=x.device, dtype=torch.float32)
-    _ck(L.lib().v2v_avgpool3s2(_p(x), _p(out), planes, h, w, L.current_stream_ptr()))
+    with _on(x):
+        _ck(L.lib().v2v_avgpool3s2(_p(x), _p(out), planes, h, w, _st(x)))
     return out
 
 
@@ -198,7 +207,8 @@ def fg_mask(real_As, ts, fg_labels):
     b, T, c, h, w = real_As.shape
     out = torch.empty((b, 1, h, w), device=real_As.device, dtype=torch.float32)
     arr = (C.c_int * len(fg_labels))(*fg_labels)
-    _ck(L.lib().v2v_fg_mask(_p(real_As), _p(out), b, T, c, h, w, ts, arr, len(fg_labels), L.current_stream_ptr()))
+    with _on(real_As):
+        _ck(L.lib().v2v_fg_mask(_p(real_As), _p(out), b, T, c, h, w, ts, arr, len(fg_labels), _st(real_As)))
     return out
 
 

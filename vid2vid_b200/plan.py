@@ -148,12 +148,16 @@ class Plan:
                            s_final + 1, s_raw_out + 1)
 
     # ---- execution
+    def _stream(self):
+        """The caller's current stream ON THE PLAN'S DEVICE (which need not be PyTorch's current device)."""
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
     def finalize(self):
-        L.check(L.lib().v2v_plan_finalize(self._h, L.current_stream_ptr()))
+        L.check(L.lib().v2v_plan_finalize(self._h, self._stream()))
         self.finalized = True
 
     def repack(self):
-        L.check(L.lib().v2v_plan_repack(self._h, L.current_stream_ptr()))
+        L.check(L.lib().v2v_plan_repack(self._h, self._stream()))
 
     def _io_array(self, io):
         arr = (C.c_void_p * self.n_slots)()
@@ -168,7 +172,7 @@ class Plan:
         arr = self._io_array(io)
         # the first execution is eager (lazy module loading, attribute setup); graphs from the second on
         g = 2 if recompute else int(use_graph and self._graph_ok)
-        L.check(L.lib().v2v_plan_run(self._h, arr, self.n_slots, g, L.current_stream_ptr()))
+        L.check(L.lib().v2v_plan_run(self._h, arr, self.n_slots, g, self._stream()))
         L.LAUNCHES[0] += self.num_kernels
         if not recompute:
             self._graph_ok = True
@@ -183,7 +187,7 @@ class Plan:
         for i, (p_, g_) in enumerate(zip(params, grads)):
             pa[i], ga[i] = p_.data_ptr(), (g_.data_ptr() if g_ is not None else None)
         L.check(L.lib().v2v_plan_backward(self._h, self._io_array(io), self._io_array(gio), self.n_slots, pa, ga, n,
-                                          L.current_stream_ptr()))
+                                          self._stream()))
         L.LAUNCHES[0] += 3 * self.num_kernels
 
     def profile(self, io=None):
@@ -195,7 +199,7 @@ class Plan:
             arr[i] = t.data_ptr() if t is not None else None
         n = self.num_kernels + 4
         kinds, ms, macs, cnt = (C.c_int * n)(), (C.c_float * n)(), (C.c_double * n)(), C.c_int()
-        L.check(L.lib().v2v_plan_profile(self._h, arr, self.n_slots, L.current_stream_ptr(), n, kinds, ms, macs,
+        L.check(L.lib().v2v_plan_profile(self._h, arr, self.n_slots, self._stream(), n, kinds, ms, macs,
                                          C.byref(cnt)))
         return [(kinds[i], ms[i], macs[i]) for i in range(cnt.value)]
 
