@@ -65,6 +65,45 @@ UNITS = [
                           BN(32), nn.LeakyReLU(0.2, True), nn.Conv2d(32, 32, 4, stride=1, padding=2), BN(32), nn.LeakyReLU(0.2, True)],
      (2, 9, 20, 28)),
 ]
+# shapes that reach the tensor-core backward (csrc/wgrad_umma.cu needs >= 64 padded channels on both operands and buffer rows of
+# >= 16 pixels; the data gradient runs as a forward conv on conv_umma_kernel for every stride-1 / stride-2 / transposed conv)
+TENSOR_UNITS = [
+    ('t_c3_128', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(128, 128, 3), BN(128), nn.ReLU(True)], (1, 128, 12, 72)),      # KP 64, ragged row
+    ('t_c3_64_192', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(64, 192, 3), BN(192), nn.ReLU(True)], (2, 64, 10, 40)),    # partial M tile, KP 32
+    ('t_c3_192_64', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(192, 64, 3), BN(64), nn.ReLU(True)], (1, 192, 10, 40)),    # 64-channel OUT
+    ('t_stem108', lambda: NW._stem(108, 64, BN), (1, 108, 10, 70)),                                                       # 7x7, 49 taps
+    ('t_down128', lambda: NW._down(64, 128, BN), (1, 64, 16, 80)),                                                        # stride 2
+    ('t_up128', lambda: NW._up(128, 64, BN), (1, 128, 8, 40)),                                                            # transposed
+    ('t_d_k4s1', lambda: [nn.Conv2d(64, 128, 4, stride=1, padding=2), BN(128), nn.LeakyReLU(0.2, True)], (1, 64, 12, 40)),
+    ('t_d_k4s2', lambda: [nn.Conv2d(64, 128, 4, stride=2, padding=2), BN(128), nn.LeakyReLU(0.2, True)], (1, 64, 16, 80)),      # cropped transposed conv
+    ('t_resblock128', lambda: [NW.ResnetBlock(128, 'reflect', BN)], (1, 128, 16, 32)),
+]
+
+
+@pytest.mark.parametrize('name,build,shape', TENSOR_UNITS, ids=[u[0] for u in TENSOR_UNITS])
+def test_tensor_core_backward_units(name, build, shape, monkeypatch):
+    """Gradients of the tcgen05 backward (data gradient as a forward conv + fold, weight gradient with pixels as the K
+    dimension) against fp64 autograd, and against the fp32 SIMT backward kernels of the same plan description."""
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(1)).cuda()
+    runner = det_fill_(NW.SequentialRunner(build()), seed=5).cuda()
+    runner.precision = 'precise'
+    names, ours, refs, out, ref = _grads(runner, x)
+    monkeypatch.setenv('V2V_BWD', 'simt')
+    simt = det_fill_(NW.SequentialRunner(build()), seed=5).cuda()
+    simt.precision = 'precise'
+    _, ours_simt, _, _, _ = _grads(simt, x)
+    bad = []
+    for n, o, r, so in zip(names, ours, refs, ours_simt):
+        if n.endswith('.bias') and r.abs().max().item() < 1e-6:
+            continue
+        try:
+            _cmp('%s tensor vs simt d/d %s' % (name, n), o, so, tol=2e-4, l2=5e-5)
+            _cmp('%s d/d %s' % (name, n), o, r, tol=None if name == 't_resblock128' else 2e-3, l2=8e-2 if name == 't_resblock128' else 1e-3)
+        except AssertionError as e:
+            bad.append(str(e)[:160])
+    assert not bad, bad
+
+
 HEADS = [
     ('head_tanh', lambda: NW._stem(8, 16, BN), lambda: NW._head(16, 3, nn.Tanh()), 1.0, (1, 8, 12, 20)),
     ('head_flow_x20', lambda: NW._stem(8, 16, BN), lambda: NW._head(16, 2), 20.0, (1, 8, 12, 20)),

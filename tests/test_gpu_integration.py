@@ -158,6 +158,11 @@ def test_reference_model_G_with_networks_swapped_in():
             det_fill_(getattr(ref, 'netG%d' % s), seed=40 + s)
             getattr(ours, 'netG%d' % s).load_state_dict(getattr(ref, 'netG%d' % s).state_dict())
             assert isinstance(getattr(ref, 'netG%d' % s), our_networks._Planned)
+            # The reference driver knows nothing of our "the one-hot input is exact in bf16" hint (model_g.py sets it on the
+            # finest scale and the plan then skips the all-zero lo half: same value, different tiling and summation order).
+            # With random weights the recurrence amplifies a 1e-6 difference ~30x per frame, so the two
+            # drivers are compared on identical kernels: then they must agree bit for bit.
+            getattr(ours, 'netG%d' % s).input_exact_bf16 = False
         seq = synth_label_sequence(5, 128, 256, label_nc=35, block=8, seed=3).cuda()
         for t in range(3):
             A = seq[:, t:t + 3]
@@ -165,6 +170,6 @@ def test_reference_model_G_with_networks_swapped_in():
             fo, _ = ours.inference(A, None, A)
             d = (fr - fo).abs()
             print('frame %d reference driver + our networks vs our driver: max|d|=%.3e' % (t, d.max().item()))
-            assert torch.isfinite(fr).all() and d.max().item() < 2e-3
+            assert torch.isfinite(fr).all() and d.max().item() == 0.0
     finally:
         ref_G.networks = old

@@ -1,0 +1,42 @@
+"""Kernel-time breakdown of one training step (torch.profiler / CUPTI): python tools/profile_train.py [workload] [out.txt]"""
+import os, sys
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+sys.path.insert(0, ROOT)
+import torch
+import bench
+from vid2vid_b200 import flownet as FN
+from vid2vid_b200.model_d import Vid2VidModelD
+from vid2vid_b200.model_g import Vid2VidModelG
+from vid2vid_b200.trainer import Trainer
+from vid2vid_b200.utils import make_opt, synth_label_sequence
+
+wl_name = sys.argv[1] if len(sys.argv) > 1 else 'cfg3'
+out_path = sys.argv[2] if len(sys.argv) > 2 else os.path.join(ROOT, 'gpurun_out', 'profile_train_%s.txt' % wl_name)
+wl = bench.WORKLOADS[wl_name]
+H, Wd = wl['H'], wl['W']
+opt = make_opt(label_nc=35, use_instance=True, fg=True, fg_labels=[26], n_scales_spatial=wl['n_scales'], ngf=wl['ngf'], num_D=3,
+               n_scales_temporal=2, n_frames_D=3, isTrain=True, no_vgg=True, gpu_ids=[0], n_frames_total=30, dataroot='datasets/Cityscapes/', loadSize=Wd)
+torch.manual_seed(1234)
+G = Vid2VidModelG().initialize(opt); D = Vid2VidModelD().initialize(opt); F = FN.FlowNet().initialize(opt)
+tr = Trainer(opt, G, D, F, world=1)
+tG = opt.n_frames_G
+T = 12
+A = synth_label_sequence(T, H, Wd, label_nc=35, block=64, seed=0).cuda()
+g = torch.Generator().manual_seed(77)
+coarse = torch.rand(T, 3, H // 16, Wd // 16, generator=g) * 2 - 1
+B = torch.nn.functional.interpolate(coarse, size=(H, Wd), mode='bilinear', align_corners=False).view(1, T, 3, H, Wd).cuda()
+for t in range(5):
+    tr.step(A[:, t:t + tG], B[:, t:t + tG], A[:, t:t + tG])
+torch.cuda.synchronize()
+from torch.profiler import profile, ProfilerActivity
+with profile(activities=[ProfilerActivity.CUDA]) as prof:
+    t = 5
+    tr.step(A[:, t:t + tG], B[:, t:t + tG], A[:, t:t + tG])
+    torch.cuda.synchronize()
+rows = sorted(prof.key_averages(), key=lambda r: -r.device_time_total)
+tot = sum(r.device_time_total for r in rows)
+with open(out_path, 'w') as f:
+    f.write('one %s training step: %.1f ms of kernel time over %d launches\n' % (wl_name, tot / 1e3, sum(r.count for r in rows)))
+    for r in rows[:40]:
+        f.write('%8.2f ms %5.1f %% %6d x  %s\n' % (r.device_time_total / 1e3, 100 * r.device_time_total / tot, r.count, r.key[:110]))
+print(open(out_path).read())

@@ -380,7 +380,7 @@ __global__ void grad_export_kernel(const float* __restrict__ src, float* __restr
   }
 }
 // dz = dy * act'(out) for a bias + activation conv epilogue unit (EPI_ACT_BF16): out = the forward activation buffer
-__global__ void convact_bwd_kernel(const float* __restrict__ dy, ActDesc out, int act, float slope, float* __restrict__ dz, int C) {
+__global__ void convact_bwd_kernel(const float* __restrict__ dy, ActDesc out, int act, float slope, float* __restrict__ dz, int C, int dz_C) {
   const size_t total = (size_t)out.N * out.H * out.W * C;
   for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(idx % C);
@@ -392,7 +392,7 @@ __global__ void convact_bwd_kernel(const float* __restrict__ dy, ActDesc out, in
     float d = dy[idx];
     if (act == ACT_RELU) d = o > 0.f ? d : 0.f;
     else if (act == ACT_LRELU) d = o > 0.f ? d : d * slope;
-    dz[idx] = d;
+    dz[(idx / C) * dz_C + c] = d;
   }
 }
 
@@ -426,6 +426,12 @@ cudaError_t launch_conv_bwd(const BwdConv& p, cudaStream_t s) {
   return cudaGetLastError();
 }
 
+cudaError_t launch_bias_grad(const float* dy, int dy_C, long long npix, int C, float* dbias, float* dbias2, int C1, cudaStream_t s) {
+  dim3 grid(C, (unsigned)std::max(1LL, std::min(64LL, npix / 4096)));
+  bias_grad_kernel<<<grid, 256, 0, s>>>(dy, dy_C, npix, C, dbias, dbias2, C1);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_norm_bwd(const NormBwd& p, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(p.sums, 0, sizeof(float) * 2 * p.N * p.C, s);
   if (e != cudaSuccess) return e;
@@ -455,8 +461,8 @@ cudaError_t launch_grad_export(const float* src, float* g, int N, int C_src, int
   grad_export_kernel<<<grid1d((size_t)N * C * H * W), 256, 0, s>>>(src, g, N, C_src, c_off, C, (size_t)H * W);
   return cudaGetLastError();
 }
-cudaError_t launch_convact_bwd(const float* dy, const ActDesc& out, int act, float slope, float* dz, int C, cudaStream_t s) {
-  convact_bwd_kernel<<<grid1d((size_t)out.N * out.H * out.W * C), 256, 0, s>>>(dy, out, act, slope, dz, C);
+cudaError_t launch_convact_bwd(const float* dy, const ActDesc& out, int act, float slope, float* dz, int C, int dz_C, cudaStream_t s) {
+  convact_bwd_kernel<<<grid1d((size_t)out.N * out.H * out.W * C), 256, 0, s>>>(dy, out, act, slope, dz, C, dz_C);
   return cudaGetLastError();
 }
 

@@ -46,12 +46,37 @@ struct CompositeBwd {
   float* d_raw; float* d_flow; float* d_weight; float* d_fg;                                          // written
 };
 
+// Tensor-core weight gradient (csrc/wgrad_umma.cu): G[tap][m][n] = sum_pixels OUT[pixel][m] * IN[pixel @ tap][n]
+struct WgradTap { int8_t plane, dy, dx, pad_; };      // IN buffer coordinate of grid pixel (y, x): plane, (y + dy, x + dx)
+struct WgradParams {
+  int N, gh, gw;               // driving grid = pixels of OUT
+  int KP, kmma;                // pixels per K chunk (64 / 32 / 16), MMAs (16 pixels each) per chunk
+  int xsegs;                   // ceil(gw / KP) chunks per grid row
+  int out_padt, out_padl;      // OUT buffer halo: buffer coordinate of grid pixel (0, 0)
+  int out_C, in_C;             // padded channel counts (multiples of 64): the lo half starts at channel coordinate C
+  int Mblocks, Nblocks;        // 64-channel blocks per M tile (2, or 1 for a 64-channel OUT) / per N tile (1 or 2)
+  int m_tiles, n_tiles, ntaps, ksplit;
+  int chunks_total, chunks_per_unit;
+  int split;                   // 1: [hi | lo] operands, three MMAs per K step
+  int stages;
+  int lbo_bytes, sbo_bytes;    // MN-major descriptor strides: between 64-channel blocks (one box) / between 8-pixel groups (1024)
+  WgradTap taps[V2V_MAX_TAPS];
+  float* stage;                // [ntaps][Mp][Np] fp32, zeroed by the launcher
+  int Mp, Np;
+};
+size_t wgrad_stage_bytes(const WgradParams& p);
+cudaError_t launch_wgrad_umma(const CUtensorMap& tmOut, const CUtensorMap& tmIn, const WgradParams& p, int M, int M1, int Nv,
+                              float* dw, float* dw2, cudaStream_t s);
+cudaError_t launch_fold_add(const float* src, int Cs, int PH, int PW, float* dx, int N, int H, int W, int C, int pad, int reflect,
+                            cudaStream_t s);
+cudaError_t launch_bias_grad(const float* dy, int dy_C, long long npix, int C, float* dbias, float* dbias2, int C1, cudaStream_t s);
+
 cudaError_t launch_conv_bwd(const BwdConv& p, cudaStream_t s);
 cudaError_t launch_norm_bwd(const NormBwd& p, cudaStream_t s);
 cudaError_t launch_head_bwd(const HeadBwd& p, cudaStream_t s);
 cudaError_t launch_composite_bwd(const CompositeBwd& p, cudaStream_t s);
 cudaError_t launch_grad_import(const float* g, float* dst, int N, int C_src, int c_off, int C, int H, int W, cudaStream_t s);
 cudaError_t launch_grad_export(const float* src, float* g, int N, int C_src, int c_off, int C, int H, int W, cudaStream_t s);
-cudaError_t launch_convact_bwd(const float* dy, const ActDesc& out, int act, float slope, float* dz, int C, cudaStream_t s);
+cudaError_t launch_convact_bwd(const float* dy, const ActDesc& out, int act, float slope, float* dz, int C, int dz_C, cudaStream_t s);
 
 }  // namespace v2v

@@ -143,7 +143,15 @@ __global__ void pack_weights_kernel(PackParams p) {
     if (p.headkx) { kx = row / p.Cout; co = row - kx * p.Cout; ky = t; }        // kx-GEMM head: one tap per filter ROW
     else { ky = p.tap_ky[t]; kx = p.tap_kx[t]; }
     float v = 0.f;
-    if (c < p.Cin) {
+    if (p.dgrad) {
+      // data-gradient form of a stride-1 conv: rows = forward INPUT channels, K columns = forward OUTPUT channels, taps flipped;
+      // the forward tensors are [Cout_f = p.Cin][Cin_f = p.Cout][kh][kw], the second set starting at forward output channel Cout1
+      if (c < p.Cin) {
+        const int fy = p.kh - 1 - ky, fx = p.kw - 1 - kx;
+        if (p.w2 && c >= p.Cout1) v = p.w2[((((size_t)(c - p.Cout1)) * p.Cout + co) * p.kh + fy) * p.kw + fx];
+        else v = p.w[((((size_t)c) * p.Cout + co) * p.kh + fy) * p.kw + fx];
+      }
+    } else if (c < p.Cin) {
       if (p.w2 && co >= p.Cout1) {
         v = p.w2[((((size_t)(co - p.Cout1)) * p.Cin + c) * p.kh + ky) * p.kw + kx];
       } else {

@@ -258,9 +258,10 @@ struct Raw {
   std::vector<int> running_done;   // channel offsets whose running stats already have an updating launch
   float* mean = nullptr; float* rstd = nullptr;   // training plans: saved statistics [N][C]
   float* graw = nullptr;           // training plans: gradient of the raw tensor, dense NHWC fp32 (channel stride desc.C)
+  bool no_stats = false;           // backward sub-plans: the conv output feeds no norm layer
 };
 
-enum GKind { G_INPUT, G_CONV, G_NORM_ACT, G_CONV_ACT, G_HEAD, G_EXPORT, G_COMPOSITE, G_CONCAT, G_CORR };
+enum GKind { G_INPUT, G_CONV, G_NORM_ACT, G_CONV_ACT, G_HEAD, G_EXPORT, G_COMPOSITE, G_CONCAT, G_CORR, G_RAWIN };
 struct GOp {
   GKind kind;
   // input
@@ -278,6 +279,10 @@ struct GOp {
   std::vector<int> cat_in;   // G_CONCAT: source values in channel order
   int value_in2 = -1;        // G_CORR: second operand
   int corr[5] = {0, 0, 0, 0, 0};   // pad, kernel, max_disp, stride1, stride2
+  const float* ext_raw = nullptr; int ext_C = 0;   // G_RAWIN: dense NHWC fp32 tensor owned by the parent plan (a gradient buffer)
+  // backward sub-plans: pack the forward weights [Cout_f][Cin_f][kh][kw] (+ second set from output channel dg_Cout1 on) transposed
+  // and flipped, so that this forward conv computes the data gradient of that conv
+  int pack_dgrad = 0; const float* dg_w2 = nullptr; int dg_Cout1 = 0;
   // lowered
   bf16* wpacked = nullptr; int Ktotal = 0, Cp = 0;
   float* gdz = nullptr;      // training plans: G_HEAD / G_CONV_ACT pre-activation gradient, dense NHWC fp32 [.][Cout]
@@ -305,7 +310,28 @@ struct XOp {
 
 using namespace v2v;
 
+// Tensor-core backward of one conv op of a training plan (precise plans, tcgen05 implementation):
+//   data gradient   = a FORWARD conv of the output gradient, run by a sub-plan on conv_umma_kernel:
+//                       mode 1  stride-1 conv          -> stride-1 conv, zero pad k-1, weights transposed + flipped; the result covers
+//                                                         the padded input extent and fold_add folds the (reflect) halo back
+//                       mode 2  transposed conv (s 2)  -> stride-2 conv of dY with the same weight tensor
+//                       mode 3  stride-2 conv          -> transposed conv of dY with the same weight tensor
+//   weight gradient = wgrad_umma_kernel over the two activation buffers the passes above left in place
+struct BwdUnit {
+  int gop = -1, mode = 0;
+  v2v_plan* child = nullptr;
+  int child_raw = -1;
+  bool wgrad = false;
+  CUtensorMap tmOut{}, tmIn{};
+  WgradParams wg{};
+  int M = 0, M1 = 0, Nv = 0;
+};
+
 struct v2v_plan {
+  std::vector<BwdUnit> bwd;     // indexed through bwd_of[gop]
+  std::vector<int> bwd_of;
+  float* wg_stage = nullptr;    // staging buffer of the weight-gradient kernel (largest unit)
+
   int device = 0;
   int impl = V2V_IMPL_UMMA;
   int precise = 0;            // V2V_PREC_BF16X3: split activations / weights, fp32 raw tensors, 3 MMAs per K block
@@ -333,6 +359,12 @@ struct v2v_plan {
   cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t graph_stream = nullptr;
 };
+
+
+extern "C" int v2v_plan_create(int device, int conv_impl, v2v_plan** out);
+extern "C" int v2v_g_conv(v2v_plan* p, int value_in, const v2v_conv_desc* c, int* raw_out);
+extern "C" int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_);
+extern "C" { static int new_value(v2v_plan* p, int N, int H, int W, int C); }
 
 namespace v2v {
 
@@ -670,6 +702,7 @@ static int pack_one(const GOp& op, cudaStream_t stream) {
   for (int ky = 0; ky < op.conv.kh; ++ky)
     for (int kx = 0; kx < op.conv.kw; ++kx) { pp.tap_ky[ky * op.conv.kw + kx] = (int8_t)ky; pp.tap_kx[ky * op.conv.kw + kx] = (int8_t)kx; }
   pp.out = op.wpacked;
+  if (op.pack_dgrad) { pp.dgrad = 1; pp.w2 = op.dg_w2; pp.Cout1 = op.dg_Cout1; }
   V2V_CUDA(launch_pack_weights(pp, stream));
   return 0;
 }
@@ -714,7 +747,7 @@ static int alloc_training(v2v_plan* P, cudaStream_t stream) {
     const GOp& op = P->gops[i];
     if (op.kind == G_HEAD || op.kind == G_CONV_ACT) {
       const Value& vin = P->values[op.value_in];
-      go[i] = take((size_t)vin.N * op.geom.out_h * op.geom.out_w * op.conv.Cout * 4);
+      go[i] = take((size_t)vin.N * op.geom.out_h * op.geom.out_w * round_up(op.conv.Cout, 8) * 4);   // channel stride: multiple of 8
       cmax = std::max(cmax, op.conv.Cout);
     } else if (op.kind == G_COMPOSITE) {
       const CompositeParams& c = op.comp;
@@ -736,6 +769,107 @@ static int alloc_training(v2v_plan* P, cudaStream_t stream) {
   P->gslot.assign(P->n_slots, nullptr);
   for (int sidx = 0; sidx < P->n_slots; ++sidx) if (so[sidx] != (size_t)-1) P->gslot[sidx] = reinterpret_cast<float*>(b + so[sidx]);
   P->gsums = reinterpret_cast<float*>(b + sums_off);
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------ training: tensor-core backward units
+static bool bwd_tensor_enabled() {      // read per plan, so that one process can build both variants (tests)
+  const char* e = getenv("V2V_BWD");
+  return !(e && !strcmp(e, "simt"));
+}
+
+static int build_backward_units(v2v_plan* P, cudaStream_t stream) {
+  P->bwd_of.assign(P->gops.size(), -1);
+  if (!P->precise || P->impl != V2V_IMPL_UMMA || !bwd_tensor_enabled()) return 0;
+  size_t stage_max = 0;
+  for (size_t i = 0; i < P->gops.size(); ++i) {
+    const GOp& op = P->gops[i];
+    if (op.kind != G_CONV && op.kind != G_CONV_ACT && op.kind != G_HEAD) continue;
+    const v2v_conv_desc& c = op.conv;
+    const Value& vin = P->values[op.value_in];
+    const int oh = op.geom.out_h, ow = op.geom.out_w;
+    BwdUnit u; u.gop = (int)i;
+    v2v_conv_desc cd{};
+    cd.Cin = c.Cout; cd.Cout = c.Cin; cd.kh = c.kh; cd.kw = c.kw; cd.pad_mode = V2V_PAD_ZERO; cd.weight = c.weight;
+    if (!c.transposed && c.stride == 1 && c.kh == c.kw && c.pad <= c.kh - 1 && (c.pad_mode != V2V_PAD_REFLECT || c.pad < std::min(vin.H, vin.W))) {
+      u.mode = 1; cd.stride = 1; cd.pad = c.kh - 1;
+    } else if (c.transposed && c.Cout2 == 0) {
+      u.mode = 2; cd.stride = 2; cd.pad = c.pad;
+    } else if (!c.transposed && c.stride == 2 && c.Cout2 == 0 && c.kh == c.kw && 2 + 2 * c.pad - c.kh >= 0 && 2 * oh >= vin.H && 2 * ow >= vin.W) {
+      // the transposed conv is asked for exactly 2 oh x 2 ow outputs (output_padding 2 + 2 pad - k; for 4x4 / pad 2 that is one
+      // row more than nn.ConvTranspose2d would accept, the extra rows are simply cropped by fold_add)
+      u.mode = 3; cd.stride = 2; cd.pad = c.pad; cd.transposed = 1; cd.output_padding = 2 + 2 * c.pad - c.kh;
+    } else continue;
+    const float* dy = op.kind == G_CONV ? P->raws[op.raw].graw : op.gdz;
+    const int dy_C = op.kind == G_CONV ? P->raws[op.raw].desc.C : round_up(c.Cout, 8);
+    // ---- sub-plan: dY (dense fp32 NHWC) -> halo-padded split activation -> conv
+    v2v_plan* C = nullptr;
+    int rc = v2v_plan_create(P->device, P->impl, &C); if (rc) return rc;
+    C->precise = P->precise; C->allow_reuse = P->allow_reuse;
+    u.child = C;
+    GOp gi; gi.kind = G_RAWIN; gi.ext_raw = dy; gi.ext_C = dy_C;
+    gi.value_out = new_value(C, vin.N, oh, ow, c.Cout);
+    C->gops.push_back(gi);
+    rc = v2v_g_conv(C, gi.value_out, &cd, &u.child_raw);
+    if (!rc) {
+      C->raws[u.child_raw].no_stats = true;
+      if (u.mode == 1) { GOp& co = C->gops.back(); co.pack_dgrad = 1; co.dg_w2 = c.Cout2 > 0 ? c.weight2 : nullptr; co.dg_Cout1 = c.Cout - c.Cout2; }
+      rc = v2v_plan_finalize(C, reinterpret_cast<v2v_stream_t>(stream));
+    }
+    if (rc) { P->bwd.push_back(u); return rc; }
+    {
+      const Raw& cr = C->raws[u.child_raw];
+      const int eh = u.mode == 1 ? vin.H + 2 * c.pad : vin.H, ew = u.mode == 1 ? vin.W + 2 * c.pad : vin.W;
+      V2V_REQUIRE(cr.H >= eh && cr.W >= ew && (u.mode == 3 || (cr.H == eh && cr.W == ew)) && cr.C == c.Cin, V2V_ERR_STATE,
+                  "internal: data-gradient conv of op %d yields %dx%dx%d, expected %dx%dx%d", (int)i, cr.H, cr.W, cr.C, eh, ew, c.Cin);
+    }
+    // ---- weight gradient on the tensor cores: OUT (gradient side) x IN (activation side) over the driving grid
+    const ActDesc& a_dy = C->acts[C->values[gi.value_out].bufs[0]];
+    const ActDesc& a_x = P->acts[vin.bufs[op.req_index]];
+    const ActDesc& a_out = u.mode == 2 ? a_x : a_dy;
+    const ActDesc& a_in = u.mode == 2 ? a_dy : a_x;
+    const int kp = std::min(a_out.Wp, a_in.Wp) >= 64 ? 64 : (std::min(a_out.Wp, a_in.Wp) >= 32 ? 32 : (std::min(a_out.Wp, a_in.Wp) >= 16 ? 16 : 0));
+    const char* ewg = getenv("V2V_WGRAD");
+    const bool wg_ok = !(ewg && !strcmp(ewg, "simt"));
+    if (wg_ok && kp > 0 && a_out.C % 64 == 0 && a_in.C % 64 == 0 && !a_out.parity && a_out.split == a_in.split && c.kh * c.kw <= V2V_MAX_TAPS) {
+      WgradParams& w = u.wg;
+      w.N = vin.N; w.gh = u.mode == 2 ? vin.H : oh; w.gw = u.mode == 2 ? vin.W : ow;
+      w.KP = kp; w.kmma = kp / 16; w.xsegs = (w.gw + kp - 1) / kp;
+      w.out_padt = a_out.pad_t; w.out_padl = a_out.pad_l; w.out_C = a_out.C; w.in_C = a_in.C;
+      w.Mblocks = a_out.C >= 128 ? 2 : 1; w.Nblocks = a_in.C >= 128 ? 2 : 1;
+      w.m_tiles = (a_out.C + w.Mblocks * 64 - 1) / (w.Mblocks * 64); w.n_tiles = (a_in.C + w.Nblocks * 64 - 1) / (w.Nblocks * 64);
+      w.ntaps = c.kh * c.kw; w.split = a_out.split; w.Mp = a_out.C; w.Np = a_in.C;
+      // taps: IN buffer coordinate of grid pixel (y, x).  Stride 1: (y + ky, x + kx); stride 2 (IN in parity planes):
+      // plane (ky & 1, kx & 1), (y + ky / 2, x + kx / 2) -- as conv_geometry lays the forward taps out
+      const bool s2 = (u.mode != 1);
+      for (int ky = 0; ky < c.kh; ++ky)
+        for (int kx = 0; kx < c.kw; ++kx)
+          w.taps[ky * c.kw + kx] = s2 ? WgradTap{(int8_t)(((ky & 1) << 1) | (kx & 1)), (int8_t)(ky >> 1), (int8_t)(kx >> 1), 0}
+                                      : WgradTap{0, (int8_t)ky, (int8_t)kx, 0};
+      V2V_REQUIRE(!s2 || a_in.parity, V2V_ERR_STATE, "internal: stride-2 weight gradient needs a parity-plane operand");
+      const int stage_bytes = (w.split ? 2 : 1) * (2 + w.Nblocks) * kp * 128;
+      w.stages = std::max(2, std::min(6, kSmemBudget / stage_bytes));
+      w.lbo_bytes = kp * 128; w.sbo_bytes = 1024;
+      if (const char* e = getenv("V2V_WG_DESC")) sscanf(e, "%d,%d", &w.lbo_bytes, &w.sbo_bytes);      // descriptor experiments
+      w.chunks_total = w.N * w.gh * w.xsegs;
+      const int base_units = w.ntaps * w.m_tiles * w.n_tiles;
+      const int want = std::max(1, (2 * device_sm_count() + base_units - 1) / base_units);
+      w.chunks_per_unit = std::max(std::min(8, w.chunks_total), (w.chunks_total + want - 1) / want);
+      w.ksplit = (w.chunks_total + w.chunks_per_unit - 1) / w.chunks_per_unit;
+      u.M = u.mode == 2 ? c.Cin : c.Cout; u.M1 = u.mode == 2 ? c.Cin : c.Cout - c.Cout2; u.Nv = u.mode == 2 ? c.Cout : c.Cin;
+      rc = make_tmap_act(&u.tmOut, a_out, kp, 1, 64); if (rc) { P->bwd.push_back(u); return rc; }
+      rc = make_tmap_act(&u.tmIn, a_in, kp, 1, 64); if (rc) { P->bwd.push_back(u); return rc; }
+      u.wgrad = true;
+      stage_max = std::max(stage_max, wgrad_stage_bytes(w));
+    }
+    P->bwd_of[i] = (int)P->bwd.size();
+    P->bwd.push_back(u);
+  }
+  if (stage_max) {
+    V2V_CUDA(cudaMalloc(reinterpret_cast<void**>(&P->wg_stage), stage_max));
+    for (auto& u : P->bwd) u.wg.stage = P->wg_stage;
+  }
   return 0;
 }
 
@@ -761,6 +895,32 @@ static int run_backward(v2v_plan* P, void* const* io, void* const* gio, const st
     b.dx = input_needs ? vin.gval : nullptr;
     b.dw = grad_of(op.conv.weight); b.dw2 = b.w2 ? grad_of(op.conv.weight2) : nullptr;
     if (bias_grad) { b.dbias = grad_of(op.conv.bias); b.dbias2 = b.w2 ? grad_of(op.conv.bias2) : nullptr; }
+    const int ui = P->bwd_of.empty() ? -1 : P->bwd_of[&op - P->gops.data()];
+    if (ui >= 0) {
+      // tensor-core path: dY -> the sub-plan's halo-padded split activation; data gradient = its conv (+ fold); weight gradient
+      // = wgrad_umma over the two activation buffers
+      const BwdUnit& u = P->bwd[ui];
+      v2v_plan* C = u.child;
+      const bool need_w = (b.dw || b.dw2);
+      if (b.dx || (need_w && u.wgrad)) {
+        for (const XOp& x : C->xops) {
+          if (x.kind == X_CONV && !b.dx) continue;
+          int rc = run_xop(C, x, s); if (rc) return rc;
+        }
+      }
+      if (b.dx) {
+        const Raw& cr = C->raws[u.child_raw];
+        const int pad = u.mode == 1 ? op.conv.pad : 0;
+        V2V_CUDA(launch_fold_add(reinterpret_cast<const float*>(cr.desc.base), cr.desc.C, cr.H, cr.W, b.dx, vin.N, vin.H, vin.W, op.conv.Cin, pad,
+                                 (op.conv.pad_mode == V2V_PAD_REFLECT && pad > 0) ? 1 : 0, s));
+      }
+      if (need_w && u.wgrad) {
+        V2V_CUDA(launch_wgrad_umma(u.tmOut, u.tmIn, u.wg, u.M, u.M1, u.Nv, b.dw, b.dw2, s));
+        b.dw = nullptr; b.dw2 = nullptr;
+      }
+      b.dx = nullptr;
+      if (!b.dw && !b.dw2 && !b.dbias && !b.dbias2) return 0;
+    }
     V2V_CUDA(launch_conv_bwd(b, s));
     return 0;
   };
@@ -789,7 +949,7 @@ static int run_backward(v2v_plan* P, void* const* io, void* const* gio, const st
       case G_HEAD: {
         const Value& vin = P->values[op.value_in];
         HeadBwd h{};
-        h.N = vin.N; h.H = op.geom.out_h; h.W = op.geom.out_w; h.Cout = op.conv.Cout; h.dz = op.gdz; h.dz_C = op.conv.Cout;
+        h.N = vin.N; h.H = op.geom.out_h; h.W = op.geom.out_w; h.Cout = op.conv.Cout; h.dz = op.gdz; h.dz_C = round_up(op.conv.Cout, 8);
         for (int j = 0; j < op.conv.Cout; ++j) {
           const int slot = op.head[j].slot;
           h.out[j] = reinterpret_cast<const float*>(io[slot]);
@@ -799,7 +959,7 @@ static int run_backward(v2v_plan* P, void* const* io, void* const* gio, const st
           h.act[j] = op.head[j].act; h.scale[j] = op.head[j].scale;
         }
         V2V_CUDA(launch_head_bwd(h, s));
-        int rc = conv_bwd(op, op.gdz, op.conv.Cout, true); if (rc) return rc;
+        int rc = conv_bwd(op, op.gdz, round_up(op.conv.Cout, 8), true); if (rc) return rc;
         break;
       }
       case G_NORM_ACT: {
@@ -832,8 +992,8 @@ static int run_backward(v2v_plan* P, void* const* io, void* const* gio, const st
       }
       case G_CONV_ACT: {
         const Value& vo = P->values[op.value_out];
-        V2V_CUDA(launch_convact_bwd(vo.gval, P->acts[vo.bufs[0]], op.act, op.slope, op.gdz, op.conv.Cout, s));
-        int rc = conv_bwd(op, op.gdz, op.conv.Cout, true); if (rc) return rc;
+        V2V_CUDA(launch_convact_bwd(vo.gval, P->acts[vo.bufs[0]], op.act, op.slope, op.gdz, op.conv.Cout, round_up(op.conv.Cout, 8), s));
+        int rc = conv_bwd(op, op.gdz, round_up(op.conv.Cout, 8), true); if (rc) return rc;
         break;
       }
       case G_INPUT: {
@@ -841,6 +1001,7 @@ static int run_backward(v2v_plan* P, void* const* io, void* const* gio, const st
         if (gio[op.slot]) V2V_CUDA(launch_grad_export(v.gval, reinterpret_cast<float*>(gio[op.slot]), v.N, op.C_src, op.c_off, v.C, v.H, v.W, s));
         break;
       }
+      case G_RAWIN: break;
       case G_CONCAT: case G_CORR:
         set_error("backward through concat / correlation is not implemented (FlowNet2 runs under no_grad, models/flownet.py:26)");
         return V2V_ERR_UNSUPPORTED;
@@ -901,6 +1062,8 @@ int v2v_plan_destroy(v2v_plan* p) {
   if (p->garena) cudaFree(p->garena);
   if (p->train_stats) cudaFree(p->train_stats);
   if (p->io_dev) cudaFree(p->io_dev);
+  if (p->wg_stage) cudaFree(p->wg_stage);
+  for (auto& u : p->bwd) if (u.child) v2v_plan_destroy(u.child);
   delete p;
   return 0;
 }
@@ -1168,7 +1331,7 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
         if (op.kind == G_CONV) {
           Raw& r = P->raws[op.raw];
           kp.epi = EPI_RAW_STATS; kp.out = r.desc.base; kp.out_C = r.desc.C; kp.out_f32 = r.desc.f32;
-          kp.stats = r.stats; kp.stats_C = r.C; kp.bias = nullptr;
+          kp.stats = r.no_stats ? nullptr : r.stats; kp.stats_C = r.C; kp.bias = nullptr;
         } else if (op.kind == G_CONV_ACT) {
           const Value& vo = P->values[op.value_out];
           V2V_REQUIRE(vo.bufs.size() == 1 && P->act_pad_mode[vo.bufs[0]] != PAD_REFLECT, V2V_ERR_UNSUPPORTED,
@@ -1262,6 +1425,19 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
         }
         break;
       }
+      case G_RAWIN: {
+        const Value& vo = P->values[op.value_out];
+        for (size_t m = 0; m < vo.bufs.size(); ++m) {
+          XOp a; a.kind = X_APPLY;
+          ApplyParams& ap = a.app;
+          ap.raw.base = const_cast<float*>(op.ext_raw); ap.raw.N = vo.N; ap.raw.H = vo.H; ap.raw.W = vo.W; ap.raw.C = op.ext_C;
+          ap.raw.Cvalid = vo.C; ap.raw.f32 = 1;
+          ap.scale = nullptr; ap.shift = nullptr; ap.scale_stride = 0; ap.act = ACT_NONE; ap.slope = 0.f; ap.n_add = 0;
+          ap.out = P->acts[vo.bufs[m]]; ap.pad_mode = P->act_pad_mode[vo.bufs[m]];
+          P->xops.push_back(a);
+        }
+        break;
+      }
       case G_EXPORT: {
         XOp x; x.kind = X_EXPORT; x.exp.io = P->io_dev; x.exp.slot = op.slot; x.exp.in = P->acts[P->values[op.value_in].bufs[0]];
         P->xops.push_back(x);
@@ -1309,7 +1485,10 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
       }
     }
   }
-  if (P->train) { rc = alloc_training(P, stream); if (rc) return rc; }
+  if (P->train) {
+    rc = alloc_training(P, stream); if (rc) return rc;
+    rc = build_backward_units(P, stream); if (rc) return rc;
+  }
   V2V_CUDA(cudaStreamSynchronize(stream));
   P->finalized = true;
   return 0;
@@ -1322,6 +1501,7 @@ int v2v_plan_repack(v2v_plan* P, v2v_stream_t stream_) {
   for (auto& op : P->gops)
     if (op.kind == G_CONV || op.kind == G_CONV_ACT || op.kind == G_HEAD) { int rc = pack_one(op, stream); if (rc) return rc; }
   for (const auto& ba : P->bias_affines) V2V_CUDA(launch_bias_affine(ba.scale, ba.shift, ba.bias, ba.N, ba.C, ba.stride, stream));
+  for (auto& u : P->bwd) if (u.child) { int rc = v2v_plan_repack(u.child, stream_); if (rc) return rc; }
   return 0;
 }
 

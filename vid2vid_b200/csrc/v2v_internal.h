@@ -228,6 +228,8 @@ struct PackParams {
   int8_t tap_ky[V2V_MAX_TAPS], tap_kx[V2V_MAX_TAPS];   // filter coordinates of packed tap t
   int split;               // 1: [Cout][2][ntaps * Cp] (hi row half, then lo row half)
   int headkx;              // > 0 (= kw): rows are (kx * Cout + co), taps are the kh filter rows: out[kx * Cout + co][ky * Cp + c]
+  int dgrad;               // 1: w is the FORWARD tensor [Cin][Cout][kh][kw] of a stride-1 conv whose data gradient this conv computes
+                           //    (rows = forward input channels, K = forward output channels, taps flipped; w2 from K index Cout1 on)
   bf16* out;               // [Cout][ntaps * Cp]
 };
 
