@@ -432,8 +432,9 @@ def run_reference(args, rank, world):
 def run_train(args, rank, world, local_rank):
     """BASELINE config 3: `python bench.py --workload cfg3 [--gpus N]`.  A step = one iteration of train.py's inner loop on one
     clip per GPU (n_frames_load = 1 generated frame): generator forward (tcgen05, precise mode), FlowNet2 (no grad), image and
-    temporal discriminator losses, the three backward passes (hand-written fp32 SIMT backward kernels -- the first correct
-    CUDA path, not yet on tensor cores), ONE flat NCCL all-reduce over [G | D | D_T] and the Adam steps.  value = clips
+    temporal discriminator losses, the three backward passes (data gradients as forward convs on conv_umma_kernel, weight
+    gradients on wgrad_umma_kernel, both in the split-bf16 precise arithmetic; norm / head / composite / loss backward on CUDA
+    cores), ONE flat NCCL all-reduce over [G | D | D_T] and the Adam steps.  value = clips
     (= generated frames) per second over all ranks; the all-reduce is timed separately with CUDA events."""
     import torch
     import torch.distributed as dist
@@ -515,7 +516,7 @@ def run_train(args, rank, world, local_rank):
     fl = 3 * 2 * gmacs                    # forward + data gradient + weight gradient of every generator convolution
     out = {'metric': 'training clips/sec (%s)' % args.workload, 'value': world * K / (ms * 1e-3), 'unit': 'clips/s', 'n_gpus': world, 'steps': K,
            'warmup': Wm, 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-           'dtype': 'forward ' + DTYPE['precise'] + '; backward f32 (SIMT)',
+           'dtype': 'forward and backward convolutions ' + DTYPE['precise'] + '; norm / loss backward f32',
            'data': 'synthetic 35-label blocky clips + low-pass noise frames, random-init G / D / FlowNet2',
            'config': {'workload': wl['desc'], 'parallelism': 'dp%d: one clip per GPU, per-rank BatchNorm statistics, ONE flat NCCL all-reduce '
                       '(%.1f M fp32 gradients of [G | D | D_T0 | D_T1]) per step' % (world, tr.grads.numel / 1e6),
@@ -525,10 +526,11 @@ def run_train(args, rank, world, local_rank):
            'gpu_launches': launches, 'clocks': sampler.summary(),
            'all_reduce': {'ms_per_step': ar, 'share_of_step': ar / step_ms, 'bytes': tr.grads.numel * 4,
                           'algbw_gbs': tr.grads.numel * 4 / (ar * 1e-3) / 1e9 if ar > 0 else None, 'backend': 'nccl' if world > 1 else 'none (1 rank)'},
-           'roofline': {'bound': 'tensor', 'kernel': 'generator convolutions, forward (tcgen05) + backward (fp32 SIMT)', 'achieved': fl / (step_ms * 1e-3) / 1e12,
+           'hbm_used_gb': round((torch.cuda.mem_get_info(dev)[1] - torch.cuda.mem_get_info(dev)[0]) / 2 ** 30, 1),
+           'roofline': {'bound': 'tensor', 'kernel': 'generator convolutions: forward + data gradient (conv_umma_kernel) + weight gradient (wgrad_umma_kernel)', 'achieved': fl / (step_ms * 1e-3) / 1e12,
                         'peak': peak_burst, 'unit': 'TFLOP/s', 'frac': fl / (step_ms * 1e-3) / 1e12 / peak_burst, 'peak_source': peak_src,
-                        'traffic': None, 'note': 'whole-step time as denominator (includes D, FlowNet2, losses, optimizer); the backward '
-                        'kernels are the first correct CUDA path and run on CUDA cores'},
+                        'traffic': None, 'note': 'whole-step time as denominator (includes the discriminators, FlowNet2, losses, optimizer); '
+                        'algorithmic FLOPs: the precise mode issues 3 MMAs per algorithmic MAC'},
            'last_losses': losses}
     print(json.dumps(out))
 

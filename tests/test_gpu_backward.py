@@ -77,19 +77,30 @@ TENSOR_UNITS = [
     ('t_d_k4s1', lambda: [nn.Conv2d(64, 128, 4, stride=1, padding=2), BN(128), nn.LeakyReLU(0.2, True)], (1, 64, 12, 40)),
     ('t_d_k4s2', lambda: [nn.Conv2d(64, 128, 4, stride=2, padding=2), BN(128), nn.LeakyReLU(0.2, True)], (1, 64, 16, 80)),      # cropped transposed conv
     ('t_resblock128', lambda: [NW.ResnetBlock(128, 'reflect', BN)], (1, 128, 16, 32)),
+    # one narrow operand (16 / 32 padded channels) on the N side of the weight-gradient GEMM
+    ('t_stem6', lambda: NW._stem(6, 64, BN), (1, 6, 12, 40)),                                                            # narrow activation
+    ('t_c3_24_128', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(24, 128, 3), BN(128), nn.ReLU(True)], (1, 24, 10, 40)),    # 32-channel rows
+    ('t_d_last', lambda: [nn.Conv2d(64, 1, 4, stride=1, padding=2)], (2, 64, 12, 40)),                                   # narrow gradient (swap)
+    ('t_down_24', lambda: NW._down(64, 24, BN), (1, 64, 16, 80)),                                                        # stride 2, narrow gradient
+    ('t_head_tanh', lambda: NW._stem(8, 64, BN), (1, 8, 12, 40), lambda: NW._head(64, 3, nn.Tanh()), 1.0),
+    ('t_head_flow', lambda: NW._stem(8, 128, BN), (1, 8, 12, 40), lambda: NW._head(128, 2), 20.0),
+    ('t_head_both_narrow', lambda: NW._stem(8, 32, BN), (1, 8, 12, 40), lambda: NW._head(32, 3, nn.Tanh()), 1.0),       # dY padded to 64 channels
 ]
 
 
-@pytest.mark.parametrize('name,build,shape', TENSOR_UNITS, ids=[u[0] for u in TENSOR_UNITS])
-def test_tensor_core_backward_units(name, build, shape, monkeypatch):
+@pytest.mark.parametrize('unit', TENSOR_UNITS, ids=[u[0] for u in TENSOR_UNITS])
+def test_tensor_core_backward_units(unit, monkeypatch):
     """Gradients of the tcgen05 backward (data gradient as a forward conv + fold, weight gradient with pixels as the K
     dimension) against fp64 autograd, and against the fp32 SIMT backward kernels of the same plan description."""
+    name, build, shape = unit[:3]
+    head, scale = (unit[3], unit[4]) if len(unit) > 3 else (None, 1.0)
+    make = lambda: NW.SequentialRunner(build(), head(), scale) if head else NW.SequentialRunner(build())
     x = torch.randn(*shape, generator=torch.Generator().manual_seed(1)).cuda()
-    runner = det_fill_(NW.SequentialRunner(build()), seed=5).cuda()
+    runner = det_fill_(make(), seed=5).cuda()
     runner.precision = 'precise'
     names, ours, refs, out, ref = _grads(runner, x)
     monkeypatch.setenv('V2V_BWD', 'simt')
-    simt = det_fill_(NW.SequentialRunner(build()), seed=5).cuda()
+    simt = det_fill_(make(), seed=5).cuda()
     simt.precision = 'precise'
     _, ours_simt, _, _, _ = _grads(simt, x)
     bad = []
@@ -197,7 +208,8 @@ def test_second_forward_in_between_triggers_recomputation():
     o1 = runner(x1)
     runner(x2)                      # overwrites the plan's buffers
     o1.sum().backward()             # -> re-executes the first forward, without touching the running statistics again
-    assert torch.allclose(x1.grad, g_direct, rtol=1e-5, atol=1e-7)
+    # (not bit for bit: the per-channel sums of the norm backward meet through float atomics, whose order varies run to run)
+    assert torch.allclose(x1.grad, g_direct, rtol=1e-4, atol=1e-6)
     assert int(runner.seq[1].num_batches_tracked.item()) == nb + 2
 
 

@@ -40,3 +40,10 @@ with open(out_path, 'w') as f:
     for r in rows[:40]:
         f.write('%8.2f ms %5.1f %% %6d x  %s\n' % (r.device_time_total / 1e3, 100 * r.device_time_total / tot, r.count, r.key[:110]))
 print(open(out_path).read())
+# per-launch durations of the weight-gradient kernel in launch order (pair with the V2V_WG_LOG=1 lines on stderr)
+evs = [e for e in prof.events() if 'wgrad_umma_kernel' in e.name]
+evs.sort(key=lambda e: e.time_range.start)
+print('WGRAD_US ' + ' '.join('%.0f' % e.device_time for e in evs))
+evs = [e for e in prof.events() if 'conv_umma_kernel' in e.name]
+evs.sort(key=lambda e: e.time_range.start)
+print('CONV_US ' + ' '.join('%.0f' % e.device_time for e in evs))

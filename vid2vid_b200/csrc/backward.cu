@@ -221,6 +221,60 @@ __global__ void __launch_bounds__(256) norm_bwd_reduce_kernel(NormBwd p) {
   }
 }
 
+// Coalesced form of norm_bwd_reduce_kernel for C % 4 == 0, C <= 1024: a thread owns 4 consecutive channels (one float4 of the
+// NHWC rows) and strides over the pixels of its block's chunk; per-block partial sums meet in shared memory, one global atomic
+// per channel and block.
+__global__ void __launch_bounds__(256) norm_bwd_reduce_vec_kernel(NormBwd p, int chunk) {
+  extern __shared__ float sred[];                  // [2][C]
+  const int vec = p.C >> 2, ppb = 256 / vec;
+  const int n = blockIdx.y;
+  const long long HW = (long long)p.H * p.W;
+  for (int i = threadIdx.x; i < 2 * p.C; i += 256) sred[i] = 0.f;
+  __syncthreads();
+  const int c4 = threadIdx.x % vec, pl = threadIdx.x / vec;
+  if (pl < ppb) {
+    const int c = c4 * 4;
+    float sc[4], sh[4], mean[4], rstd[4], s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      sc[j] = p.scale[(size_t)n * p.stat_stride + c + j]; sh[j] = p.shift[(size_t)n * p.stat_stride + c + j];
+      mean[j] = p.mean ? p.mean[(size_t)n * p.stat_stride + c + j] : 0.f; rstd[j] = p.rstd ? p.rstd[(size_t)n * p.stat_stride + c + j] : 1.f;
+    }
+    const long long begin = (long long)blockIdx.x * chunk, end = min(HW, begin + chunk);
+    for (long long i = begin + pl; i < end; i += ppb) {
+      const size_t pix = (size_t)n * HW + i;
+      float raw[4];
+      if (p.raw.f32) {
+        const float4 r4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.raw.base) + pix * p.raw.C + p.c_off + c);
+        raw[0] = r4.x; raw[1] = r4.y; raw[2] = r4.z; raw[3] = r4.w;
+      } else {
+        const bf16* rp = reinterpret_cast<const bf16*>(p.raw.base) + pix * p.raw.C + p.c_off + c;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) raw[j] = __bfloat162float(rp[j]);
+      }
+      const float4 d4 = *reinterpret_cast<const float4*>(p.dy + pix * p.C + c);
+      const float dy[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float z = fmaf(raw[j], sc[j], sh[j]);
+        float dz = dy[j];
+        if (p.act == ACT_RELU) dz = z > 0.f ? dz : 0.f;
+        else if (p.act == ACT_LRELU) dz = z > 0.f ? dz : dz * p.slope;
+        s1[j] += dz;
+        s2[j] += dz * (raw[j] - mean[j]) * rstd[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { atomicAdd(&sred[c + j], s1[j]); atomicAdd(&sred[p.C + c + j], s2[j]); }
+  }
+  __syncthreads();
+  const int row = p.batch_stats ? 0 : n;
+  for (int i = threadIdx.x; i < p.C; i += 256) {
+    atomicAdd(&p.sums[(size_t)row * p.C + i], sred[i]);
+    atomicAdd(&p.sums[((size_t)p.N + row) * p.C + i], sred[p.C + i]);
+  }
+}
+
 // draw = gamma * rstd * (dz - mean(dz) - xhat * mean(dz * xhat))   (train-mode norm)   or   draw = dz (norm-less unit);
 // the addends of the unit (residual / skip inputs) receive dy unchanged.
 __global__ void __launch_bounds__(256) norm_bwd_apply_kernel(NormBwd p) {
@@ -379,6 +433,46 @@ __global__ void grad_export_kernel(const float* __restrict__ src, float* __restr
     g[((size_t)n * C_src + c_off + c) * HW + pix] += src[((size_t)n * HW + pix) * C + c];
   }
 }
+// 32 x 32 tiles through shared memory: both the NCHW side (pixel-contiguous) and the NHWC side (channel-contiguous) are
+// accessed coalesced.  IMPORT: dst(NHWC) += g(NCHW window); EXPORT: g(NCHW window) += src(NHWC).
+template <bool IMPORT>
+__global__ void __launch_bounds__(256) grad_layout_tiled_kernel(float* __restrict__ nchw, float* __restrict__ nhwc, int C_src, int c_off, int C,
+                                                                size_t HW) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const size_t pix0 = (size_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32, n = blockIdx.z;
+  if (IMPORT) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + ty + 8 * j;
+      const size_t pix = pix0 + tx;
+      tile[ty + 8 * j][tx] = (c < C && pix < HW) ? nchw[((size_t)n * C_src + c_off + c) * HW + pix] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t pix = pix0 + ty + 8 * j;
+      const int c = c0 + tx;
+      if (c < C && pix < HW) nhwc[((size_t)n * HW + pix) * C + c] += tile[tx][ty + 8 * j];
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const size_t pix = pix0 + ty + 8 * j;
+      const int c = c0 + tx;
+      tile[ty + 8 * j][tx] = (c < C && pix < HW) ? nhwc[((size_t)n * HW + pix) * C + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = c0 + ty + 8 * j;
+      const size_t pix = pix0 + tx;
+      if (c < C && pix < HW) nchw[((size_t)n * C_src + c_off + c) * HW + pix] += tile[tx][ty + 8 * j];
+    }
+  }
+}
+
 // dz = dy * act'(out) for a bias + activation conv epilogue unit (EPI_ACT_BF16): out = the forward activation buffer
 __global__ void convact_bwd_kernel(const float* __restrict__ dy, ActDesc out, int act, float slope, float* __restrict__ dz, int C, int dz_C) {
   const size_t total = (size_t)out.N * out.H * out.W * C;
@@ -437,8 +531,16 @@ cudaError_t launch_norm_bwd(const NormBwd& p, cudaStream_t s) {
   if (e != cudaSuccess) return e;
   if (p.has_norm || p.dbeta) {
     const long long HW = (long long)p.H * p.W;
-    dim3 grid(p.C, p.N, (unsigned)std::max(1LL, std::min(32LL, HW / 8192)));
-    norm_bwd_reduce_kernel<<<grid, 256, 0, s>>>(p);
+    if (p.C % 4 == 0 && p.C <= 1024 && p.raw.C % 4 == 0 && p.c_off % 4 == 0) {
+      const int ppb = 256 / (p.C / 4);
+      const long long want_blocks = std::max(1LL, (4LL * 148) / p.N);
+      long long chunk = std::max<long long>((long long)ppb * 8, (HW + want_blocks - 1) / want_blocks);
+      dim3 grid((unsigned)((HW + chunk - 1) / chunk), p.N);
+      norm_bwd_reduce_vec_kernel<<<grid, 256, 2 * p.C * sizeof(float), s>>>(p, (int)chunk);
+    } else {
+      dim3 grid(p.C, p.N, (unsigned)std::max(1LL, std::min(32LL, HW / 8192)));
+      norm_bwd_reduce_kernel<<<grid, 256, 0, s>>>(p);
+    }
   }
   norm_bwd_apply_kernel<<<grid1d((size_t)p.N * p.H * p.W * p.C), 256, 0, s>>>(p);
   if (p.dgamma || p.dbeta) norm_param_grad_kernel<<<(p.C + 127) / 128, 128, 0, s>>>(p);
@@ -454,10 +556,22 @@ cudaError_t launch_composite_bwd(const CompositeBwd& p, cudaStream_t s) {
   return cudaGetLastError();
 }
 cudaError_t launch_grad_import(const float* g, float* dst, int N, int C_src, int c_off, int C, int H, int W, cudaStream_t s) {
+  const size_t HW = (size_t)H * W;
+  if (C >= 8 && (HW + 31) / 32 <= 0x7fffffffULL && N <= 65535) {
+    dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N);
+    grad_layout_tiled_kernel<true><<<grid, 256, 0, s>>>(const_cast<float*>(g), dst, C_src, c_off, C, HW);
+    return cudaGetLastError();
+  }
   grad_import_kernel<<<grid1d((size_t)N * C * H * W), 256, 0, s>>>(g, dst, N, C_src, c_off, C, (size_t)H * W);
   return cudaGetLastError();
 }
 cudaError_t launch_grad_export(const float* src, float* g, int N, int C_src, int c_off, int C, int H, int W, cudaStream_t s) {
+  const size_t HW = (size_t)H * W;
+  if (C >= 8 && N <= 65535) {
+    dim3 grid((unsigned)((HW + 31) / 32), (C + 31) / 32, N);
+    grad_layout_tiled_kernel<false><<<grid, 256, 0, s>>>(g, const_cast<float*>(src), C_src, c_off, C, HW);
+    return cudaGetLastError();
+  }
   grad_export_kernel<<<grid1d((size_t)N * C * H * W), 256, 0, s>>>(src, g, N, C_src, c_off, C, (size_t)H * W);
   return cudaGetLastError();
 }

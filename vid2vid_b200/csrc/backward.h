@@ -53,19 +53,20 @@ struct WgradParams {
   int KP, kmma;                // pixels per K chunk (64 / 32 / 16), MMAs (16 pixels each) per chunk
   int xsegs;                   // ceil(gw / KP) chunks per grid row
   int out_padt, out_padl;      // OUT buffer halo: buffer coordinate of grid pixel (0, 0)
-  int out_C, in_C;             // padded channel counts (multiples of 64): the lo half starts at channel coordinate C
-  int Mblocks, Nblocks;        // 64-channel blocks per M tile (2, or 1 for a 64-channel OUT) / per N tile (1 or 2)
+  int swap;                    // 0: A (M side) = OUT, B (N side) = IN;  1: A = IN, B = OUT (narrow gradient tensors)
+  int a_C, b_C;                // padded channel counts of the A / B tensors: the lo half starts at channel coordinate C
+  int Mblocks, Nblocks;        // A: 64-channel blocks per M tile (2, or 1 for a 64-channel tensor); B: blocks per N tile
+  int b_row, BN;               // B: bytes per pixel row of one block (128 / 64 / 32) and channels per N tile (16 .. 128)
   int m_tiles, n_tiles, ntaps, ksplit;
   int chunks_total, chunks_per_unit;
   int split;                   // 1: [hi | lo] operands, three MMAs per K step
   int stages;
-  int lbo_bytes, sbo_bytes;    // MN-major descriptor strides: between 64-channel blocks (one box) / between 8-pixel groups (1024)
   WgradTap taps[V2V_MAX_TAPS];
   float* stage;                // [ntaps][Mp][Np] fp32, zeroed by the launcher
-  int Mp, Np;
+  int Mp, Np;                  // = a_C, b_C
 };
 size_t wgrad_stage_bytes(const WgradParams& p);
-cudaError_t launch_wgrad_umma(const CUtensorMap& tmOut, const CUtensorMap& tmIn, const WgradParams& p, int M, int M1, int Nv,
+cudaError_t launch_wgrad_umma(const CUtensorMap& tmOut, const CUtensorMap& tmIn, const WgradParams& p, int R, int R1, int Cc,
                               float* dw, float* dw2, cudaStream_t s);
 cudaError_t launch_fold_add(const float* src, int Cs, int PH, int PW, float* dx, int N, int H, int W, int C, int pad, int reflect,
                             cudaStream_t s);

@@ -58,10 +58,12 @@ struct DeviceGuard {
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
 static inline size_t round_up_sz(size_t a, size_t b) { return (a + b - 1) / b * b; }
 // padded channel count of an activation buffer: one K block of min(C,64) channels per shared-memory row
+static thread_local int g_pad_min = 0;     // set while a backward sub-plan is being described (build_backward_units)
 static inline int pad_channels(int c) {
   const char* e = getenv("V2V_KC64");
   if (e && e[0] == '1') return round_up(c, 64);
-  return c <= 16 ? 16 : (c <= 32 ? 32 : round_up(c, 64));
+  const int r = c <= 16 ? 16 : (c <= 32 ? 32 : round_up(c, 64));
+  return std::max(r, g_pad_min);
 }
 
 // ------------------------------------------------------------------------------ conv geometry
@@ -804,6 +806,10 @@ static int build_backward_units(v2v_plan* P, cudaStream_t stream) {
     const float* dy = op.kind == G_CONV ? P->raws[op.raw].graw : op.gdz;
     const int dy_C = op.kind == G_CONV ? P->raws[op.raw].desc.C : round_up(c.Cout, 8);
     // ---- sub-plan: dY (dense fp32 NHWC) -> halo-padded split activation -> conv
+    // the weight-gradient GEMM needs >= 64 channels on one side: when the forward input AND output are narrow (the 32 -> 3
+    // foreground head), the sub-plan carries dY padded to 64 channels
+    g_pad_min = (pad_channels(c.Cout) < 64 && pad_channels(c.Cin) < 64) ? 64 : 0;
+    struct PadReset { ~PadReset() { g_pad_min = 0; } } pad_reset;
     v2v_plan* C = nullptr;
     int rc = v2v_plan_create(P->device, P->impl, &C); if (rc) return rc;
     C->precise = P->precise; C->allow_reuse = P->allow_reuse;
@@ -825,6 +831,7 @@ static int build_backward_units(v2v_plan* P, cudaStream_t stream) {
                   "internal: data-gradient conv of op %d yields %dx%dx%d, expected %dx%dx%d", (int)i, cr.H, cr.W, cr.C, eh, ew, c.Cin);
     }
     // ---- weight gradient on the tensor cores: OUT (gradient side) x IN (activation side) over the driving grid
+    g_pad_min = 0;
     const ActDesc& a_dy = C->acts[C->values[gi.value_out].bufs[0]];
     const ActDesc& a_x = P->acts[vin.bufs[op.req_index]];
     const ActDesc& a_out = u.mode == 2 ? a_x : a_dy;
@@ -832,14 +839,24 @@ static int build_backward_units(v2v_plan* P, cudaStream_t stream) {
     const int kp = std::min(a_out.Wp, a_in.Wp) >= 64 ? 64 : (std::min(a_out.Wp, a_in.Wp) >= 32 ? 32 : (std::min(a_out.Wp, a_in.Wp) >= 16 ? 16 : 0));
     const char* ewg = getenv("V2V_WGRAD");
     const bool wg_ok = !(ewg && !strcmp(ewg, "simt"));
-    if (wg_ok && kp > 0 && a_out.C % 64 == 0 && a_in.C % 64 == 0 && !a_out.parity && a_out.split == a_in.split && c.kh * c.kw <= V2V_MAX_TAPS) {
+    const bool wide_out = a_out.C % 64 == 0, wide_in = a_in.C % 64 == 0;
+    const bool narrow_ok_out = a_out.C == 16 || a_out.C == 32, narrow_ok_in = a_in.C == 16 || a_in.C == 32;
+    if (wg_ok && kp > 0 && ((wide_out && (wide_in || narrow_ok_in)) || (wide_in && narrow_ok_out)) && !a_out.parity && a_out.split == a_in.split &&
+        c.kh * c.kw <= V2V_MAX_TAPS) {
       WgradParams& w = u.wg;
       w.N = vin.N; w.gh = u.mode == 2 ? vin.H : oh; w.gw = u.mode == 2 ? vin.W : ow;
       w.KP = kp; w.kmma = kp / 16; w.xsegs = (w.gw + kp - 1) / kp;
-      w.out_padt = a_out.pad_t; w.out_padl = a_out.pad_l; w.out_C = a_out.C; w.in_C = a_in.C;
-      w.Mblocks = a_out.C >= 128 ? 2 : 1; w.Nblocks = a_in.C >= 128 ? 2 : 1;
-      w.m_tiles = (a_out.C + w.Mblocks * 64 - 1) / (w.Mblocks * 64); w.n_tiles = (a_in.C + w.Nblocks * 64 - 1) / (w.Nblocks * 64);
-      w.ntaps = c.kh * c.kw; w.split = a_out.split; w.Mp = a_out.C; w.Np = a_in.C;
+      w.out_padt = a_out.pad_t; w.out_padl = a_out.pad_l;
+      w.swap = wide_out ? 0 : 1;                          // the narrow tensor (16 / 32 channels) always sits on the N side
+      const ActDesc& aA = w.swap ? a_in : a_out;
+      const ActDesc& aB = w.swap ? a_out : a_in;
+      w.a_C = aA.C; w.b_C = aB.C;
+      w.Mblocks = aA.C >= 128 ? 2 : 1;
+      w.b_row = aB.C >= 64 ? 128 : aB.C * 2;
+      w.Nblocks = aB.C >= 128 ? 2 : 1;
+      w.BN = aB.C >= 128 ? 128 : aB.C;
+      w.m_tiles = (aA.C + w.Mblocks * 64 - 1) / (w.Mblocks * 64); w.n_tiles = (aB.C + w.BN - 1) / w.BN;
+      w.ntaps = c.kh * c.kw; w.split = a_out.split; w.Mp = aA.C; w.Np = aB.C;
       // taps: IN buffer coordinate of grid pixel (y, x).  Stride 1: (y + ky, x + kx); stride 2 (IN in parity planes):
       // plane (ky & 1, kx & 1), (y + ky / 2, x + kx / 2) -- as conv_geometry lays the forward taps out
       const bool s2 = (u.mode != 1);
@@ -848,18 +865,17 @@ static int build_backward_units(v2v_plan* P, cudaStream_t stream) {
           w.taps[ky * c.kw + kx] = s2 ? WgradTap{(int8_t)(((ky & 1) << 1) | (kx & 1)), (int8_t)(ky >> 1), (int8_t)(kx >> 1), 0}
                                       : WgradTap{0, (int8_t)ky, (int8_t)kx, 0};
       V2V_REQUIRE(!s2 || a_in.parity, V2V_ERR_STATE, "internal: stride-2 weight gradient needs a parity-plane operand");
-      const int stage_bytes = (w.split ? 2 : 1) * (2 + w.Nblocks) * kp * 128;
+      const int stage_bytes = (w.split ? 2 : 1) * (2 * kp * 128 + round_up(w.Nblocks * kp * w.b_row, 1024));
       w.stages = std::max(2, std::min(6, kSmemBudget / stage_bytes));
-      w.lbo_bytes = kp * 128; w.sbo_bytes = 1024;
-      if (const char* e = getenv("V2V_WG_DESC")) sscanf(e, "%d,%d", &w.lbo_bytes, &w.sbo_bytes);      // descriptor experiments
       w.chunks_total = w.N * w.gh * w.xsegs;
       const int base_units = w.ntaps * w.m_tiles * w.n_tiles;
       const int want = std::max(1, (2 * device_sm_count() + base_units - 1) / base_units);
       w.chunks_per_unit = std::max(std::min(8, w.chunks_total), (w.chunks_total + want - 1) / want);
       w.ksplit = (w.chunks_total + w.chunks_per_unit - 1) / w.chunks_per_unit;
+      // parameter gradient [R][Cc][taps]: rows = channels of OUT, columns = channels of IN
       u.M = u.mode == 2 ? c.Cin : c.Cout; u.M1 = u.mode == 2 ? c.Cin : c.Cout - c.Cout2; u.Nv = u.mode == 2 ? c.Cout : c.Cin;
-      rc = make_tmap_act(&u.tmOut, a_out, kp, 1, 64); if (rc) { P->bwd.push_back(u); return rc; }
-      rc = make_tmap_act(&u.tmIn, a_in, kp, 1, 64); if (rc) { P->bwd.push_back(u); return rc; }
+      rc = make_tmap_act(&u.tmOut, a_out, kp, 1, std::min(a_out.C, 64)); if (rc) { P->bwd.push_back(u); return rc; }
+      rc = make_tmap_act(&u.tmIn, a_in, kp, 1, std::min(a_in.C, 64)); if (rc) { P->bwd.push_back(u); return rc; }
       u.wgrad = true;
       stage_max = std::max(stage_max, wgrad_stage_bytes(w));
     }

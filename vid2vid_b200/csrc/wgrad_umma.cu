@@ -10,7 +10,7 @@
 // 8-K groups 1024 bytes apart, 64-element blocks one box apart), so no transposed copy of any tensor is made: the same
 // bytes serve the forward conv K-major and this kernel MN-major.
 //
-// One CTA per work unit (tap, M tile of 128 output-gradient channels, N tile of 64 / 128 input channels, K split); the K
+// One CTA per work unit (tap, M tile of 128 channels of one tensor, N tile of 16 .. 128 channels of the other, K split); the K
 // loop walks row segments of KP pixels through a ring of shared-memory stages:
 //   warp 0     TMA producer (one elected lane)
 //   warp 1     tcgen05.mma issuer (one elected lane) + TMEM owner; precise plans accumulate OUT_hi*IN_hi + OUT_lo*IN_hi +
@@ -18,6 +18,7 @@
 //   warps 2-5  epilogue: tcgen05.ld the 128 x BN fp32 accumulator and add it to the staging buffer G (vector atomics: the K
 //              splits of one (tap, tile) meet there); unstage_wgrad_kernel then adds G into the caller's gradient tensor in
 //              the parameter's own layout [M][N][kh][kw].
+#include <cstdlib>
 #include "ptx.cuh"
 #include "v2v_internal.h"
 #include "backward.h"
@@ -26,14 +27,15 @@ namespace v2v {
 
 static constexpr int kWgThreads = 192;
 
-__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, int lbo_bytes, int sbo_bytes) {
-  // MN-major SWIZZLE_128B: LBO = distance between 64-element M/N blocks, SBO = distance between groups of 8 K indices
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, int lbo_bytes, int sbo_bytes, int layout_type) {
+  // MN-major, swizzled: one K index = one shared-memory row of 128 / 64 / 32 bytes (64 / 32 / 16 contiguous M or N elements,
+  // layout type 2 / 4 / 6); SBO = distance between groups of 8 K indices (8 rows), LBO = distance between row-wide blocks
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
 }
 
@@ -42,10 +44,13 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_consta
                   const __grid_constant__ WgradParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int box = p.KP * 128;                                   // one TMA box: KP pixels x 64 channels
+  // A operand (M side, 128 rows of the accumulator): two 64-channel blocks of 128-byte rows.  B operand (N side): Nblocks
+  // blocks of b_row bytes per pixel (128: 64 channels; 64 / 32: a 32- / 16-channel tensor in one block).
+  const int boxA = p.KP * 128, boxB = p.KP * p.b_row;
   const int nh = p.split ? 2 : 1;
-  const int out_bytes = nh * 2 * box, in_bytes = nh * p.Nblocks * box;   // OUT always holds two 64-channel blocks (M = 128)
-  const int stage_bytes = out_bytes + in_bytes;
+  const int a_half = 2 * boxA, b_half = (p.Nblocks * boxB + 1023) & ~1023;
+  const int a_bytes = nh * a_half, b_bytes = nh * b_half;
+  const int stage_bytes = a_bytes + b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + p.stages;
@@ -53,7 +58,7 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int BN = p.Nblocks * 64;
+  const int BN = p.BN;
   const uint32_t tmem_cols = BN < 32 ? 32 : BN;
 
   // unit -> (K split, tap, M tile, N tile), tiles fastest: the CTAs running together walk the same pixel range, so every
@@ -86,6 +91,12 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_consta
   if (warp == 0) {
     if (elect_one_sync()) {
       const WgradTap t = p.taps[tap];
+      // swap == 0: A = OUT (gradient side, grid pixel itself), B = IN (activation side, shifted by the tap); swap == 1: the
+      // other way round (a narrow gradient tensor -- heads, the discriminators' last layer -- sits on the N side)
+      const CUtensorMap* tmA = p.swap ? &tmIn : &tmOut;
+      const CUtensorMap* tmB = p.swap ? &tmOut : &tmIn;
+      const int ax = p.swap ? t.dx : p.out_padl, ay = p.swap ? t.dy : p.out_padt, apl = p.swap ? t.plane : 0;
+      const int bx = p.swap ? p.out_padl : t.dx, by = p.swap ? p.out_padt : t.dy, bpl = p.swap ? 0 : t.plane;
       int xs = c_begin % p.xsegs;
       int row = c_begin / p.xsegs;                               // img * gh + y
       int y = row % p.gh, img = row / p.gh;
@@ -93,18 +104,17 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_consta
       for (int c = 0; c < nchunks; ++c) {
         uint8_t* st = smem + (size_t)s * stage_bytes;
         mbar_wait(&empty[s], par ^ 1);
-        mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+        mbar_expect_tx(&full[s], (uint32_t)(nh * (2 * boxA + p.Nblocks * boxB)));
         for (int hf = 0; hf < nh; ++hf)
           for (int mb = 0; mb < 2; ++mb) {
-            // a 64-channel OUT tensor fills both halves of the M = 128 tile with the same block (rows 64.. are not stored)
+            // a 64-channel A tensor fills both halves of the M = 128 tile with the same block (rows 64.. are not stored)
             const int blk = p.Mblocks == 2 ? mt * 2 + mb : mt;
-            tma_load_5d(st + (size_t)(hf * 2 + mb) * box, &tmOut, &full[s], hf * p.out_C + blk * 64, xs * p.KP + p.out_padl,
-                        y + p.out_padt, 0, img);
+            tma_load_5d(st + (size_t)hf * a_half + (size_t)mb * boxA, tmA, &full[s], hf * p.a_C + blk * 64, xs * p.KP + ax, y + ay, apl, img);
           }
         for (int hf = 0; hf < nh; ++hf)
           for (int nb = 0; nb < p.Nblocks; ++nb)
-            tma_load_5d(st + out_bytes + (size_t)(hf * p.Nblocks + nb) * box, &tmIn, &full[s], hf * p.in_C + (nt * p.Nblocks + nb) * 64,
-                        xs * p.KP + t.dx, y + t.dy, t.plane, img);
+            tma_load_5d(st + a_bytes + (size_t)hf * b_half + (size_t)nb * boxB, tmB, &full[s], hf * p.b_C + (nt * p.Nblocks + nb) * 64,
+                        xs * p.KP + bx, y + by, bpl, img);
         if (++s == p.stages) { s = 0; par ^= 1; }
         if (++xs == p.xsegs) { xs = 0; if (++y == p.gh) { y = 0; ++img; } }
       }
@@ -113,16 +123,18 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_consta
     if (elect_one_sync()) {
       const uint32_t idesc = make_idesc_bf16(128, BN) | (1u << 15) | (1u << 16);      // A and B MN-major
       const int ps_step = p.split ? 1 : 3;
+      const int b_layout = p.b_row == 128 ? 2 : (p.b_row == 64 ? 4 : 6);
+      const int b_kstep = 16 * p.b_row, b_sbo = 8 * p.b_row;        // 16 pixels per MMA = two 8-row groups
       int s = 0; uint32_t par = 0;
       uint32_t first = 0;
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(&full[s], par);
         tcgen05_fence_after();
-        const uint32_t a0 = smem_u32(smem + (size_t)s * stage_bytes), b0 = a0 + out_bytes;
+        const uint32_t a0 = smem_u32(smem + (size_t)s * stage_bytes), b0 = a0 + a_bytes;
         for (int ps = 0; ps < 3; ps += ps_step) {
-          const uint32_t a = a0 + (ps == 1 ? 2 * box : 0), b = b0 + (ps == 2 ? p.Nblocks * box : 0);
-          for (int k = 0; k < p.kmma; ++k) {                      // 16 pixels = two 8-K groups = 2048 bytes per MMA
-            umma_bf16(tmem_base, make_mnmajor_desc(a + k * 2048, p.lbo_bytes, p.sbo_bytes), make_mnmajor_desc(b + k * 2048, p.lbo_bytes, p.sbo_bytes), idesc, first);
+          const uint32_t a = a0 + (ps == 1 ? a_half : 0), b = b0 + (ps == 2 ? b_half : 0);
+          for (int k = 0; k < p.kmma; ++k) {
+            umma_bf16(tmem_base, make_mnmajor_desc(a + k * 2048, boxA, 1024, 2), make_mnmajor_desc(b + k * b_kstep, boxB, b_sbo, b_layout), idesc, first);
             first = 1u;
           }
         }
@@ -140,15 +152,15 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_consta
     tcgen05_fence_after();
     const int n0 = nt * BN;
     float* dst = p.stage + ((size_t)tap * p.Mp + (valid ? m : 0)) * p.Np + n0;
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t r[32];
-      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 32, r);
+    for (int c = 0; c < BN / 16; ++c) {
+      uint32_t r[16];
+      tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 16, r);
       tmem_ld_wait();
       if (valid) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (n0 + c * 32 + j * 4 < p.Np)
-            atomicAdd(reinterpret_cast<float4*>(dst + c * 32 + j * 4),
+        for (int j = 0; j < 4; ++j)
+          if (n0 + c * 16 + j * 4 < p.Np)
+            atomicAdd(reinterpret_cast<float4*>(dst + c * 16 + j * 4),
                       make_float4(__uint_as_float(r[j * 4]), __uint_as_float(r[j * 4 + 1]), __uint_as_float(r[j * 4 + 2]),
                                   __uint_as_float(r[j * 4 + 3])));
       }
@@ -159,28 +171,30 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
 }
 
-// G[tap][m][n] -> parameter gradient [M][Nv][taps] (+=); rows >= M1 go to the second weight set of a fused unit
-__global__ void __launch_bounds__(256) unstage_wgrad_kernel(const float* __restrict__ stage, int Mp, int Np, int M, int M1, int Nv,
+// G[tap][m][n] -> parameter gradient [R][Cc][taps] (+=) with (row, column) = (m, n), or (n, m) when the operands were swapped;
+// rows >= R1 go to the second weight set of a fused unit
+__global__ void __launch_bounds__(256) unstage_wgrad_kernel(const float* __restrict__ stage, int Mp, int Np, int swap, int R, int R1, int Cc,
                                                             int taps, float* __restrict__ dw, float* __restrict__ dw2) {
-  const long long total = (long long)M * Nv * taps;
+  const long long total = (long long)R * Cc * taps;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int t = (int)(idx % taps);
     const long long r = idx / taps;
-    const int n = (int)(r % Nv), m = (int)(r / Nv);
+    const int col = (int)(r % Cc), row = (int)(r / Cc);
+    const int m = swap ? col : row, n = swap ? row : col;
     const float v = stage[((size_t)t * Mp + m) * Np + n];
-    if (m < M1) { if (dw) dw[idx] += v; }
-    else if (dw2) dw2[((size_t)(m - M1) * Nv + n) * taps + t] += v;
+    if (row < R1) { if (dw) dw[idx] += v; }
+    else if (dw2) dw2[((size_t)(row - R1) * Cc + col) * taps + t] += v;
   }
 }
 
 size_t wgrad_stage_bytes(const WgradParams& p) { return (size_t)p.ntaps * p.Mp * p.Np * sizeof(float); }
 
-cudaError_t launch_wgrad_umma(const CUtensorMap& tmOut, const CUtensorMap& tmIn, const WgradParams& p, int M, int M1, int Nv,
+cudaError_t launch_wgrad_umma(const CUtensorMap& tmOut, const CUtensorMap& tmIn, const WgradParams& p, int R, int R1, int Cc,
                               float* dw, float* dw2, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(p.stage, 0, wgrad_stage_bytes(p), s);
   if (e != cudaSuccess) return e;
   const int nh = p.split ? 2 : 1;
-  const size_t stage_bytes = (size_t)nh * (2 + p.Nblocks) * p.KP * 128;
+  const size_t stage_bytes = (size_t)nh * (2 * p.KP * 128 + ((p.Nblocks * p.KP * p.b_row + 1023) & ~1023));
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (2 * p.stages + 2) * sizeof(uint64_t);
   static size_t configured = 0;
   if (smem > configured) {
@@ -189,12 +203,15 @@ cudaError_t launch_wgrad_umma(const CUtensorMap& tmOut, const CUtensorMap& tmIn,
     configured = smem;
   }
   const int units = p.ntaps * p.m_tiles * p.n_tiles * p.ksplit;
+  static const bool log = getenv("V2V_WG_LOG") != nullptr;        // one line per launch, to pair with a profiler's kernel list
+  if (log) fprintf(stderr, "wgrad grid %dx%dx%d taps %d aC %d bC %d BN %d swap %d KP %d units %d (ksplit %d x %d chunks) R %d Cc %d\n", p.N, p.gh, p.gw,
+                   p.ntaps, p.a_C, p.b_C, p.BN, p.swap, p.KP, units, p.ksplit, p.chunks_per_unit, R, Cc);
   wgrad_umma_kernel<<<units, kWgThreads, smem, s>>>(tmOut, tmIn, p);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const long long total = (long long)M * Nv * p.ntaps;
+  const long long total = (long long)R * Cc * p.ntaps;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-  unstage_wgrad_kernel<<<blocks, 256, 0, s>>>(p.stage, p.Mp, p.Np, M, M1, Nv, p.ntaps, dw, dw2);
+  unstage_wgrad_kernel<<<blocks, 256, 0, s>>>(p.stage, p.Mp, p.Np, p.swap, R, R1, Cc, p.ntaps, dw, dw2);
   return cudaGetLastError();
 }
 
