@@ -43,6 +43,8 @@ WORKLOADS = {
     'cfg3': dict(W=1024, H=512, n_scales=2, ngf=128, train=True,
                  desc='label2city 1024x512 training step (G + multiscale D + FlowNet2 warp loss), batch-sharded, n_scales_spatial=2'),
     'cfg3_small': dict(W=256, H=128, n_scales=2, ngf=32, train=True, desc='plumbing: 256x128 training step, ngf 32'),
+    # the reference-flow network of the training step on its own (models/flownet.py:25-62): FlowNetC -> S -> S || SD -> Fusion
+    'flownet2': dict(W=1024, H=512, flownet=True, desc='FlowNet2 (flow, confidence) of one 1024x512 frame pair, 162.5 M parameters'),
 }
 
 
@@ -410,7 +412,7 @@ def cpu_frames_per_s(workload, steps, warm, budget_s=150.0):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    if WORKLOADS[args.workload].get('train'):
+    if WORKLOADS[args.workload].get('train') or WORKLOADS[args.workload].get('flownet'):
         print(json.dumps({'impl': 'reference', 'unavailable': 'the CPU reference arm is defined for the headline inference workloads; '
                           'the reference training step needs its CUDA-only FlowNet2 ops (see DESIGN.md)'}))
         return
@@ -535,6 +537,84 @@ def run_train(args, rank, world, local_rank):
     print(json.dumps(out))
 
 
+# ----------------------------------------------------------------------------------------------- FlowNet2 (a14 / a15)
+def run_flownet2(args, rank, world, local_rank):
+    """`python bench.py --workload flownet2`: a step = flowNet(frame_t, frame_t-1) -> (flow, confidence) for one 1024x512 pair
+    (models/flownet.py:25-62; 264.3 algorithmic GMAC over the five sub-networks, SURVEY 8d).  value = pairs/s device-resident;
+    e2e = two pinned fp32 host frames in, flow + confidence back to pinned host memory, every step."""
+    import torch
+    from vid2vid_b200 import _lib as L
+    from vid2vid_b200 import flownet as FN
+    from vid2vid_b200.utils import make_opt
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    wl = WORKLOADS[args.workload]
+    H, Wd = wl['H'], wl['W']
+    torch.manual_seed(1234)
+    F = FN.FlowNet().initialize(make_opt(gpu_ids=[local_rank]))
+    K, Wm = args.steps, max(args.warmup, 3)
+    g = torch.Generator().manual_seed(5 + rank)
+    coarse = torch.rand(K + Wm + 1, 3, H // 16, Wd // 16, generator=g)
+    frames = torch.nn.functional.interpolate(coarse, size=(H, Wd), mode='bilinear', align_corners=False).pin_memory()
+    frames_dev = frames.to(dev)
+    out_flow = torch.empty(1, 2, H, Wd).pin_memory()
+    out_conf = torch.empty(1, 1, H, Wd).pin_memory()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    for t in range(Wm):
+        F(frames_dev[t + 1:t + 2], frames_dev[t:t + 1])
+    barrier()
+    sampler.recording = True
+    l0 = L.LAUNCHES[0]
+    e0, e1, e2, e3 = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    e0.record()
+    for t in range(Wm, Wm + K):
+        F(frames_dev[t + 1:t + 2], frames_dev[t:t + 1])
+    e1.record()
+    barrier()
+    launches = L.LAUNCHES[0] - l0
+    e2.record()
+    for t in range(Wm, Wm + K):
+        a, b = frames[t + 1:t + 2].to(dev, non_blocking=True), frames[t:t + 1].to(dev, non_blocking=True)
+        flow, conf = F(a, b)
+        out_flow.copy_(flow, non_blocking=True)
+        out_conf.copy_(conf, non_blocking=True)
+    e3.record()
+    barrier()
+    sampler.stop_flag = True
+    ms_dev, ms_e2e = reduce_times([e0.elapsed_time(e1), e2.elapsed_time(e3)], world, dev)
+    if rank != 0:
+        return
+    conv_ms, conv_macs, other_ms, n_conv = 0.0, 0.0, 0.0, 0
+    for key, ent in F.flowNet._plans().items():
+        for kind, ms, macs in ent['plan'].profile():
+            if kind == 1:
+                conv_ms += ms; conv_macs += macs; n_conv += 1
+            else:
+                other_ms += ms
+    peak_burst, peak_sust, peak_gbs, peak_src = peaks()
+    ach = 2.0 * conv_macs / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
+    out = {'metric': 'frame pairs/sec (FlowNet2 1024x512)', 'value': world * K / (ms_dev * 1e-3), 'unit': 'pairs/s', 'n_gpus': world, 'steps': K,
+           'warmup': Wm, 'ms_per_step': ms_dev / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': DTYPE['precise'],
+           'data': 'synthetic low-pass noise frames, random-init (xavier) FlowNet2 weights',
+           'config': {'workload': wl['desc'], 'parallelism': 'replicas x%d' % world, 'conv_flops_per_pair': 2.0 * conv_macs},
+           'e2e': {'value': world * K / (ms_e2e * 1e-3), 'unit': 'pairs/s', 'h2d_bytes_per_step': 2 * 3 * H * Wd * 4, 'd2h_bytes_per_step': 3 * H * Wd * 4,
+                   'api': 'FlowNet.forward(pinned fp32 frame pair) -> (flow, conf) in pinned host memory'},
+           'gpu_launches': launches, 'clocks': sampler.summary(),
+           'roofline': {'bound': 'tensor', 'kernel': 'conv_umma_kernel (all launches of the five sub-network plans)', 'achieved': ach, 'peak': peak_burst,
+                        'unit': 'TFLOP/s', 'frac': ach / peak_burst, 'peak_source': peak_src, 'mma_passes_per_k_block': 3,
+                        'issued_tensor_tflops': 3 * ach, 'traffic': None, 'launches_per_pair': n_conv, 'conv_kernel_ms_per_pair': conv_ms,
+                        'other_plan_kernels_ms_per_pair': other_ms}}
+    print(json.dumps(out))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -558,6 +638,8 @@ def main():
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     if WORKLOADS[args.workload].get('train'):
         run_train(args, rank, world, local_rank)
+    elif WORKLOADS[args.workload].get('flownet'):
+        run_flownet2(args, rank, world, local_rank)
     else:
         run_ours(args, rank, world, local_rank)
     if world > 1:

@@ -28,6 +28,20 @@ B = torch.nn.functional.interpolate(coarse, size=(H, Wd), mode='bilinear', align
 for t in range(5):
     tr.step(A[:, t:t + tG], B[:, t:t + tG], A[:, t:t + tG])
 torch.cuda.synchronize()
+if os.environ.get('PROFILE_CPU'):
+    import cProfile, pstats, time
+    pr = cProfile.Profile()
+    t0 = time.time()
+    pr.enable()
+    for t in range(5, 8):
+        tr.step(A[:, t:t + tG], B[:, t:t + tG], A[:, t:t + tG])
+    torch.cuda.synchronize()
+    pr.disable()
+    print('3 steps wall %.1f ms each' % ((time.time() - t0) / 3 * 1e3))
+    st = pstats.Stats(pr)
+    st.sort_stats('cumulative').print_stats(45)
+    st.sort_stats('tottime').print_stats(30)
+    sys.exit(0)
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA]) as prof:
     t = 5
