@@ -72,8 +72,9 @@ class ClockSampler(threading.Thread):
 
     REASONS = {'hw_slowdown': 0x8, 'sw_thermal_slowdown': 0x20, 'hw_thermal_slowdown': 0x40, 'sw_power_cap': 0x4}
 
-    def __init__(self, index):
+    def __init__(self, index, period=0.05):
         super().__init__(daemon=True)
+        self.period = period
         self.index, self.sm, self.reasons, self.max_mhz, self.stop_flag = index, [], set(), None, False
         self.recording = False      # NVML init and the first (slow) queries happen during warm-up, outside the timed region
         self.nvml = None
@@ -101,7 +102,7 @@ class ClockSampler(threading.Thread):
                         for n, bit in self.REASONS.items():
                             if mask & bit:
                                 self.reasons.add(n)
-                    time.sleep(0.05)
+                    time.sleep(self.period)
                 elif not self.recording:
                     time.sleep(0.02)
                 else:
@@ -459,7 +460,9 @@ def run_train(args, rank, world, local_rank):
     D = Vid2VidModelD().initialize(opt)
     F = FN.FlowNet().initialize(opt)
     tr = Trainer(opt, G, D, F, world=world)
-    K, Wm = args.steps, max(args.warmup, 3)
+    # warm-up must reach the steady state of the clip: the temporal discriminators switch on as the frame history fills
+    # (scale s needs tD**s * (tD - 1) + 1 frames, vid2vid_model_D.py:267-282) and build their plans at that step
+    K, Wm = args.steps, max(args.warmup, opt.n_frames_D ** (opt.n_scales_temporal - 1) * (opt.n_frames_D - 1) + 3)
     tG = opt.n_frames_G
     T = K + Wm + tG + 2
     A = synth_label_sequence(T, H, Wd, label_nc=35, block=64, seed=rank).pin_memory()
@@ -472,7 +475,7 @@ def run_train(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, period=0.25)     # (NVML queries take the driver lock the ~3600 launches of a step also need)
     sampler.start()
     ar_ms = []
     orig_ar = tr.grads.all_reduce_mean

@@ -272,9 +272,27 @@ class _PlanFunction(torch.autograd.Function):
                 gin.append(None)
         if os.environ.get('V2V_DEBUG_AUTOGRAD'):
             print('plan backward: in_slots', ctx.in_slots, 'needs', ctx.needs_input_grad[6:6 + ctx.n_in], 'gin', [g is not None for g in gin])
-        pgrads = [torch.zeros_like(p) if ctx.needs_input_grad[6 + ctx.n_in + j] else None for j, p in enumerate(ctx.params)]
+        # Parameter gradients.  The kernels ACCUMULATE into the tensors they are given, so a parameter that already owns a
+        # .grad (the trainer's flat all-reduce buffer, or a previous backward) receives its gradient in place and autograd gets
+        # None for it: no per-parameter zero fill, no per-parameter accumulate kernel (~1000 of each per step otherwise).  The
+        # others share ONE zero-filled buffer.
+        need = [bool(ctx.needs_input_grad[6 + ctx.n_in + j]) for j in range(len(ctx.params))]
+        direct = [need[j] and p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 and
+                  p.grad.device == p.device for j, p in enumerate(ctx.params)]
+        fresh = [j for j, p in enumerate(ctx.params) if need[j] and not direct[j]]
+        pgrads, ret = [None] * len(ctx.params), [None] * len(ctx.params)
+        if fresh:
+            flat = torch.zeros(sum(ctx.params[j].numel() for j in fresh), device=ctx.params[fresh[0]].device, dtype=torch.float32)
+            off = 0
+            for j in fresh:
+                n = ctx.params[j].numel()
+                pgrads[j] = ret[j] = flat[off:off + n].view_as(ctx.params[j])
+                off += n
+        for j, p in enumerate(ctx.params):
+            if direct[j]:
+                pgrads[j] = p.grad
         plan.backward(io, gio, ctx.params, pgrads)
-        return (None,) * 6 + tuple(gin) + tuple(pgrads)
+        return (None,) * 6 + tuple(gin) + tuple(ret)
 
 
 # Arithmetic of the conv stack (include/v2v_b200.h V2V_PREC_*): 'precise' = split-bf16 3-MMA, fp32-class -- the mode
@@ -305,8 +323,13 @@ class _Planned(nn.Module):
         return self.__dict__['_plan_cache']
 
     def _signature(self):
+        # (the tensor list is cached: walking the module tree costs ~0.6 ms per call, and a training step makes ~40 calls;
+        # .cuda() / .to() / load_state_dict keep the Parameter objects, so the list stays valid)
+        ts = self.__dict__.get('_sig_tensors')
+        if ts is None:
+            ts = self.__dict__['_sig_tensors'] = list(self.parameters()) + list(self.buffers())
         ptrs, ver = 0, 0
-        for t in list(self.parameters()) + list(self.buffers()):
+        for t in ts:
             ptrs = (ptrs * 1000003 + t.data_ptr()) & 0xFFFFFFFFFFFF
             ver += t._version
         return ptrs, ver
