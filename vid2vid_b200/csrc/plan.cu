@@ -1294,7 +1294,7 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
   // (a CTA only writes the (phase, image) rows it actually worked on)
   const size_t stats_begin = off;
   for (size_t i = 0; i < P->raws.size(); ++i)
-    if (P->raws[i].conv_op >= 0) raw_off[i].stats = take((size_t)P->raws[i].N * 2 * P->raws[i].C * sizeof(stat_t) + 64);   // + ticket counter
+    if (P->raws[i].conv_op >= 0 && !P->raws[i].no_stats) raw_off[i].stats = take((size_t)P->raws[i].N * 2 * P->raws[i].C * sizeof(stat_t) + 64);   // + ticket counter
   const size_t stats_end = off;
   P->arena_bytes = off;
   V2V_CUDA(cudaMalloc(&P->arena, P->arena_bytes));

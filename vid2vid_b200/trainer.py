@@ -149,4 +149,10 @@ class Trainer:
         D.optimizer_D.step()
         for s in range(len(loss_D_T)):
             getattr(D, 'optimizer_D_T' + str(s)).step()
-        return {k: float(v.detach()) for k, v in loss_dict.items()}, [{k: float(v.detach()) for k, v in d.items()} for d in loss_dict_T]
+        # ONE device -> host read per step: the loss values of all dictionaries stacked
+        keys = [(None, k) for k in loss_dict] + [(i, k) for i, d in enumerate(loss_dict_T) for k in d]
+        vals = torch.stack([(loss_dict if i is None else loss_dict_T[i])[k].detach().reshape(()).float() for i, k in keys]).tolist()
+        out, out_T = {}, [dict() for _ in loss_dict_T]
+        for (i, k), v in zip(keys, vals):
+            (out if i is None else out_T[i])[k] = v
+        return out, out_T
