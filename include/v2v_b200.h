@@ -239,7 +239,13 @@ int v2v_plan_set_training(v2v_plan* plan, int on);
 int v2v_plan_backward(v2v_plan* plan, void* const* io_ptrs, void* const* grad_io_ptrs, int n_io, const void* const* params,
                       void* const* param_grads, int n_params, v2v_stream_t stream);
 
+/* Lower the graph, pack the weights, build the TMA descriptors and the kernel list.  v2v_plan_finalize allocates the plan's
+ * arena (activation buffers, raw conv outputs, packed weights, statistics rows) itself; v2v_plan_finalize_ws places it in
+ * caller-owned device memory instead: `workspace` must be 1024-byte aligned and hold v2v_plan_workspace_bytes(plan) bytes
+ * (valid to ask BEFORE finalize: the layout is computed on the host), stays owned by the caller and must outlive the plan.
+ * (Training plans additionally allocate their gradient buffers and backward sub-plans themselves.) */
 int v2v_plan_finalize(v2v_plan* plan, v2v_stream_t stream);
+int v2v_plan_finalize_ws(v2v_plan* plan, void* workspace, int64_t workspace_bytes, v2v_stream_t stream);
 /* Re-read all weight pointers and repack (after an optimiser step / load_state_dict). */
 int v2v_plan_repack(v2v_plan* plan, v2v_stream_t stream);
 /* Run once.  io_ptrs[slot] = device pointer of the caller tensor bound to that slot.  use_graph: 0 eager, 1 replay the
@@ -254,7 +260,7 @@ int v2v_plan_profile(v2v_plan* plan, void* const* io_ptrs, int n_io, v2v_stream_
 /* Introspection (host logic tests, bench accounting). */
 int v2v_plan_num_kernels(const v2v_plan* plan);             /* kernels launched per run */
 double v2v_plan_conv_macs(const v2v_plan* plan);            /* algorithmic conv MACs per run (dense, unpadded) */
-int64_t v2v_plan_workspace_bytes(const v2v_plan* plan);
+int64_t v2v_plan_workspace_bytes(const v2v_plan* plan);       /* arena bytes; may be called before finalize (host only) */
 /* Writes a JSON description of the lowered plan (buffers, tiles, tap groups) into buf; returns needed size. */
 int64_t v2v_plan_describe(const v2v_plan* plan, char* buf, int64_t cap);
 

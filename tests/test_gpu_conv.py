@@ -182,3 +182,28 @@ def test_repack_after_weight_update():
         ref = E.run_units(list(runner.seq), E.r16(x))
     assert not torch.equal(a, b)
     _check(b, ref, 'after_repack')
+
+
+@pytest.mark.parametrize('mode', ['fast', 'precise'])
+def test_caller_provided_workspace(mode):
+    """v2v_plan_finalize_ws: the plan's arena in caller-owned memory gives bit-identical results; the size is known beforehand."""
+    from vid2vid_b200.plan import Plan
+    mods = [nn.ReflectionPad2d(1), nn.Conv2d(32, 64, 3), BN(64), nn.ReLU(True)] + NW._down(64, 64, BN) + NW._up(64, 32, BN)
+    runner = det_fill_(NW.SequentialRunner(mods), seed=9).cuda()
+    runner.precision = mode
+    x = _x(2, 32, 24, 40).cuda()
+    with torch.no_grad():
+        ref = runner(x)
+    p = Plan(x.device.index, precision=mode)
+    runner._describe(p, *x.shape)
+    need = p.workspace_bytes
+    assert need > 0
+    ws = torch.empty(need + 1024, dtype=torch.uint8, device=x.device)
+    with pytest.raises(ValueError):
+        p.finalize(workspace=ws[:need // 2])
+    p.finalize(workspace=ws)
+    out = torch.empty_like(ref)
+    p.run([x, out], use_graph=False)
+    p.run([x, out], use_graph=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref)

@@ -220,3 +220,21 @@ def test_flownet2_state_dict_keys_match_reference():
     ref = {k: s for k, s in keys}
     assert ours == ref, (sorted(set(ours) ^ set(ref))[:10], [k for k in ref if k in ours and ours[k] != ref[k]][:10])
     assert [k for k, _ in keys] == list(sd.keys())
+
+
+def test_workspace_bytes_is_known_before_finalize():
+    """include/v2v_b200.h: v2v_plan_workspace_bytes lays the arena out on the host, so a caller can allocate it and hand it to
+    v2v_plan_finalize_ws (no GPU involved in the sizing)."""
+    from vid2vid_b200.plan import Plan
+    opt = _street_opt()
+    g0 = NW.build_netG(opt, 0)
+    sizes = []
+    for mode in ('fast', 'precise'):
+        for (h, w) in ((128, 256), (256, 512)):
+            p = Plan(0, precision=mode)
+            g0._describe(p, 1, h, w)
+            assert not p.finalized
+            sizes.append(p.workspace_bytes)
+            assert p.workspace_bytes == sizes[-1]                     # idempotent
+    assert all(s > 0 and s % 1024 == 0 for s in sizes)
+    assert sizes[1] > sizes[0] and sizes[3] > sizes[2] and sizes[2] > sizes[0]      # grows with the frame and with the precise mode

@@ -355,7 +355,12 @@ struct v2v_plan {
   double conv_macs = 0.0;
   struct BiasAffine { float* scale; float* shift; const float* bias; int N, C, stride; };
   std::vector<BiasAffine> bias_affines;   // norm-less biased convs routed through the normalise pass (scale 1, shift bias)
-  // device
+  // arena layout (size_arena) and device memory
+  struct RawOff { size_t raw = 0, stats = 0, scale = 0, shift = 0; };
+  bool sized = false, arena_owned = true;
+  std::vector<size_t> act_off, w_off, corr_off;
+  std::vector<RawOff> raw_off;
+  size_t stats_begin = 0, stats_end = 0;
   void* arena = nullptr; size_t arena_bytes = 0;
   void** io_dev = nullptr;
   cudaGraphExec_t graph_exec = nullptr;
@@ -1074,7 +1079,7 @@ int v2v_plan_destroy(v2v_plan* p) {
   if (!p) return 0;
   if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
   if (p->graph_stream) cudaStreamDestroy(p->graph_stream);
-  if (p->arena) cudaFree(p->arena);
+  if (p->arena && p->arena_owned) cudaFree(p->arena);
   if (p->garena) cudaFree(p->garena);
   if (p->train_stats) cudaFree(p->train_stats);
   if (p->io_dev) cudaFree(p->io_dev);
@@ -1253,51 +1258,66 @@ int v2v_g_composite_ex(v2v_plan* p, int s_raw, int s_flow, int s_weight, int s_p
   return 0;
 }
 
-int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
-  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  V2V_REQUIRE(P && !P->finalized, V2V_ERR_STATE, "plan null or already finalized");
+// Host-only: lower the graph, choose every conv's tiling and lay the arena out (offsets only).  Idempotent.
+static int size_arena(v2v_plan* P) {
+  if (P->sized) return 0;
   int rc = lower(P); if (rc) return rc;
-  DeviceGuard guard(P->device);
-
-  // ---- size the arena
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = round_up_sz(off + bytes, 1024); return o; };
-  std::vector<size_t> act_off(P->acts.size());
-  for (size_t i = 0; i < P->acts.size(); ++i) act_off[i] = take(P->acts[i].elems() * sizeof(bf16));
-  struct RawOff { size_t raw, stats, scale, shift; };
-  std::vector<RawOff> raw_off(P->raws.size());
-  std::vector<size_t> w_off(P->gops.size(), 0);
+  P->act_off.assign(P->acts.size(), 0);
+  for (size_t i = 0; i < P->acts.size(); ++i) P->act_off[i] = take(P->acts[i].elems() * sizeof(bf16));
+  P->raw_off.assign(P->raws.size(), v2v_plan::RawOff{});
+  P->w_off.assign(P->gops.size(), 0);
   for (size_t i = 0; i < P->gops.size(); ++i) {
     GOp& op = P->gops[i];
     if (op.kind == G_CONV || op.kind == G_CONV_ACT || op.kind == G_HEAD) {
       fill_conv_params(P, op);
-      w_off[i] = take((size_t)P->sp() * (op.geom.headkx ? op.geom.headkx * op.conv.Cout : op.conv.Cout) * op.Ktotal * sizeof(bf16));
+      P->w_off[i] = take((size_t)P->sp() * (op.geom.headkx ? op.geom.headkx * op.conv.Cout : op.conv.Cout) * op.Ktotal * sizeof(bf16));
       if (op.kind == G_CONV) {
         Raw& r = P->raws[op.raw];
         r.desc.N = r.N; r.desc.H = r.H; r.desc.W = r.W; r.desc.Cvalid = r.C; r.desc.C = round_up(r.C, 8);
         r.desc.f32 = P->precise;
         if (P->impl == V2V_IMPL_UMMA) { r.tiles_per_img = op.kp.grid; r.num_phases = op.kp.num_phases; }
         else { r.tiles_per_img = 1; r.num_phases = 1; }
-        raw_off[op.raw].raw = take(r.desc.elems() * r.desc.elem_bytes());
-        raw_off[op.raw].scale = take((size_t)r.N * r.C * sizeof(float));
-        raw_off[op.raw].shift = take((size_t)r.N * r.C * sizeof(float));
+        P->raw_off[op.raw].raw = take(r.desc.elems() * r.desc.elem_bytes());
+        P->raw_off[op.raw].scale = take((size_t)r.N * r.C * sizeof(float));
+        P->raw_off[op.raw].shift = take((size_t)r.N * r.C * sizeof(float));
       }
     }
   }
-  std::vector<size_t> corr_off(P->gops.size(), 0);
+  P->corr_off.assign(P->gops.size(), 0);
   for (size_t i = 0; i < P->gops.size(); ++i)
     if (P->gops[i].kind == G_CORR) {
       const Value& a = P->values[P->gops[i].value_in], &o = P->values[P->gops[i].value_out];
-      corr_off[i] = take((2 * (size_t)a.N * a.C * a.H * a.W + (size_t)o.N * o.C * o.H * o.W) * sizeof(float));
+      P->corr_off[i] = take((2 * (size_t)a.N * a.C * a.H * a.W + (size_t)o.N * o.C * o.H * o.W) * sizeof(float));
     }
-  // all norm-statistics partials live in one contiguous region that is zeroed at the start of every run
-  // (a CTA only writes the (phase, image) rows it actually worked on)
-  const size_t stats_begin = off;
+  // all norm-statistics rows live in one contiguous region that is zeroed at the start of every run
+  P->stats_begin = off;
   for (size_t i = 0; i < P->raws.size(); ++i)
-    if (P->raws[i].conv_op >= 0 && !P->raws[i].no_stats) raw_off[i].stats = take((size_t)P->raws[i].N * 2 * P->raws[i].C * sizeof(stat_t) + 64);   // + ticket counter
-  const size_t stats_end = off;
+    if (P->raws[i].conv_op >= 0 && !P->raws[i].no_stats) P->raw_off[i].stats = take((size_t)P->raws[i].N * 2 * P->raws[i].C * sizeof(stat_t) + 64);   // + ticket counter
+  P->stats_end = off;
   P->arena_bytes = off;
-  V2V_CUDA(cudaMalloc(&P->arena, P->arena_bytes));
+  P->sized = true;
+  return 0;
+}
+
+static int finalize_impl(v2v_plan* P, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+  V2V_REQUIRE(P && !P->finalized, V2V_ERR_STATE, "plan null or already finalized");
+  int rc = size_arena(P); if (rc) return rc;
+  DeviceGuard guard(P->device);
+  const std::vector<size_t>& act_off = P->act_off;
+  const std::vector<v2v_plan::RawOff>& raw_off = P->raw_off;
+  const std::vector<size_t>& w_off = P->w_off;
+  const std::vector<size_t>& corr_off = P->corr_off;
+  const size_t stats_begin = P->stats_begin, stats_end = P->stats_end;
+  if (workspace) {
+    // caller-owned arena (v2v_plan_workspace_bytes before this call): not freed by v2v_plan_destroy
+    V2V_REQUIRE(workspace_bytes >= P->arena_bytes && (reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, V2V_ERR_INVALID,
+                "workspace of %zu bytes (1024-byte aligned) needed, got %zu at %p", P->arena_bytes, workspace_bytes, workspace);
+    P->arena = workspace; P->arena_owned = false;
+  } else {
+    V2V_CUDA(cudaMalloc(&P->arena, P->arena_bytes));
+  }
   V2V_CUDA(cudaMemsetAsync(P->arena, 0, P->arena_bytes, stream));
   V2V_CUDA(cudaMalloc(reinterpret_cast<void**>(&P->io_dev), sizeof(void*) * std::max(1, P->n_slots)));
   uint8_t* base = reinterpret_cast<uint8_t*>(P->arena);
@@ -1510,6 +1530,15 @@ int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
   return 0;
 }
 
+int v2v_plan_finalize(v2v_plan* P, v2v_stream_t stream_) {
+  return finalize_impl(P, nullptr, 0, reinterpret_cast<cudaStream_t>(stream_));
+}
+
+int v2v_plan_finalize_ws(v2v_plan* P, void* workspace, int64_t workspace_bytes, v2v_stream_t stream_) {
+  V2V_REQUIRE(workspace && workspace_bytes > 0, V2V_ERR_INVALID, "null workspace");
+  return finalize_impl(P, workspace, (size_t)workspace_bytes, reinterpret_cast<cudaStream_t>(stream_));
+}
+
 int v2v_plan_repack(v2v_plan* P, v2v_stream_t stream_) {
   V2V_REQUIRE(P && P->finalized, V2V_ERR_STATE, "plan not finalized");
   DeviceGuard guard(P->device);
@@ -1596,7 +1625,13 @@ double v2v_plan_conv_macs(const v2v_plan* P) {
   if (!P->lowered) lower(const_cast<v2v_plan*>(P));
   return P->conv_macs;
 }
-int64_t v2v_plan_workspace_bytes(const v2v_plan* P) { return P ? (int64_t)P->arena_bytes : 0; }
+int64_t v2v_plan_workspace_bytes(const v2v_plan* P_) {
+  // valid before v2v_plan_finalize(_ws): lowers the graph and lays the arena out on the host (no GPU work)
+  v2v_plan* P = const_cast<v2v_plan*>(P_);
+  if (!P) return 0;
+  if (!P->sized && size_arena(P)) return -1;
+  return (int64_t)P->arena_bytes;
+}
 
 int64_t v2v_plan_describe(const v2v_plan* P_, char* buf, int64_t cap) {
   v2v_plan* P = const_cast<v2v_plan*>(P_);

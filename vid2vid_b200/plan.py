@@ -152,8 +152,19 @@ class Plan:
         """The caller's current stream ON THE PLAN'S DEVICE (which need not be PyTorch's current device)."""
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
-    def finalize(self):
-        L.check(L.lib().v2v_plan_finalize(self._h, self._stream()))
+    def finalize(self, workspace=None):
+        """workspace: optional caller-owned uint8 CUDA tensor of at least workspace_bytes + 1024 bytes that holds the plan's arena
+        (v2v_plan_finalize_ws); the plan keeps a reference so that it outlives the kernels."""
+        if workspace is None:
+            L.check(L.lib().v2v_plan_finalize(self._h, self._stream()))
+        else:
+            need = self.workspace_bytes
+            base = (workspace.data_ptr() + 1023) // 1024 * 1024
+            avail = workspace.data_ptr() + workspace.numel() * workspace.element_size() - base
+            if avail < need:
+                raise ValueError('workspace holds %d usable bytes, the plan needs %d' % (avail, need))
+            self._workspace = workspace
+            L.check(L.lib().v2v_plan_finalize_ws(self._h, C.c_void_p(base), need, self._stream()))
         self.finalized = True
 
     def repack(self):
