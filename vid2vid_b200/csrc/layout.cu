@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(256) import_nchw_kernel(ImportParams p) {
       const float f0 = tile[2 * threadIdx.x][px], f1 = tile[2 * threadIdx.x + 1][px];
       bf16* d = o.base + o.offset(n, yp - o.pad_t, xo - o.pad_l) + cblk + 2 * threadIdx.x;
       *reinterpret_cast<uint32_t*>(d) = pack_bf16x2(f0, f1);
-      if (o.split) *reinterpret_cast<uint32_t*>(d + o.C) = pack_bf16x2(f0 - __bfloat162float(__float2bfloat16_rn(f0)),
+      if (o.split && !p.skip_lo) *reinterpret_cast<uint32_t*>(d + o.C) = pack_bf16x2(f0 - __bfloat162float(__float2bfloat16_rn(f0)),
                                                                       f1 - __bfloat162float(__float2bfloat16_rn(f1)));
     }
   } else {
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(256) import_nchw_kernel(ImportParams p) {
       const float f0 = tile[2 * cp][px], f1 = tile[2 * cp + 1][px];
       bf16* d = o.base + o.offset(n, yp - o.pad_t, xo - o.pad_l) + cblk + 2 * cp;
       *reinterpret_cast<uint32_t*>(d) = pack_bf16x2(f0, f1);
-      if (o.split) *reinterpret_cast<uint32_t*>(d + o.C) = pack_bf16x2(f0 - __bfloat162float(__float2bfloat16_rn(f0)),
+      if (o.split && !p.skip_lo) *reinterpret_cast<uint32_t*>(d + o.C) = pack_bf16x2(f0 - __bfloat162float(__float2bfloat16_rn(f0)),
                                                                       f1 - __bfloat162float(__float2bfloat16_rn(f1)));
     }
   }

@@ -1354,6 +1354,7 @@ static int finalize_impl(v2v_plan* P, void* workspace, size_t workspace_bytes, c
           x.imp.io = reinterpret_cast<const void* const*>(P->io_dev); x.imp.slot = op.slot;
           x.imp.c_off = op.c_off; x.imp.C_src = op.C_src;
           x.imp.out = P->acts[v.bufs[m]]; x.imp.pad_mode = P->act_pad_mode[v.bufs[m]];
+          x.imp.skip_lo = v.exact_bf16 ? 1 : 0;
           P->xops.push_back(x);
         }
         break;

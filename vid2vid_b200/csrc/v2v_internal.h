@@ -197,6 +197,8 @@ struct ImportParams {
   int c_off, C_src;        // channel window [c_off, c_off + out.Cvalid) of a tensor with C_src channels
   ActDesc out;
   int pad_mode;
+  int skip_lo;             // the caller promised values exact in bf16 (one-hot labels, edges): the lo half stays at the zeros the
+                           // arena was initialised with
 };
 // halo-padded NHWC bf16 interior -> fp32 NCHW (caller tensor)
 struct ExportParams {
