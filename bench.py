@@ -498,10 +498,15 @@ def run_train(args, rank, world, local_rank):
     l0 = L.LAUNCHES[0]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    pending = None
     for _ in range(K):
         a, b = A[:, t:t + tG].to(dev, non_blocking=True), B[:, t:t + tG].to(dev, non_blocking=True)     # H2D of the step's inputs
-        losses, _ = tr.step(a, b, a)                                                                  # float(loss) = D2H of the result
+        nxt = tr.step_async(a, b, a)           # the step's loss values start their way to pinned host memory (D2H every step)
+        if pending is not None:
+            losses, _ = pending.get()          # ... and are read one step late, so neither the host nor the GPU waits for the other
+        pending = nxt
         t += 1
+    losses, _ = pending.get()                  # (inside the timed region: the last step's losses complete it)
     e1.record()
     barrier()
     sampler.stop_flag = True
@@ -527,7 +532,9 @@ def run_train(args, rank, world, local_rank):
                       '(%.1f M fp32 gradients of [G | D | D_T0 | D_T1]) per step' % (world, tr.grads.numel / 1e6),
                       'frames_per_step': 1, 'generator_conv_flops_fwd_bwd_per_step': fl},
            'e2e': {'value': world * K / (ms * 1e-3), 'unit': 'clips/s', 'h2d_bytes_per_step': int(2 * tG * H * Wd * 4 + tG * 3 * H * Wd * 4),
-                   'd2h_bytes_per_step': 9 * 4, 'api': 'Trainer.step(host label / frame tensors) -> host loss values'},
+                   'd2h_bytes_per_step': 9 * 4,
+                   'api': 'Trainer.step_async(host label / frame tensors) -> PendingLosses.get() one step later (loss values in pinned host memory '
+                          'every step; the reference reads them every print_freq steps, train.py:102-107)'},
            'gpu_launches': launches, 'clocks': sampler.summary(),
            'all_reduce': {'ms_per_step': ar, 'share_of_step': ar / step_ms, 'bytes': tr.grads.numel * 4,
                           'algbw_gbs': tr.grads.numel * 4 / (ar * 1e-3) / 1e9 if ar > 0 else None, 'backend': 'nccl' if world > 1 else 'none (1 rank)'},

@@ -60,12 +60,14 @@ struct WgradParams {
   int m_tiles, n_tiles, ntaps, ksplit;
   int chunks_total, chunks_per_unit;
   int split;                   // 1: [hi | lo] operands, three MMAs per K step
+  int kxr;                     // taps per unit that share one IN patch (kw for stride-1 filters, else 1)
   int stages;
   WgradTap taps[V2V_MAX_TAPS];
   float* stage;                // [ntaps][Mp][Np] fp32, zeroed by the launcher
   int Mp, Np;                  // = a_C, b_C
 };
 size_t wgrad_stage_bytes(const WgradParams& p);
+size_t wgrad_stage_smem_bytes(const WgradParams& p);
 cudaError_t launch_wgrad_umma(const CUtensorMap& tmOut, const CUtensorMap& tmIn, const WgradParams& p, int R, int R1, int Cc,
                               float* dw, float* dw2, cudaStream_t s);
 cudaError_t launch_fold_add(const float* src, int Cs, int PH, int PW, float* dx, int N, int H, int W, int C, int pad, int reflect,

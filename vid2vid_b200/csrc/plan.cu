@@ -870,17 +870,29 @@ static int build_backward_units(v2v_plan* P, cudaStream_t stream) {
           w.taps[ky * c.kw + kx] = s2 ? WgradTap{(int8_t)(((ky & 1) << 1) | (kx & 1)), (int8_t)(ky >> 1), (int8_t)(kx >> 1), 0}
                                       : WgradTap{0, (int8_t)ky, (int8_t)kx, 0};
       V2V_REQUIRE(!s2 || a_in.parity, V2V_ERR_STATE, "internal: stride-2 weight gradient needs a parity-plane operand");
-      const int stage_bytes = (w.split ? 2 : 1) * (2 * kp * 128 + round_up(w.Nblocks * kp * w.b_row, 1024));
+      // stride-1 filters: the kw taps of a filter row share one IN patch (see wgrad_umma.cu) when their accumulators fit in TMEM
+      w.kxr = 1;
+      {
+        const char* ek = getenv("V2V_WG_KX");
+        const bool kx_ok = !(ek && ek[0] == '0');
+        if (kx_ok && u.mode == 1 && c.kw > 1 && kp + c.kw - 1 <= a_in.Wp) {
+          if (c.kw * std::max(32, w.BN) > 512 && w.BN == 128) {       // 7x7 over >= 128 channels: 64-wide N tiles (7 x 64 = 448 columns)
+            w.BN = 64; w.Nblocks = 1; w.n_tiles = (aB.C + 63) / 64;
+          }
+          if (c.kw * std::max(32, w.BN) <= 512) w.kxr = c.kw;
+        }
+      }
+      const int stage_bytes = (int)wgrad_stage_smem_bytes(w);
       w.stages = std::max(2, std::min(6, kSmemBudget / stage_bytes));
       w.chunks_total = w.N * w.gh * w.xsegs;
-      const int base_units = w.ntaps * w.m_tiles * w.n_tiles;
+      const int base_units = (w.ntaps / w.kxr) * w.m_tiles * w.n_tiles;
       const int want = std::max(1, (2 * device_sm_count() + base_units - 1) / base_units);
       w.chunks_per_unit = std::max(std::min(8, w.chunks_total), (w.chunks_total + want - 1) / want);
       w.ksplit = (w.chunks_total + w.chunks_per_unit - 1) / w.chunks_per_unit;
       // parameter gradient [R][Cc][taps]: rows = channels of OUT, columns = channels of IN
       u.M = u.mode == 2 ? c.Cin : c.Cout; u.M1 = u.mode == 2 ? c.Cin : c.Cout - c.Cout2; u.Nv = u.mode == 2 ? c.Cout : c.Cin;
       rc = make_tmap_act(&u.tmOut, a_out, kp, 1, std::min(a_out.C, 64)); if (rc) { P->bwd.push_back(u); return rc; }
-      rc = make_tmap_act(&u.tmIn, a_in, kp, 1, std::min(a_in.C, 64)); if (rc) { P->bwd.push_back(u); return rc; }
+      rc = make_tmap_act(&u.tmIn, a_in, kp + w.kxr - 1, 1, std::min(a_in.C, 64)); if (rc) { P->bwd.push_back(u); return rc; }
       u.wgrad = true;
       stage_max = std::max(stage_max, wgrad_stage_bytes(w));
     }

@@ -46,9 +46,15 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // A operand (M side, 128 rows of the accumulator): two 64-channel blocks of 128-byte rows.  B operand (N side): Nblocks
   // blocks of b_row bytes per pixel (128: 64 channels; 64 / 32: a 32- / 16-channel tensor in one block).
-  const int boxA = p.KP * 128, boxB = p.KP * p.b_row;
+  // kxr > 1 (stride-1 filters): a unit covers the kxr taps of one filter row.  The IN tensor is fetched once per chunk as a
+  // patch of KP + kxr - 1 pixels; tap kx reads it with the descriptor start advanced by kx pixel rows (rows are the K index of
+  // an MN-major operand; the swizzle applies to absolute address bits, so a row-shifted start stays consistent -- the same
+  // property the forward kernel's tap reuse rests on), each tap into its own accumulator columns.
+  const int pxA = p.KP + (p.swap ? p.kxr - 1 : 0), pxB = p.KP + (p.swap ? 0 : p.kxr - 1);
+  const int boxA = pxA * 128, boxB = pxB * p.b_row;               // bytes one TMA box delivers
+  const int blkA = (boxA + 1023) & ~1023, blkB = (boxB + 1023) & ~1023;      // block strides in shared memory (TMA destinations 1024-byte aligned)
   const int nh = p.split ? 2 : 1;
-  const int a_half = 2 * boxA, b_half = (p.Nblocks * boxB + 1023) & ~1023;
+  const int a_half = 2 * blkA, b_half = p.Nblocks * blkB;
   const int a_bytes = nh * a_half, b_bytes = nh * b_half;
   const int stage_bytes = a_bytes + b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
@@ -59,15 +65,18 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = p.BN;
-  const uint32_t tmem_cols = BN < 32 ? 32 : BN;
+  const int acc_cols = BN < 32 ? 32 : BN;                          // accumulator stride of one tap
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.kxr * acc_cols) tmem_cols <<= 1;
 
-  // unit -> (K split, tap, M tile, N tile), tiles fastest: the CTAs running together walk the same pixel range, so every
+  // unit -> (K split, tap group, M tile, N tile), tiles fastest: the CTAs running together walk the same pixel range, so every
   // operand row is fetched from HBM once and then served by L2 to the other (tap, tile) units
   int u = blockIdx.x;
   const int nt = u % p.n_tiles; u /= p.n_tiles;
   const int mt = u % p.m_tiles; u /= p.m_tiles;
-  const int tap = u % p.ntaps;
-  const int ks = u / p.ntaps;
+  const int ngroups = p.ntaps / p.kxr;
+  const int tap = (u % ngroups) * p.kxr;                           // first tap of the group
+  const int ks = u / ngroups;
   const int c_begin = ks * p.chunks_per_unit;
   const int c_end = min(p.chunks_total, c_begin + p.chunks_per_unit);
   const int nchunks = c_end - c_begin;                           // >= 1 by construction (launcher)
@@ -104,16 +113,16 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_consta
       for (int c = 0; c < nchunks; ++c) {
         uint8_t* st = smem + (size_t)s * stage_bytes;
         mbar_wait(&empty[s], par ^ 1);
-        mbar_expect_tx(&full[s], (uint32_t)(nh * (2 * boxA + p.Nblocks * boxB)));
+        mbar_expect_tx(&full[s], (uint32_t)(nh * (2 * boxA + p.Nblocks * boxB)));      // (what the boxes deliver, not the padded slots)
         for (int hf = 0; hf < nh; ++hf)
           for (int mb = 0; mb < 2; ++mb) {
             // a 64-channel A tensor fills both halves of the M = 128 tile with the same block (rows 64.. are not stored)
             const int blk = p.Mblocks == 2 ? mt * 2 + mb : mt;
-            tma_load_5d(st + (size_t)hf * a_half + (size_t)mb * boxA, tmA, &full[s], hf * p.a_C + blk * 64, xs * p.KP + ax, y + ay, apl, img);
+            tma_load_5d(st + (size_t)hf * a_half + (size_t)mb * blkA, tmA, &full[s], hf * p.a_C + blk * 64, xs * p.KP + ax, y + ay, apl, img);
           }
         for (int hf = 0; hf < nh; ++hf)
           for (int nb = 0; nb < p.Nblocks; ++nb)
-            tma_load_5d(st + a_bytes + (size_t)hf * b_half + (size_t)nb * boxB, tmB, &full[s], hf * p.b_C + (nt * p.Nblocks + nb) * 64,
+            tma_load_5d(st + a_bytes + (size_t)hf * b_half + (size_t)nb * blkB, tmB, &full[s], hf * p.b_C + (nt * p.Nblocks + nb) * 64,
                         xs * p.KP + bx, y + by, bpl, img);
         if (++s == p.stages) { s = 0; par ^= 1; }
         if (++xs == p.xsegs) { xs = 0; if (++y == p.gh) { y = 0; ++img; } }
@@ -125,19 +134,23 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_consta
       const int ps_step = p.split ? 1 : 3;
       const int b_layout = p.b_row == 128 ? 2 : (p.b_row == 64 ? 4 : 6);
       const int b_kstep = 16 * p.b_row, b_sbo = 8 * p.b_row;        // 16 pixels per MMA = two 8-row groups
+      const int a_shift = p.swap ? 128 : 0, b_shift = p.swap ? 0 : p.b_row;      // one pixel row of the IN patch per tap
       int s = 0; uint32_t par = 0;
       uint32_t first = 0;
       for (int c = 0; c < nchunks; ++c) {
         mbar_wait(&full[s], par);
         tcgen05_fence_after();
         const uint32_t a0 = smem_u32(smem + (size_t)s * stage_bytes), b0 = a0 + a_bytes;
-        for (int ps = 0; ps < 3; ps += ps_step) {
-          const uint32_t a = a0 + (ps == 1 ? a_half : 0), b = b0 + (ps == 2 ? b_half : 0);
-          for (int k = 0; k < p.kmma; ++k) {
-            umma_bf16(tmem_base, make_mnmajor_desc(a + k * 2048, boxA, 1024, 2), make_mnmajor_desc(b + k * b_kstep, boxB, b_sbo, b_layout), idesc, first);
-            first = 1u;
+        for (int kx = 0; kx < p.kxr; ++kx) {
+          const uint32_t tmem_d = tmem_base + kx * acc_cols;
+          for (int ps = 0; ps < 3; ps += ps_step) {
+            const uint32_t a = a0 + (ps == 1 ? a_half : 0) + kx * a_shift, b = b0 + (ps == 2 ? b_half : 0) + kx * b_shift;
+            for (int k = 0; k < p.kmma; ++k)
+              umma_bf16(tmem_d, make_mnmajor_desc(a + k * 2048, blkA, 1024, 2), make_mnmajor_desc(b + k * b_kstep, blkB, b_sbo, b_layout), idesc,
+                        (first | (uint32_t)(ps > 0) | (uint32_t)(k > 0)) ? 1u : 0u);
           }
         }
+        first = 1u;
         umma_commit(&empty[s]);
         if (++s == p.stages) { s = 0; par ^= 1; }
       }
@@ -151,18 +164,20 @@ wgrad_umma_kernel(const __grid_constant__ CUtensorMap tmOut, const __grid_consta
     mbar_wait(acc_full, 0);
     tcgen05_fence_after();
     const int n0 = nt * BN;
-    float* dst = p.stage + ((size_t)tap * p.Mp + (valid ? m : 0)) * p.Np + n0;
-    for (int c = 0; c < BN / 16; ++c) {
-      uint32_t r[16];
-      tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c * 16, r);
-      tmem_ld_wait();
-      if (valid) {
+    for (int kx = 0; kx < p.kxr; ++kx) {
+      float* dst = p.stage + ((size_t)(tap + kx) * p.Mp + (valid ? m : 0)) * p.Np + n0;
+      for (int c = 0; c < BN / 16; ++c) {
+        uint32_t r[16];
+        tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kx * acc_cols + c * 16, r);
+        tmem_ld_wait();
+        if (valid) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (n0 + c * 16 + j * 4 < p.Np)
-            atomicAdd(reinterpret_cast<float4*>(dst + c * 16 + j * 4),
-                      make_float4(__uint_as_float(r[j * 4]), __uint_as_float(r[j * 4 + 1]), __uint_as_float(r[j * 4 + 2]),
-                                  __uint_as_float(r[j * 4 + 3])));
+          for (int j = 0; j < 4; ++j)
+            if (n0 + c * 16 + j * 4 < p.Np)
+              atomicAdd(reinterpret_cast<float4*>(dst + c * 16 + j * 4),
+                        make_float4(__uint_as_float(r[j * 4]), __uint_as_float(r[j * 4 + 1]), __uint_as_float(r[j * 4 + 2]),
+                                    __uint_as_float(r[j * 4 + 3])));
+        }
       }
     }
   }
@@ -189,12 +204,18 @@ __global__ void __launch_bounds__(256) unstage_wgrad_kernel(const float* __restr
 
 size_t wgrad_stage_bytes(const WgradParams& p) { return (size_t)p.ntaps * p.Mp * p.Np * sizeof(float); }
 
+// shared memory of one pipeline stage (must match the kernel's layout)
+size_t wgrad_stage_smem_bytes(const WgradParams& p) {
+  const int pxA = p.KP + (p.swap ? p.kxr - 1 : 0), pxB = p.KP + (p.swap ? 0 : p.kxr - 1);
+  const size_t blkA = ((size_t)pxA * 128 + 1023) & ~(size_t)1023, blkB = ((size_t)pxB * p.b_row + 1023) & ~(size_t)1023;
+  return (size_t)(p.split ? 2 : 1) * (2 * blkA + p.Nblocks * blkB);
+}
+
 cudaError_t launch_wgrad_umma(const CUtensorMap& tmOut, const CUtensorMap& tmIn, const WgradParams& p, int R, int R1, int Cc,
                               float* dw, float* dw2, cudaStream_t s) {
   cudaError_t e = cudaMemsetAsync(p.stage, 0, wgrad_stage_bytes(p), s);
   if (e != cudaSuccess) return e;
-  const int nh = p.split ? 2 : 1;
-  const size_t stage_bytes = (size_t)nh * (2 * p.KP * 128 + ((p.Nblocks * p.KP * p.b_row + 1023) & ~1023));
+  const size_t stage_bytes = wgrad_stage_smem_bytes(p);
   const size_t smem = (size_t)p.stages * stage_bytes + 1024 + (2 * p.stages + 2) * sizeof(uint64_t);
   static size_t configured = 0;
   if (smem > configured) {
@@ -202,9 +223,9 @@ cudaError_t launch_wgrad_umma(const CUtensorMap& tmOut, const CUtensorMap& tmIn,
     if (e != cudaSuccess) return e;
     configured = smem;
   }
-  const int units = p.ntaps * p.m_tiles * p.n_tiles * p.ksplit;
+  const int units = (p.ntaps / p.kxr) * p.m_tiles * p.n_tiles * p.ksplit;
   static const bool log = getenv("V2V_WG_LOG") != nullptr;        // one line per launch, to pair with a profiler's kernel list
-  if (log) fprintf(stderr, "wgrad grid %dx%dx%d taps %d aC %d bC %d BN %d swap %d KP %d units %d (ksplit %d x %d chunks) R %d Cc %d\n", p.N, p.gh, p.gw,
+  if (log) fprintf(stderr, "wgrad kxr %d grid %dx%dx%d taps %d aC %d bC %d BN %d swap %d KP %d units %d (ksplit %d x %d chunks) R %d Cc %d\n", p.kxr, p.N, p.gh, p.gw,
                    p.ntaps, p.a_C, p.b_C, p.BN, p.swap, p.KP, units, p.ksplit, p.chunks_per_unit, R, Cc);
   wgrad_umma_kernel<<<units, kWgThreads, smem, s>>>(tmOut, tmIn, p);
   e = cudaGetLastError();

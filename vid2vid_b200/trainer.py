@@ -130,8 +130,8 @@ class Trainer:
         loss_G, loss_D, loss_D_T, t_act = D.get_losses(loss_dict, loss_dict_T, self.t_scales)
         return loss_G, loss_D, loss_D_T, loss_dict, loss_dict_T
 
-    def step(self, input_A, input_B, inst_A):
-        """One iteration of train.py's inner loop on this rank's shard of the batch."""
+    def step_async(self, input_A, input_B, inst_A):
+        """One iteration of train.py's inner loop on this rank's shard of the batch; returns the PendingLosses of the step."""
         G, D = self.modelG, self.modelD
         loss_G, loss_D, loss_D_T, loss_dict, loss_dict_T = self.losses(input_A, input_B, inst_A)
         # backward passes in the reference's order (train.py:83-90): the generator loss also back-propagates through the
@@ -149,10 +149,36 @@ class Trainer:
         D.optimizer_D.step()
         for s in range(len(loss_D_T)):
             getattr(D, 'optimizer_D_T' + str(s)).step()
-        # ONE device -> host read per step: the loss values of all dictionaries stacked
+        # ONE device -> host read per step: the loss values of all dictionaries stacked, copied to pinned host memory
+        # asynchronously; PendingLosses.get() waits for that copy only
         keys = [(None, k) for k in loss_dict] + [(i, k) for i, d in enumerate(loss_dict_T) for k in d]
-        vals = torch.stack([(loss_dict if i is None else loss_dict_T[i])[k].detach().reshape(()).float() for i, k in keys]).tolist()
-        out, out_T = {}, [dict() for _ in loss_dict_T]
-        for (i, k), v in zip(keys, vals):
+        vals = torch.stack([(loss_dict if i is None else loss_dict_T[i])[k].detach().reshape(()).float() for i, k in keys])
+        return PendingLosses(keys, vals, len(loss_dict_T))
+
+    def step(self, input_A, input_B, inst_A):
+        """One iteration of train.py's inner loop on this rank's shard of the batch -> (loss dict, [temporal loss dicts]) as
+        Python floats (blocks until the step has finished on the GPU, as reading `v.data.item()` in train.py:104 does)."""
+        return self.step_async(input_A, input_B, inst_A).get()
+
+
+class PendingLosses:
+    """Loss values of a step on their way to the host.  The reference reads them every print_freq steps (train.py:102-107); a
+    training loop that reads every step can do so one step late -- issue step n + 1, then get() step n -- so that the host
+    never waits for the GPU and the GPU never waits for the host."""
+
+    def __init__(self, keys, vals, n_T):
+        self.keys, self.n_T = keys, n_T
+        self.host = torch.empty(vals.shape, dtype=torch.float32, pin_memory=vals.is_cuda)
+        self.host.copy_(vals, non_blocking=True)
+        self.event = None
+        if vals.is_cuda:
+            self.event = torch.cuda.Event()
+            self.event.record(torch.cuda.current_stream(vals.device))
+
+    def get(self):
+        if self.event is not None:
+            self.event.synchronize()
+        out, out_T = {}, [dict() for _ in range(self.n_T)]
+        for (i, k), v in zip(self.keys, self.host.tolist()):
             (out if i is None else out_T[i])[k] = v
         return out, out_T
