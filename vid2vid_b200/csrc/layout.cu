@@ -5,6 +5,8 @@
 // The boundary tensors are the ones Vid2VidModelG passes to netG.forward
 // (models/vid2vid_model_G.py:225-226); caller pointers are read from a small device-side IO
 // table so the captured CUDA graph stays valid when PyTorch hands us new tensors every frame.
+#include <cstdlib>
+#include <algorithm>
 #include "ptx.cuh"
 #include "v2v_internal.h"
 
@@ -235,7 +237,75 @@ cudaError_t launch_export_nchw(const ExportParams& p, cudaStream_t stream) {
   return launch_pdl(export_nchw_kernel, grid, block, 0, stream, p);
 }
 
+// Tiled variant for plain convs (forward packing and the data-gradient packing of stride-1 convs): a block stages a
+// [TC output channels][32 input channels][taps] tile of the torch-layout tensor through shared memory, so both the fp32 reads
+// (32 * taps contiguous floats per output channel) and the bf16 writes (32 / TC contiguous K columns per row and tap) are
+// coalesced; the elementwise kernel above reads with a stride of kh * kw floats.  Every optimiser step re-packs every weight of
+// the forward plans and of the backward sub-plans (~0.9 G parameters at cfg3), which made this kernel 4 % of a training step.
+__global__ void __launch_bounds__(256) pack_weights_tiled_kernel(PackParams p, int TC) {
+  extern __shared__ float wt[];                       // [TC][32][tstride] with odd strides (conflict-free along either channel axis)
+  const int taps = p.kh * p.kw, tstride = taps | 1, astride = 32 * tstride + 1;
+  // forward tensors: [Cf_out][Cf_in][taps]; dgrad packing sees them as [p.Cin][p.Cout][taps], plain packing as [p.Cout][p.Cin][taps]
+  const int f_out = p.dgrad ? p.Cin : p.Cout, f_in = p.dgrad ? p.Cout : p.Cin;
+  const int co0 = blockIdx.y * TC, ci0 = blockIdx.x * 32;
+  for (int i = threadIdx.x; i < TC * 32 * taps; i += 256) {
+    const int a = i / (32 * taps), r = i - a * (32 * taps);
+    const int b = r / taps, t = r - b * taps;
+    const int co = co0 + a, ci = ci0 + b;
+    float v = 0.f;
+    if (co < f_out && ci < f_in) {
+      if (p.w2 && co >= p.Cout1) v = p.w2[((size_t)(co - p.Cout1) * f_in + ci) * taps + t];
+      else v = p.w[((size_t)co * f_in + ci) * taps + t];
+    }
+    wt[a * astride + b * tstride + t] = v;
+  }
+  __syncthreads();
+  const int K = p.ntaps * p.Cp;
+  if (!p.dgrad) {
+    // out[co][t * Cp + ci]: ci fastest
+    for (int i = threadIdx.x; i < TC * taps * 32; i += 256) {
+      const int b = i & 31, r = i >> 5;
+      const int t = r % taps, a = r / taps;
+      const int co = co0 + a, ci = ci0 + b;
+      if (co >= p.Cout || ci >= p.Cp) continue;
+      const float v = wt[a * astride + b * tstride + t];
+      const size_t k = (size_t)t * p.Cp + ci;
+      if (p.split) split_bf16(v, p.out[(size_t)co * 2 * K + k], p.out[(size_t)co * 2 * K + K + k]);
+      else p.out[(size_t)co * K + k] = __float2bfloat16_rn(v);
+    }
+  } else {
+    // out[ci_f][t' * Cp + co_f] with t' the flipped tap: co_f fastest
+    for (int i = threadIdx.x; i < 32 * taps * TC; i += 256) {
+      const int a = i % TC, r = i / TC;
+      const int t = r % taps, b = r / taps;
+      const int co = co0 + a, ci = ci0 + b;                  // forward output / input channel
+      if (ci >= p.Cout || co >= p.Cp) continue;              // rows = forward input channels (p.Cout of this conv), K channels padded to Cp
+      const float v = wt[a * astride + b * tstride + (taps - 1 - t)];
+      const size_t k = (size_t)t * p.Cp + co;
+      if (p.split) split_bf16(v, p.out[(size_t)ci * 2 * K + k], p.out[(size_t)ci * 2 * K + K + k]);
+      else p.out[(size_t)ci * K + k] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
 cudaError_t launch_pack_weights(const PackParams& p, cudaStream_t stream) {
+  const int taps = p.kh * p.kw;
+  bool natural = !p.transposed && !p.headkx && p.ntaps == taps;
+  for (int t = 0; t < taps && natural; ++t) natural = (p.tap_ky[t] * p.kw + p.tap_kx[t] == t);
+  static const bool tiled_ok = [] { const char* e = getenv("V2V_PACK_TILED"); return !(e && e[0] == '0'); }();
+  if (natural && tiled_ok) {
+    const int tstride = taps | 1;
+    int TC = 32;
+    while (TC > 4 && (size_t)TC * (32 * tstride + 1) * sizeof(float) > 40 * 1024) TC >>= 1;
+    if ((size_t)TC * (32 * tstride + 1) * sizeof(float) <= 48 * 1024) {
+      // grid: x over the 32-wide tiles of the forward INPUT channel axis, y over TC-wide tiles of the forward OUTPUT channel axis;
+      // each axis covers the padded extent where it is the K axis of the packed matrix (zero fill)
+      const int f_out = p.dgrad ? std::max(p.Cin, p.Cp) : p.Cout, f_in = p.dgrad ? p.Cout : std::max(p.Cin, p.Cp);
+      dim3 grid((f_in + 31) / 32, (f_out + TC - 1) / TC);
+      pack_weights_tiled_kernel<<<grid, 256, (size_t)TC * (32 * tstride + 1) * sizeof(float), stream>>>(p, TC);
+      return cudaGetLastError();
+    }
+  }
   const long long total = (long long)(p.headkx ? p.headkx * p.Cout : p.Cout) * p.ntaps * p.Cp;
   long long b = (total + 255) / 256;
   if (b > 148 * 16) b = 148 * 16;
