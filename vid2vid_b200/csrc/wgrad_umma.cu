@@ -10,7 +10,8 @@
 // 8-K groups 1024 bytes apart, 64-element blocks one box apart), so no transposed copy of any tensor is made: the same
 // bytes serve the forward conv K-major and this kernel MN-major.
 //
-// One CTA per work unit (tap, M tile of 128 channels of one tensor, N tile of 16 .. 128 channels of the other, K split); the K
+// One CTA per work unit (filter row or single tap, M tile of 128 channels of one tensor, N tile of 16 .. 128 channels of the
+// other, K split); the K
 // loop walks row segments of KP pixels through a ring of shared-memory stages:
 //   warp 0     TMA producer (one elected lane)
 //   warp 1     tcgen05.mma issuer (one elected lane) + TMEM owner; precise plans accumulate OUT_hi*IN_hi + OUT_lo*IN_hi +
