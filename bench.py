@@ -439,6 +439,7 @@ def run_train(args, rank, world, local_rank):
     gradients on wgrad_umma_kernel, both in the split-bf16 precise arithmetic; norm / head / composite / loss backward on CUDA
     cores), ONE flat NCCL all-reduce over [G | D | D_T] and the Adam steps.  value = clips
     (= generated frames) per second over all ranks; the all-reduce is timed separately with CUDA events."""
+    import gc
     import torch
     import torch.distributed as dist
     from vid2vid_b200 import _lib as L
@@ -499,16 +500,22 @@ def run_train(args, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     pending = None
+    gc.collect()
+    gc.disable()          # (a generation-2 collection over the module / plan object graph inside a ~1 s region costs 10 % of it)
+    step_wall = []
     for _ in range(K):
+        t_wall = time.perf_counter()
         a, b = A[:, t:t + tG].to(dev, non_blocking=True), B[:, t:t + tG].to(dev, non_blocking=True)     # H2D of the step's inputs
         nxt = tr.step_async(a, b, a)           # the step's loss values start their way to pinned host memory (D2H every step)
         if pending is not None:
             losses, _ = pending.get()          # ... and are read one step late, so neither the host nor the GPU waits for the other
         pending = nxt
         t += 1
+        step_wall.append((time.perf_counter() - t_wall) * 1e3)
     losses, _ = pending.get()                  # (inside the timed region: the last step's losses complete it)
     e1.record()
     barrier()
+    gc.enable()
     sampler.stop_flag = True
     ms = e0.elapsed_time(e1)
     launches = L.LAUNCHES[0] - l0
@@ -538,6 +545,7 @@ def run_train(args, rank, world, local_rank):
            'gpu_launches': launches, 'clocks': sampler.summary(),
            'all_reduce': {'ms_per_step': ar, 'share_of_step': ar / step_ms, 'bytes': tr.grads.numel * 4,
                           'algbw_gbs': tr.grads.numel * 4 / (ar * 1e-3) / 1e9 if ar > 0 else None, 'backend': 'nccl' if world > 1 else 'none (1 rank)'},
+           'host_ms_per_step_issue': [round(x, 1) for x in step_wall],
            'hbm_used_gb': round((torch.cuda.mem_get_info(dev)[1] - torch.cuda.mem_get_info(dev)[0]) / 2 ** 30, 1),
            'roofline': {'bound': 'tensor', 'kernel': 'generator convolutions: forward + data gradient (conv_umma_kernel) + weight gradient (wgrad_umma_kernel)', 'achieved': fl / (step_ms * 1e-3) / 1e12,
                         'peak': peak_burst, 'unit': 'TFLOP/s', 'frac': fl / (step_ms * 1e-3) / 1e12 / peak_burst, 'peak_source': peak_src,

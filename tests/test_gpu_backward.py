@@ -77,6 +77,8 @@ TENSOR_UNITS = [
     ('t_d_k4s1', lambda: [nn.Conv2d(64, 128, 4, stride=1, padding=2), BN(128), nn.LeakyReLU(0.2, True)], (1, 64, 12, 40)),
     ('t_d_k4s2', lambda: [nn.Conv2d(64, 128, 4, stride=2, padding=2), BN(128), nn.LeakyReLU(0.2, True)], (1, 64, 16, 80)),      # cropped transposed conv
     ('t_resblock128', lambda: [NW.ResnetBlock(128, 'reflect', BN)], (1, 128, 16, 32)),
+    ('t_c3_256_128', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(256, 128, 3), BN(128), nn.ReLU(True)], (1, 256, 8, 40)),   # 256-wide N tile
+    ('t_c3_320_64', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(320, 64, 3), BN(64), nn.ReLU(True)], (1, 320, 8, 40)),     # partial 256-wide tile
     # one narrow operand (16 / 32 padded channels) on the N side of the weight-gradient GEMM
     ('t_stem6', lambda: NW._stem(6, 64, BN), (1, 6, 12, 40)),                                                            # narrow activation
     ('t_c3_24_128', lambda: [nn.ReflectionPad2d(1), nn.Conv2d(24, 128, 3), BN(128), nn.ReLU(True)], (1, 24, 10, 40)),    # 32-channel rows
@@ -113,6 +115,15 @@ def test_tensor_core_backward_units(unit, monkeypatch):
         except AssertionError as e:
             bad.append(str(e)[:160])
     assert not bad, bad
+
+
+@pytest.mark.parametrize('name', ['t_c3_128', 't_d_k4s1', 't_stem6', 't_c3_24_128', 't_d_last', 't_head_tanh', 't_head_both_narrow'])
+def test_weight_gradient_tap_rows(name, monkeypatch):
+    """V2V_WG_KX=1: the kw taps of a filter row share one patch of the activation-side operand (row-shifted MN-major descriptors,
+    one accumulator per tap) -- measured no faster than one unit per tap (profiles/r02i_wgrad_layers.txt) and therefore off by
+    default, kept correct here."""
+    monkeypatch.setenv('V2V_WG_KX', '1')
+    test_tensor_core_backward_units([u for u in TENSOR_UNITS if u[0] == name][0], monkeypatch)
 
 
 HEADS = [

@@ -870,17 +870,18 @@ static int build_backward_units(v2v_plan* P, cudaStream_t stream) {
           w.taps[ky * c.kw + kx] = s2 ? WgradTap{(int8_t)(((ky & 1) << 1) | (kx & 1)), (int8_t)(ky >> 1), (int8_t)(kx >> 1), 0}
                                       : WgradTap{0, (int8_t)ky, (int8_t)kx, 0};
       V2V_REQUIRE(!s2 || a_in.parity, V2V_ERR_STATE, "internal: stride-2 weight gradient needs a parity-plane operand");
-      // stride-1 filters: the kw taps of a filter row share one IN patch (see wgrad_umma.cu) when their accumulators fit in TMEM
+      // Measured (profiles/r02i_wgrad_layers.txt): an MN-major MMA costs ~100 cycles whatever N <= 128 is (twice the K-major
+      // rate at N = 128), so this kernel is MMA-issue bound, not operand-traffic bound: the widest N per instruction wins.
+      //   * 256-wide N tiles when the N-side tensor has >= 256 channels (one accumulator of 256 TMEM columns);
+      //   * sharing one IN patch between the kw taps of a filter row (kxr = kw, V2V_WG_KX=1) saves operand traffic only and
+      //     measured neutral to slower (1024->1024: 98 -> 103 us; 7x7 with 64-wide tiles 1.9 -> 3.3 ms): off by default.
       w.kxr = 1;
       {
         const char* ek = getenv("V2V_WG_KX");
-        const bool kx_ok = !(ek && ek[0] == '0');
-        if (kx_ok && u.mode == 1 && c.kw > 1 && kp + c.kw - 1 <= a_in.Wp) {
-          if (c.kw * std::max(32, w.BN) > 512 && w.BN == 128) {       // 7x7 over >= 128 channels: 64-wide N tiles (7 x 64 = 448 columns)
-            w.BN = 64; w.Nblocks = 1; w.n_tiles = (aB.C + 63) / 64;
-          }
-          if (c.kw * std::max(32, w.BN) <= 512) w.kxr = c.kw;
-        }
+        const bool kx_on = ek && ek[0] == '1';
+        if (kx_on && u.mode == 1 && c.kw > 1 && kp + c.kw - 1 <= a_in.Wp && c.kw * std::max(32, w.BN) <= 512) w.kxr = c.kw;
+        const char* e2 = getenv("V2V_WG_N256");
+        if (w.kxr == 1 && aB.C >= 256 && !(e2 && e2[0] == '0')) { w.BN = 256; w.Nblocks = 4; w.n_tiles = (aB.C + 255) / 256; }
       }
       const int stage_bytes = (int)wgrad_stage_smem_bytes(w);
       w.stages = std::max(2, std::min(6, kSmemBudget / stage_bytes));
