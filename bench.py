@@ -489,10 +489,15 @@ def run_train(args, rank, world, local_rank):
         ar_ms.append((e0, e1))
     tr.grads.all_reduce_mean = timed_ar
     t = 0
-    for _ in range(Wm):
+    pending = None
+    for _ in range(Wm):        # same pipelined pattern as the timed region (it also sizes the caching allocator's pool for it)
         a, b = A[:, t:t + tG].to(dev, non_blocking=True), B[:, t:t + tG].to(dev, non_blocking=True)
-        tr.step(a, b, a)
+        nxt = tr.step_async(a, b, a)
+        if pending is not None:
+            pending.get()
+        pending = nxt
         t += 1
+    pending.get()
     barrier()
     ar_ms.clear()
     sampler.recording = True

@@ -25,18 +25,20 @@ A = synth_label_sequence(T, H, Wd, label_nc=35, block=64, seed=0).cuda()
 g = torch.Generator().manual_seed(77)
 coarse = torch.rand(T, 3, H // 16, Wd // 16, generator=g) * 2 - 1
 B = torch.nn.functional.interpolate(coarse, size=(H, Wd), mode='bilinear', align_corners=False).view(1, T, 3, H, Wd).cuda()
-for t in range(5):
-    tr.step(A[:, t:t + tG], B[:, t:t + tG], A[:, t:t + tG])
+NW_ = int(os.environ.get('PROFILE_WARMUP', '5'))
+for t in range(NW_):
+    tr.step(A[:, t % 9:t % 9 + tG], B[:, t % 9:t % 9 + tG], A[:, t % 9:t % 9 + tG])
 torch.cuda.synchronize()
 if os.environ.get('PROFILE_CPU'):
     import cProfile, pstats, time
     pr = cProfile.Profile()
     t0 = time.time()
     pr.enable()
-    for t in range(5, 8):
-        tr.step(A[:, t:t + tG], B[:, t:t + tG], A[:, t:t + tG])
-    torch.cuda.synchronize()
+    pend = [tr.step_async(A[:, t:t + tG], B[:, t:t + tG], A[:, t:t + tG]) for t in range(5, 8)]
     pr.disable()
+    t1 = time.time()
+    torch.cuda.synchronize()
+    print('host issue time of 3 steps: %.1f ms each (then %.1f ms until the GPU was done)' % ((t1 - t0) / 3 * 1e3, (time.time() - t1) * 1e3))
     print('3 steps wall %.1f ms each' % ((time.time() - t0) / 3 * 1e3))
     st = pstats.Stats(pr)
     st.sort_stats('cumulative').print_stats(45)
