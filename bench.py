@@ -489,35 +489,25 @@ def run_train(args, rank, world, local_rank):
         ar_ms.append((e0, e1))
     tr.grads.all_reduce_mean = timed_ar
     t = 0
-    pending = None
-    for _ in range(Wm):        # same pipelined pattern as the timed region (it also sizes the caching allocator's pool for it)
+    for _ in range(Wm):
         a, b = A[:, t:t + tG].to(dev, non_blocking=True), B[:, t:t + tG].to(dev, non_blocking=True)
-        nxt = tr.step_async(a, b, a)
-        if pending is not None:
-            pending.get()
-        pending = nxt
+        tr.step(a, b, a)
         t += 1
-    pending.get()
     barrier()
     ar_ms.clear()
     sampler.recording = True
     l0 = L.LAUNCHES[0]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    pending = None
     gc.collect()
     gc.disable()          # (a generation-2 collection over the module / plan object graph inside a ~1 s region costs 10 % of it)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     step_wall = []
     for _ in range(K):
         t_wall = time.perf_counter()
         a, b = A[:, t:t + tG].to(dev, non_blocking=True), B[:, t:t + tG].to(dev, non_blocking=True)     # H2D of the step's inputs
-        nxt = tr.step_async(a, b, a)           # the step's loss values start their way to pinned host memory (D2H every step)
-        if pending is not None:
-            losses, _ = pending.get()          # ... and are read one step late, so neither the host nor the GPU waits for the other
-        pending = nxt
+        losses, _ = tr.step(a, b, a)           # ... and the D2H read of its loss values (one stacked copy to pinned host memory)
         t += 1
         step_wall.append((time.perf_counter() - t_wall) * 1e3)
-    losses, _ = pending.get()                  # (inside the timed region: the last step's losses complete it)
     e1.record()
     barrier()
     gc.enable()
@@ -545,12 +535,12 @@ def run_train(args, rank, world, local_rank):
                       'frames_per_step': 1, 'generator_conv_flops_fwd_bwd_per_step': fl},
            'e2e': {'value': world * K / (ms * 1e-3), 'unit': 'clips/s', 'h2d_bytes_per_step': int(2 * tG * H * Wd * 4 + tG * 3 * H * Wd * 4),
                    'd2h_bytes_per_step': 9 * 4,
-                   'api': 'Trainer.step_async(host label / frame tensors) -> PendingLosses.get() one step later (loss values in pinned host memory '
-                          'every step; the reference reads them every print_freq steps, train.py:102-107)'},
+                   'api': 'Trainer.step(host label / frame tensors) -> host loss values, every step (the reference reads them every '
+                          'print_freq steps, train.py:102-107; Trainer.step_async defers the read)'},
            'gpu_launches': launches, 'clocks': sampler.summary(),
            'all_reduce': {'ms_per_step': ar, 'share_of_step': ar / step_ms, 'bytes': tr.grads.numel * 4,
                           'algbw_gbs': tr.grads.numel * 4 / (ar * 1e-3) / 1e9 if ar > 0 else None, 'backend': 'nccl' if world > 1 else 'none (1 rank)'},
-           'host_ms_per_step_issue': [round(x, 1) for x in step_wall],
+           'wall_ms_each_step': [round(x, 1) for x in step_wall],
            'hbm_used_gb': round((torch.cuda.mem_get_info(dev)[1] - torch.cuda.mem_get_info(dev)[0]) / 2 ** 30, 1),
            'roofline': {'bound': 'tensor', 'kernel': 'generator convolutions: forward + data gradient (conv_umma_kernel) + weight gradient (wgrad_umma_kernel)', 'achieved': fl / (step_ms * 1e-3) / 1e12,
                         'peak': peak_burst, 'unit': 'TFLOP/s', 'frac': fl / (step_ms * 1e-3) / 1e12 / peak_burst, 'peak_source': peak_src,
