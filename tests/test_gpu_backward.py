@@ -126,6 +126,13 @@ def test_weight_gradient_tap_rows(name, monkeypatch):
     test_tensor_core_backward_units([u for u in TENSOR_UNITS if u[0] == name][0], monkeypatch)
 
 
+@pytest.mark.parametrize('name', ['t_c3_256_128', 't_c3_320_64'])
+def test_weight_gradient_wide_n_tiles(name, monkeypatch):
+    """V2V_WG_N256=1: 256-wide N tiles (one accumulator of 256 TMEM columns); measured neutral, off by default."""
+    monkeypatch.setenv('V2V_WG_N256', '1')
+    test_tensor_core_backward_units([u for u in TENSOR_UNITS if u[0] == name][0], monkeypatch)
+
+
 HEADS = [
     ('head_tanh', lambda: NW._stem(8, 16, BN), lambda: NW._head(16, 3, nn.Tanh()), 1.0, (1, 8, 12, 20)),
     ('head_flow_x20', lambda: NW._stem(8, 16, BN), lambda: NW._head(16, 2), 20.0, (1, 8, 12, 20)),

@@ -870,18 +870,18 @@ static int build_backward_units(v2v_plan* P, cudaStream_t stream) {
           w.taps[ky * c.kw + kx] = s2 ? WgradTap{(int8_t)(((ky & 1) << 1) | (kx & 1)), (int8_t)(ky >> 1), (int8_t)(kx >> 1), 0}
                                       : WgradTap{0, (int8_t)ky, (int8_t)kx, 0};
       V2V_REQUIRE(!s2 || a_in.parity, V2V_ERR_STATE, "internal: stride-2 weight gradient needs a parity-plane operand");
-      // Measured (profiles/r02i_wgrad_layers.txt): an MN-major MMA costs ~100 cycles whatever N <= 128 is (twice the K-major
-      // rate at N = 128), so this kernel is MMA-issue bound, not operand-traffic bound: the widest N per instruction wins.
-      //   * 256-wide N tiles when the N-side tensor has >= 256 channels (one accumulator of 256 TMEM columns);
-      //   * sharing one IN patch between the kw taps of a filter row (kxr = kw, V2V_WG_KX=1) saves operand traffic only and
-      //     measured neutral to slower (1024->1024: 98 -> 103 us; 7x7 with 64-wide tiles 1.9 -> 3.3 ms): off by default.
+      // Measured (profiles/r02i_wgrad_layers.txt): an MN-major MMA (M = 128, K = 16) costs ~100 cycles for any N <= 128 and ~200
+      // at N = 256 -- half the K-major rate -- so this kernel is MMA-issue bound, not operand-traffic bound.  Two variants that
+      // only save operand traffic are therefore opt-in experiments:
+      //   * V2V_WG_KX=1: the kw taps of a filter row share one IN patch (kxr = kw): 1024->1024 98 -> 103 us, narrow 7x7 unchanged;
+      //   * V2V_WG_N256=1: 256-wide N tiles: 1024->1024 98 -> 99 us.
       w.kxr = 1;
       {
         const char* ek = getenv("V2V_WG_KX");
         const bool kx_on = ek && ek[0] == '1';
         if (kx_on && u.mode == 1 && c.kw > 1 && kp + c.kw - 1 <= a_in.Wp && c.kw * std::max(32, w.BN) <= 512) w.kxr = c.kw;
         const char* e2 = getenv("V2V_WG_N256");
-        if (w.kxr == 1 && aB.C >= 256 && !(e2 && e2[0] == '0')) { w.BN = 256; w.Nblocks = 4; w.n_tiles = (aB.C + 255) / 256; }
+        if (w.kxr == 1 && aB.C >= 256 && e2 && e2[0] == '1') { w.BN = 256; w.Nblocks = 4; w.n_tiles = (aB.C + 255) / 256; }
       }
       const int stage_bytes = (int)wgrad_stage_smem_bytes(w);
       w.stages = std::max(2, std::min(6, kSmemBudget / stage_bytes));
