@@ -647,6 +647,8 @@ def main():
     if world > 1:
         import torch
         import torch.distributed as dist
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'          # (keeps NCCL's version banner off stdout: ONE JSON line)
         torch.cuda.set_device(local_rank)
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
     if WORKLOADS[args.workload].get('train'):

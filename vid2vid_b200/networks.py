@@ -13,6 +13,7 @@ tensor, as the reference does at inference because it never calls .eval() on G/D
 import copy
 import functools
 import os
+import sys
 
 import torch
 import torch.nn as nn
@@ -348,6 +349,8 @@ class _Planned(nn.Module):
         if ent is not None and ent['ptrs'] != ptrs:
             ent = None
         if ent is None:
+            if os.environ.get('V2V_LOG_PLANS'):
+                print('v2v: building plan %s for %s (cached: %d)' % (key, type(self).__name__, len(self._plans())), file=sys.stderr, flush=True)
             plan = Plan(device.index if device.index is not None else torch.cuda.current_device(),
                         precision=self._precision(), train=train)
             build(plan)
