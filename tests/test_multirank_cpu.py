@@ -40,9 +40,9 @@ def test_times_are_max_over_ranks_gloo():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = dict(q.get(timeout=120) for _ in range(world))
+    res = dict(q.get(timeout=300) for _ in range(world))
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=120)
         assert p.exitcode == 0
     assert res[0] == res[1] == [11.0, 20.0]
 
@@ -109,9 +109,9 @@ def test_flat_gradient_all_reduce_world2_gloo():
     procs = [ctx.Process(target=_flat_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=120)
     (r0, l0, a0, v0), (r1, l1, a1, v1) = res
     import torch
     assert torch.allclose(a0, (l0 + l1) / 2, atol=1e-7) and torch.equal(a0, a1)
