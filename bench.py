@@ -320,7 +320,7 @@ def run_ours(args, rank, world, local_rank):
         out['fast'] = line('fast')          # the bf16-operand mode, reported beside the fp32-class headline
     if world == 1 and not args.no_cpu_baseline:
         out['cpu_baseline'] = cpu_frames_per_s(args.workload, steps=1, warm=0, budget_s=25.0)
-    print(json.dumps(out))
+    emit(out)
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
@@ -414,8 +414,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     if WORKLOADS[args.workload].get('train') or WORKLOADS[args.workload].get('flownet'):
-        print(json.dumps({'impl': 'reference', 'unavailable': 'the CPU reference arm is defined for the headline inference workloads; '
-                          'the reference training step needs its CUDA-only FlowNet2 ops (see DESIGN.md)'}))
+        emit({'impl': 'reference', 'unavailable': 'the CPU reference arm is defined for the headline inference workloads; '
+                          'the reference training step needs its CUDA-only FlowNet2 ops (see DESIGN.md)'})
         return
     K, Wm = args.steps, args.warmup
     r = cpu_frames_per_s(args.workload, steps=K, warm=min(Wm, 1), budget_s=180.0)
@@ -428,7 +428,7 @@ def run_reference(args, rank, world):
            'config': {'workload': wl['desc'], 'parallelism': 'host CPU, rank 0 only'},
            'cpu_baseline': {k: r[k] for k in ('value', 'unit', 'cores', 'kind', 'sample')},
            'e2e': {'value': r['value'], 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 # ----------------------------------------------------------------------------------------------- training step (cfg3)
@@ -547,7 +547,7 @@ def run_train(args, rank, world, local_rank):
                         'traffic': None, 'note': 'whole-step time as denominator (includes the discriminators, FlowNet2, losses, optimizer); '
                         'algorithmic FLOPs: the precise mode issues 3 MMAs per algorithmic MAC'},
            'last_losses': losses}
-    print(json.dumps(out))
+    emit(out)
 
 
 # ----------------------------------------------------------------------------------------------- FlowNet2 (a14 / a15)
@@ -625,10 +625,29 @@ def run_flownet2(args, rank, world, local_rank):
                         'unit': 'TFLOP/s', 'frac': ach / peak_burst, 'peak_source': peak_src, 'mma_passes_per_k_block': 3,
                         'issued_tensor_tflops': 3 * ach, 'traffic': None, 'launches_per_pair': n_conv, 'conv_kernel_ms_per_pair': conv_ms,
                         'other_plan_kernels_ms_per_pair': other_ms}}
-    print(json.dumps(out))
+    emit(out)
+
+
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    """The ONE JSON line of the contract, on the process's real stdout."""
+    line = (json.dumps(obj) + '\n').encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(line.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, line)
 
 
 def main():
+    # Everything else that lands on stdout (NCCL prints its version banner there on these boxes, libraries may print notices)
+    # goes to stderr instead: file descriptor 1 is pointed at stderr for the duration of the run.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=30)

@@ -85,7 +85,8 @@ def _flat_worker(rank, world, port, q):
     loss.backward()
     local = fg.flat.clone()
     fg.all_reduce_mean(world)
-    q.put((rank, local, fg.flat.clone(), [p.grad.data_ptr() == fg.flat[o:].data_ptr() for p, o in
+    # (plain lists, not tensors: a tensor travels through the queue as a shared-memory handle that dies with this process)
+    q.put((rank, local.tolist(), fg.flat.clone().tolist(), [p.grad.data_ptr() == fg.flat[o:].data_ptr() for p, o in
                                           zip(list(g.parameters()) + list(d.parameters()), _offsets(list(g.parameters()) + list(d.parameters())))]))
     dist.destroy_process_group()
 
@@ -105,15 +106,15 @@ def test_flat_gradient_all_reduce_world2_gloo():
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 29731
+    port = _free_port()
     procs = [ctx.Process(target=_flat_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=120)
-    (r0, l0, a0, v0), (r1, l1, a1, v1) = res
     import torch
+    (r0, l0, a0, v0), (r1, l1, a1, v1) = [(r, torch.tensor(l), torch.tensor(a), v) for r, l, a, v in res]
     assert torch.allclose(a0, (l0 + l1) / 2, atol=1e-7) and torch.equal(a0, a1)
     assert all(v0) and all(v1)
     assert not torch.allclose(l0, l1)
