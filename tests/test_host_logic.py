@@ -238,3 +238,14 @@ def test_workspace_bytes_is_known_before_finalize():
             assert p.workspace_bytes == sizes[-1]                     # idempotent
     assert all(s > 0 and s % 1024 == 0 for s in sizes)
     assert sizes[1] > sizes[0] and sizes[3] > sizes[2] and sizes[2] > sizes[0]      # grows with the frame and with the precise mode
+
+
+def test_pending_losses_round_trip_on_cpu():
+    """trainer.PendingLosses: the stacked loss vector comes back as the per-dictionary Python floats (host logic; on CUDA the copy
+    is asynchronous and get() waits for its event only)."""
+    import torch
+    from vid2vid_b200.trainer import PendingLosses
+    keys = [(None, 'G_GAN'), (None, 'D_real'), (0, 'G_T_GAN'), (1, 'D_T_fake')]
+    p = PendingLosses(keys, torch.tensor([1.5, 2.5, 3.5, 4.5]), 2)
+    out, out_T = p.get()
+    assert out == {'G_GAN': 1.5, 'D_real': 2.5} and out_T == [{'G_T_GAN': 3.5}, {'D_T_fake': 4.5}]
