@@ -6,6 +6,7 @@ outside the hot path: `--no_vgg` is required, as in the or
 import torch
 import torch.nn as nn
 
+from .base_model import HostScheduleMixin
 from . import networks, ops
 
 
@@ -21,7 +22,7 @@ def _adam(params, **kw):
     return torch.optim.Adam(params, **kw)
 
 
-class Vid2VidModelD(nn.Module):
+class Vid2VidModelD(HostScheduleMixin, nn.Module):
     def name(self):
         return 'Vid2VidModelD'
 
@@ -134,6 +135,27 @@ class Vid2VidModelD(nn.Module):
             loss_G_GAN, loss_G_GAN_Feat = loss_G_GAN + r[2], loss_G_GAN_Feat + r[3]
         return [t.reshape(-1, 1) for t in (loss_G_VGG, loss_G_GAN, loss_G_GAN_Feat, loss_D_real, loss_D_fake, loss_G_Warp,
                                             loss_F_Flow, loss_F_Warp, loss_W)]
+
+    def save(self, label):
+        """vid2vid_model_D.py:266-272 (no face discriminator here)."""
+        self.save_network(self.netD, 'D', label, self.gpu_ids)
+        for s in range(self.opt.n_scales_temporal):
+            self.save_network(getattr(self, 'netD_T' + str(s)), 'D_T' + str(s), label, self.gpu_ids)
+
+    def get_all_skipped_frames(self, frames_all, real_B, fake_B, flow_ref, conf_ref, t_scales, tD, n_frames_load, i, flowNet):
+        """vid2vid_model_D.py:232-247: the temporally sub-sampled real / fake / flow groups of every temporal scale (dense form;
+        --sparse_D is not implemented)."""
+        from .trainer import get_skipped_flows, get_skipped_frames
+        if getattr(self.opt, 'sparse_D', False):
+            raise NotImplementedError('--sparse_D is out of scope (DESIGN.md section 9)')
+        real_B_all, fake_B_all, flow_ref_all, conf_ref_all = frames_all
+        real_sk = fake_sk = flow_sk = conf_sk = None
+        if t_scales > 0:
+            real_B_all, real_sk = get_skipped_frames(real_B_all, real_B, t_scales, tD)
+            fake_B_all, fake_sk = get_skipped_frames(fake_B_all, fake_B, t_scales, tD)
+            flow_ref_all, conf_ref_all, flow_sk, conf_sk = get_skipped_flows(flowNet, flow_ref_all, conf_ref_all, real_sk, flow_ref, conf_ref,
+                                                                              t_scales, tD)
+        return (real_B_all, fake_B_all, flow_ref_all, conf_ref_all), (real_sk, fake_sk, flow_sk, conf_sk)
 
     def get_losses(self, loss_dict, loss_dict_T, t_scales):
         """vid2vid_model_D.py:243-259."""

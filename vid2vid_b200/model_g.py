@@ -10,6 +10,7 @@ import os
 import torch
 import torch.nn as nn
 
+from .base_model import HostScheduleMixin
 from . import networks, ops
 
 
@@ -25,7 +26,7 @@ def _adam(params, **kw):
     return torch.optim.Adam(params, **kw)
 
 
-class Vid2VidModelG(nn.Module):
+class Vid2VidModelG(HostScheduleMixin, nn.Module):
     def name(self):
         return 'Vid2VidModelG'
 
@@ -229,7 +230,9 @@ class Vid2VidModelG(nn.Module):
     def init_train(self):
         """The training half of vid2vid_model_G.py:19-84: per-GPU frame budget and the generator optimizer."""
         opt = self.opt
-        self.n_frames_load = min(getattr(opt, 'max_frames_per_gpu', 1), opt.n_frames_total - opt.n_frames_G + 1)
+        self.n_gpus = 1                                                    # one process per GPU (vid2vid_model_G.py:57-61 with n_gpus_gen = 1)
+        self.n_frames_per_gpu = min(getattr(opt, 'max_frames_per_gpu', 1), opt.n_frames_total - opt.n_frames_G + 1)
+        self.n_frames_load = self.n_gpus * self.n_frames_per_gpu
         self.n_frames_bp = min(getattr(opt, 'max_frames_backpropagate', 1), self.n_frames_load)
         self.finetune_all = True                                           # niter_fix_global == 0 (:66-68)
         params = []
@@ -289,6 +292,11 @@ class Vid2VidModelG(nn.Module):
                     if flow is not None:
                         flows, weights = cat(flows, flow.unsqueeze(1)), cat(weights, weight.unsqueeze(1))
         return fake_B_pyr, fake_Bs_raw, flows, weights
+
+    def save(self, label):
+        """vid2vid_model_G.py:338-340."""
+        for s in range(self.n_scales):
+            self.save_network(getattr(self, 'netG' + str(s)), 'G' + str(s), label, self.gpu_ids)
 
     def compute_fake_B_prev(self, real_B_prev, fake_B_last, fake_B):
         """vid2vid_model_G.py:332-336."""
