@@ -249,3 +249,19 @@ def test_pending_losses_round_trip_on_cpu():
     p = PendingLosses(keys, torch.tensor([1.5, 2.5, 3.5, 4.5]), 2)
     out, out_T = p.get()
     assert out == {'G_GAN': 1.5, 'D_real': 2.5} and out_T == [{'G_T_GAN': 3.5}, {'D_T_fake': 4.5}]
+
+
+def test_bench_prints_exactly_one_json_line_on_stdout():
+    """The driver parses bench.py's stdout: whatever libraries print there (NCCL's version banner on the GPU boxes) is routed to
+    stderr, the JSON line goes to the real stdout."""
+    import json
+    import subprocess
+    import sys
+    code = ("import os, sys; sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'cfg3']; import bench; "
+            "bench.main.__globals__['run_reference'] = (lambda a, r, w: (os.write(1, b'noise on fd 1\\n'), print('noise via print'), "
+            "bench.emit({'impl': 'reference', 'ok': 1}))); bench.main()")
+    r = subprocess.run([sys.executable, '-c', code], cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    lines = r.stdout.splitlines()
+    assert len(lines) == 1 and json.loads(lines[0]) == {'impl': 'reference', 'ok': 1}
+    assert 'noise on fd 1' in r.stderr and 'noise via print' in r.stderr
